@@ -1,0 +1,90 @@
+// c_api.cu -- extern "C" entry points of libfreesplat_b200.so (see include/freesplat_b200.h).
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace fs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return FS_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return FS_ERR_CUDA;
+}
+
+}  // namespace fs
+
+using namespace fs;
+
+extern "C" {
+
+int fs_abi_version(void) { return FS_ABI_VERSION; }
+const char* fs_last_error(void) { return g_err; }
+
+int fs_device_sm_count(void) {
+  int dev = 0, n = 0;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  if (int rc = check_cuda(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
+  return n;
+}
+
+#define FS_REQUIRE(cond, msg)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      set_error("invalid argument: %s", msg); \
+      return FS_ERR_INVALID_ARG;         \
+    }                                    \
+  } while (0)
+
+int fs_raster_forward(const FsRasterFwdArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr, "args is NULL");
+  FS_REQUIRE(a->P >= 0 && a->V >= 1 && a->V <= 65535 && a->H >= 1 && a->W >= 1, "bad sizes");
+  FS_REQUIRE((a->shs != nullptr) != (a->colors_precomp != nullptr), "provide exactly one of shs / colors_precomp");
+  FS_REQUIRE((a->cov3D_precomp != nullptr) != (a->scales != nullptr && a->rotations != nullptr),
+             "provide exactly one of cov3D_precomp / (scales, rotations)");
+  FS_REQUIRE(a->sh_degree >= 0 && a->sh_degree <= 3, "sh_degree must be 0..3");
+  FS_REQUIRE(a->shs == nullptr || ((a->sh_degree + 1) * (a->sh_degree + 1) <= a->M && a->M <= 16), "M too small for sh_degree (or > 16)");
+  FS_REQUIRE(a->capacity >= 0 && a->capacity <= 0xffffffffll, "capacity out of range");
+  FS_REQUIRE(a->views && a->out_color && a->out_depth && a->final_T && a->n_contrib && a->radii && a->rec && a->cov3D &&
+                 a->tiles_touched && a->clamped && a->tile_count && a->tile_cursor && a->ranges && a->status,
+             "NULL buffer");
+  FS_REQUIRE(a->P == 0 || (a->means3D && a->opacities), "NULL input");
+  FS_REQUIRE(a->capacity == 0 || (a->keybuf && a->point_list), "NULL key buffers");
+  FS_REQUIRE((long long)tiles_x(a->W) * tiles_y(a->H) * a->V < (1ll << 31), "too many tiles");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = launch_preprocess(*a, s))) return rc;
+  if ((rc = launch_binning(*a, s))) return rc;
+  if ((rc = launch_render_fwd(*a, s))) return rc;
+  return FS_OK;
+}
+
+int fs_raster_backward(const FsRasterBwdArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr, "args is NULL");
+  FS_REQUIRE(a->P >= 0 && a->V >= 1 && a->V <= 65535 && a->H >= 1 && a->W >= 1, "bad sizes");
+  FS_REQUIRE(a->views && a->rec && a->cov3D && a->radii && a->clamped && a->ranges && a->final_T && a->n_contrib &&
+                 a->status && a->dL_dcolor && a->dL_dscreen && a->dL_dmeans2D && a->dL_dmeans3D && a->dL_dopacities,
+             "NULL buffer");
+  FS_REQUIRE(!a->has_depth_grad || a->dL_ddepth, "has_depth_grad set but dL_ddepth is NULL");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = launch_render_bwd(*a, s))) return rc;
+  if ((rc = launch_preprocess_bwd(*a, s))) return rc;
+  return FS_OK;
+}
+
+int fs_mark_visible(int32_t P, const float* means3D, const float* view, uint8_t* visible, void* stream) {
+  FS_REQUIRE(P >= 0 && (P == 0 || (means3D && view && visible)), "bad arguments");
+  return launch_mark_visible(P, means3D, view, visible, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

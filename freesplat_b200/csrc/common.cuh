@@ -1,0 +1,31 @@
+// common.cuh -- shared declarations of the sm_100a kernels behind the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/freesplat_b200.h"
+
+namespace fs {
+
+constexpr int kThreads = 256;
+constexpr int kViewFloats = FS_VIEW_FLOATS;
+constexpr int kRecFloats = FS_REC_FLOATS;
+// keys sorted in shared memory by one block (64-bit keys); larger tiles sort in global memory.
+constexpr int kSortSmemKeys = 4096;
+
+// error plumbing (thread-local message, see c_api.cu)
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+// launchers (each returns FsStatus)
+int launch_preprocess(const FsRasterFwdArgs& a, cudaStream_t s);     // raster_pre.cu
+int launch_binning(const FsRasterFwdArgs& a, cudaStream_t s);        // raster_bin.cu
+int launch_render_fwd(const FsRasterFwdArgs& a, cudaStream_t s);     // raster_render.cu
+int launch_render_bwd(const FsRasterBwdArgs& a, cudaStream_t s);     // raster_render.cu
+int launch_preprocess_bwd(const FsRasterBwdArgs& a, cudaStream_t s); // raster_pre.cu
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* vis, cudaStream_t s);
+
+__host__ __device__ inline int tiles_x(int W) { return (W + FS_TILE - 1) / FS_TILE; }
+__host__ __device__ inline int tiles_y(int H) { return (H + FS_TILE - 1) / FS_TILE; }
+
+}  // namespace fs

@@ -1,0 +1,325 @@
+// raster_pre.cu -- per-Gaussian stages of the rasterizer (sm_100a).
+//   preprocess_kernel       : SURVEY §8a R1  (upstream forward.cu::preprocessCUDA) + per-tile counting
+//   preprocess_bwd_kernel   : SURVEY §8a R8+R9 (upstream backward.cu::computeCov2DCUDA, preprocessCUDA)
+//   mark_visible_kernel     : upstream rasterizer_impl.cu::checkFrustum
+// Compiled with -fmad=false: the only fused operations are the explicit fmaf()
+// calls of raster_math.cuh, which makes radius / tile-rect / depth-key decisions
+// bit-identical to the CPU oracle (oracle/raster_oracle.c).
+//
+// HBM-bound streaming kernels: one thread per (view, Gaussian), 256-thread blocks,
+// grid = ceil(P/256) x V.  Algorithmic bytes per Gaussian and view:
+//   read 12 (mean) + 24 (cov6) + 4 (opacity) + 12*M (SH)  = 148 B at M=9
+//   write 48 (record) + 24 (cov used) + 4 (radius) + 4 (tiles) + 1 (clamp) = 81 B
+#include "common.cuh"
+#include "raster_math.cuh"
+
+namespace fs {
+
+__global__ void __launch_bounds__(kThreads) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  const int v = blockIdx.y;
+  if (i >= a.P) return;
+  const size_t vi = (size_t)v * a.P + i;
+  const float* __restrict__ view = a.views + (size_t)v * kViewFloats;
+  const float* __restrict__ proj = view + 16;
+  const float tanx = view[38], tany = view[39], sscale = view[40];
+
+  float mean[3];
+  mean[0] = __ldg(a.means3D + 3 * (size_t)i + 0) * sscale;
+  mean[1] = __ldg(a.means3D + 3 * (size_t)i + 1) * sscale;
+  mean[2] = __ldg(a.means3D + 3 * (size_t)i + 2) * sscale;
+  float c6[6];
+  if (a.cov3D_precomp) {
+    const float2* cp = reinterpret_cast<const float2*>(a.cov3D_precomp + 6 * (size_t)i);
+    const float2 c01 = __ldg(cp), c23 = __ldg(cp + 1), c45 = __ldg(cp + 2);
+    c6[0] = c01.x; c6[1] = c01.y; c6[2] = c23.x; c6[3] = c23.y; c6[4] = c45.x; c6[5] = c45.y;
+  } else {
+    float s[3] = {__ldg(a.scales + 3 * (size_t)i), __ldg(a.scales + 3 * (size_t)i + 1), __ldg(a.scales + 3 * (size_t)i + 2)};
+    float q[4] = {__ldg(a.rotations + 4 * (size_t)i), __ldg(a.rotations + 4 * (size_t)i + 1),
+                  __ldg(a.rotations + 4 * (size_t)i + 2), __ldg(a.rotations + 4 * (size_t)i + 3)};
+    fsm::cov3d_from_scale_rot(s, a.scale_modifier, q, c6);
+  }
+  const float s2 = sscale * sscale;
+#pragma unroll
+  for (int k = 0; k < 6; k++) c6[k] = c6[k] * s2;
+
+  const fsm::Projected pr = fsm::project_gaussian(mean, c6, view, proj, tanx, tany, a.H, a.W);
+
+  float4* __restrict__ rec = reinterpret_cast<float4*>(a.rec) + 3 * vi;
+  float2* __restrict__ covo = reinterpret_cast<float2*>(a.cov3D + 6 * vi);
+  covo[0] = make_float2(c6[0], c6[1]); covo[1] = make_float2(c6[2], c6[3]); covo[2] = make_float2(c6[4], c6[5]);
+
+  if (pr.radius == 0) {
+    a.radii[vi] = 0; a.tiles_touched[vi] = 0; a.clamped[vi] = 0;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec[0] = z; rec[1] = z; rec[2] = make_float4(0.f, 0.f, -3.0e38f, -3.0e38f);
+    return;
+  }
+  float rgb[3];
+  int clampmask = 0;
+  if (a.colors_precomp) {
+    rgb[0] = __ldg(a.colors_precomp + 3 * (size_t)i); rgb[1] = __ldg(a.colors_precomp + 3 * (size_t)i + 1);
+    rgb[2] = __ldg(a.colors_precomp + 3 * (size_t)i + 2);
+  } else {
+    float sh[48];
+    const int nf = ((a.sh_degree + 1) * (a.sh_degree + 1)) * 3;   // only the active coefficients are read
+    const float* shp = a.shs + (size_t)i * a.M * 3;
+#pragma unroll
+    for (int k = 0; k < 48; k++) sh[k] = (k < nf) ? __ldg(shp + k) : 0.f;
+    clampmask = fsm::sh_to_rgb(a.sh_degree, mean, view + 32, sh, rgb);
+  }
+  const float opacity = __ldg(a.opacities + i);
+  float hx, hy;
+  fsm::alpha_extent(pr.con_x, pr.con_y, pr.con_z, opacity, &hx, &hy);
+  if (hx < 0.f) { hx = -3.0e38f; hy = -3.0e38f; }
+  rec[0] = make_float4(pr.px, pr.py, pr.con_x, pr.con_y);
+  rec[1] = make_float4(pr.con_z, opacity, rgb[0], rgb[1]);
+  rec[2] = make_float4(rgb[2], pr.depth, hx, hy);
+  a.radii[vi] = pr.radius;
+  a.tiles_touched[vi] = (uint32_t)((pr.x1 - pr.x0) * (pr.y1 - pr.y0));
+  a.clamped[vi] = (uint8_t)clampmask;
+  // per-tile population count (tile ranges come from a scan over these counters)
+  uint32_t* __restrict__ cnt = a.tile_count + (size_t)v * gx * gy;
+  for (int ty = pr.y0; ty < pr.y1; ty++)
+    for (int tx = pr.x0; tx < pr.x1; tx++) atomicAdd(cnt + ty * gx + tx, 1u);
+}
+
+__global__ void __launch_bounds__(kThreads) mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                                                const float* __restrict__ view,
+                                                                uint8_t* __restrict__ vis) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= P) return;
+  const float s = view[40];
+  const float z = fsm::dot4row(view, 2, means3D[3 * (size_t)i] * s, means3D[3 * (size_t)i + 1] * s,
+                               means3D[3 * (size_t)i + 2] * s);
+  vis[i] = z > 0.2f ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward of the per-Gaussian stages.  One thread per Gaussian loops over the V views, so the
+// sums over views are deterministic and need no atomics.
+__global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArgs a) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= a.P) return;
+  const int H = a.H, W = a.W;
+  float g_mean[3] = {0.f, 0.f, 0.f}, g_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, g_op = 0.f, g_col[3] = {0.f, 0.f, 0.f};
+  const int nsh = a.M * 3;
+  bool sh_written = false;
+  const float m0 = a.means3D[3 * (size_t)i], m1 = a.means3D[3 * (size_t)i + 1], m2 = a.means3D[3 * (size_t)i + 2];
+
+  for (int v = 0; v < a.V; v++) {
+    const size_t vi = (size_t)v * a.P + i;
+    float* g2d = a.dL_dmeans2D + 3 * vi;
+    if (!(a.radii[vi] > 0)) { g2d[0] = 0.f; g2d[1] = 0.f; g2d[2] = 0.f; continue; }
+    const float* __restrict__ view = a.views + (size_t)v * kViewFloats;
+    const float* __restrict__ pm = view + 16;
+    const float tanx = view[38], tany = view[39], ss = view[40];
+    const float fx = (float)W / (2.0f * tanx), fy = (float)H / (2.0f * tany);
+    const float4* gs = reinterpret_cast<const float4*>(a.dL_dscreen + 12 * vi);
+    const float4 ga = gs[0], gb = gs[1], gc = gs[2];
+    // ga = (mean2D.x, mean2D.y, conic.x, conic.y)  gb = (conic.w, opacity, r, g)  gc = (b, depth, -, -)
+    g2d[0] = ga.x; g2d[1] = ga.y; g2d[2] = 0.f;
+    g_op += gb.y;
+    const float mean[3] = {m0 * ss, m1 * ss, m2 * ss};
+    const float* c6 = a.cov3D + 6 * vi;
+    const float pvx = fsm::dot4row(view, 0, mean[0], mean[1], mean[2]);
+    const float pvy = fsm::dot4row(view, 1, mean[0], mean[1], mean[2]);
+    const float pvz = fsm::dot4row(view, 2, mean[0], mean[1], mean[2]);
+    const fsm::Cov2D cv = fsm::cov2d(pvx, pvy, pvz, fx, fy, tanx, tany, c6, view);
+    const float xg = cv.clampx ? 0.f : 1.f, yg = cv.clampy ? 0.f : 1.f;
+    const float ca = cv.a, cb = cv.b, cc = cv.c;
+    const float gxx = ga.z, gxy = ga.w, gyy = gb.x;
+    const float denom = ca * cc - cb * cb;
+    const float d2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+    const float* A3 = cv.Ta; const float* B3 = cv.Tb;
+    float gcv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (d2inv != 0.f) {
+      dL_da = d2inv * (-cc * cc * gxx + 2.f * cb * cc * gxy + (denom - ca * cc) * gyy);
+      dL_dc = d2inv * (-ca * ca * gyy + 2.f * ca * cb * gxy + (denom - ca * cc) * gxx);
+      dL_db = d2inv * 2.f * (cb * cc * gxx - (denom + 2.f * cb * cb) * gxy + ca * cb * gyy);
+      gcv[0] = A3[0] * A3[0] * dL_da + A3[0] * B3[0] * dL_db + B3[0] * B3[0] * dL_dc;
+      gcv[3] = A3[1] * A3[1] * dL_da + A3[1] * B3[1] * dL_db + B3[1] * B3[1] * dL_dc;
+      gcv[5] = A3[2] * A3[2] * dL_da + A3[2] * B3[2] * dL_db + B3[2] * B3[2] * dL_dc;
+      gcv[1] = 2.f * A3[0] * A3[1] * dL_da + (A3[0] * B3[1] + A3[1] * B3[0]) * dL_db + 2.f * B3[0] * B3[1] * dL_dc;
+      gcv[2] = 2.f * A3[0] * A3[2] * dL_da + (A3[0] * B3[2] + A3[2] * B3[0]) * dL_db + 2.f * B3[0] * B3[2] * dL_dc;
+      gcv[4] = 2.f * A3[2] * A3[1] * dL_da + (A3[1] * B3[2] + A3[2] * B3[1]) * dL_db + 2.f * B3[1] * B3[2] * dL_dc;
+    }
+    const float s2 = ss * ss;
+#pragma unroll
+    for (int k = 0; k < 6; k++) g_cov[k] += gcv[k] * s2;
+    const float S[9] = {c6[0], c6[1], c6[2], c6[1], c6[3], c6[4], c6[2], c6[4], c6[5]};
+    float Sa[3], Sb[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      Sa[k] = S[3 * k] * A3[0] + S[3 * k + 1] * A3[1] + S[3 * k + 2] * A3[2];
+      Sb[k] = S[3 * k] * B3[0] + S[3 * k + 1] * B3[1] + S[3 * k + 2] * B3[2];
+    }
+    float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float dTa = 2.f * Sa[k] * dL_da + Sb[k] * dL_db;
+      const float dTb = 2.f * Sb[k] * dL_dc + Sa[k] * dL_db;
+      const float R0 = view[k * 4 + 0], R1 = view[k * 4 + 1], R2 = view[k * 4 + 2];
+      dJ00 += R0 * dTa; dJ02 += R2 * dTa; dJ11 += R1 * dTb; dJ12 += R2 * dTb;
+    }
+    const float tz = 1.f / cv.tz, tz2 = tz * tz, tz3 = tz2 * tz;
+    const float dtx = xg * -fx * tz2 * dJ02;
+    const float dty = yg * -fy * tz2 * dJ12;
+    const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2.f * fx * cv.tx) * tz3 * dJ02 + (2.f * fy * cv.ty) * tz3 * dJ12;
+    float dm[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) dm[k] = view[4 * k] * dtx + view[4 * k + 1] * dty + view[4 * k + 2] * dtz;
+    if (a.has_depth_grad) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) dm[k] += view[4 * k + 2] * gc.y;
+    }
+    // projection term (screen-space mean gradient)
+    const float phx = fsm::dot4row(pm, 0, mean[0], mean[1], mean[2]);
+    const float phy = fsm::dot4row(pm, 1, mean[0], mean[1], mean[2]);
+    const float phw = fsm::dot4row(pm, 3, mean[0], mean[1], mean[2]);
+    const float mw = 1.0f / (phw + 0.0000001f);
+    const float mul1 = phx * mw * mw, mul2 = phy * mw * mw;
+    dm[0] += (pm[0] * mw - pm[3] * mul1) * ga.x + (pm[1] * mw - pm[3] * mul2) * ga.y;
+    dm[1] += (pm[4] * mw - pm[7] * mul1) * ga.x + (pm[5] * mw - pm[7] * mul2) * ga.y;
+    dm[2] += (pm[8] * mw - pm[11] * mul1) * ga.x + (pm[9] * mw - pm[11] * mul2) * ga.y;
+
+    const float grgb[3] = {gb.z, gb.w, gc.x};
+    if (a.colors_precomp) {
+      g_col[0] += grgb[0]; g_col[1] += grgb[1]; g_col[2] += grgb[2];
+    } else if (a.shs && a.dL_dshs) {
+      const float* campos = view + 32;
+      const float dox = mean[0] - campos[0], doy = mean[1] - campos[1], doz = mean[2] - campos[2];
+      const float sum2 = dox * dox + doy * doy + doz * doz;
+      const float len = sqrtf(sum2);
+      const float x = dox / len, y = doy / len, z = doz / len;
+      const float* sh = a.shs + (size_t)i * nsh;
+      float* gsh = a.dL_dshs + (size_t)i * nsh;
+      const uint8_t cm = a.clamped[vi];
+      const int D = a.sh_degree;
+      float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+      float basis[16];
+      basis[0] = fsm::kShC0;
+      if (D > 0) {
+        basis[1] = -fsm::kShC1 * y; basis[2] = fsm::kShC1 * z; basis[3] = -fsm::kShC1 * x;
+        if (D > 1) {
+          const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+          basis[4] = fsm::kShC2_0 * xy; basis[5] = fsm::kShC2_1 * yz; basis[6] = fsm::kShC2_2 * (2.f * zz - xx - yy);
+          basis[7] = fsm::kShC2_3 * xz; basis[8] = fsm::kShC2_4 * (xx - yy);
+          if (D > 2) {
+            basis[9] = fsm::kShC3_0 * y * (3.f * xx - yy); basis[10] = fsm::kShC3_1 * xy * z;
+            basis[11] = fsm::kShC3_2 * y * (4.f * zz - xx - yy); basis[12] = fsm::kShC3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+            basis[13] = fsm::kShC3_4 * x * (4.f * zz - xx - yy); basis[14] = fsm::kShC3_5 * z * (xx - yy);
+            basis[15] = fsm::kShC3_6 * x * (xx - 3.f * yy);
+          }
+        }
+      }
+      const int nb = (D + 1) * (D + 1);
+      for (int ch = 0; ch < 3; ch++) {
+        const float g = ((cm >> ch) & 1) ? 0.f : grgb[ch];
+        for (int k = 0; k < a.M; k++) {
+          const float val = (k < nb) ? basis[k] * g : 0.f;
+          if (sh_written) gsh[k * 3 + ch] += val; else gsh[k * 3 + ch] = val;
+        }
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+#define SHV(k) sh[(k) * 3 + ch]
+        if (D > 0) {
+          rx = -fsm::kShC1 * SHV(3); ry = -fsm::kShC1 * SHV(1); rz = fsm::kShC1 * SHV(2);
+          if (D > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            rx += fsm::kShC2_0 * y * SHV(4) + fsm::kShC2_2 * 2.f * -x * SHV(6) + fsm::kShC2_3 * z * SHV(7) + fsm::kShC2_4 * 2.f * x * SHV(8);
+            ry += fsm::kShC2_0 * x * SHV(4) + fsm::kShC2_1 * z * SHV(5) + fsm::kShC2_2 * 2.f * -y * SHV(6) + fsm::kShC2_4 * 2.f * -y * SHV(8);
+            rz += fsm::kShC2_1 * y * SHV(5) + fsm::kShC2_2 * 2.f * 2.f * z * SHV(6) + fsm::kShC2_3 * x * SHV(7);
+            if (D > 2) {
+              rx += fsm::kShC3_0 * SHV(9) * 3.f * 2.f * xy + fsm::kShC3_1 * SHV(10) * yz + fsm::kShC3_2 * SHV(11) * -2.f * xy +
+                    fsm::kShC3_3 * SHV(12) * -3.f * 2.f * xz + fsm::kShC3_4 * SHV(13) * (-3.f * xx + 4.f * zz - yy) +
+                    fsm::kShC3_5 * SHV(14) * 2.f * xz + fsm::kShC3_6 * SHV(15) * 3.f * (xx - yy);
+              ry += fsm::kShC3_0 * SHV(9) * 3.f * (xx - yy) + fsm::kShC3_1 * SHV(10) * xz + fsm::kShC3_2 * SHV(11) * (-3.f * yy + 4.f * zz - xx) +
+                    fsm::kShC3_3 * SHV(12) * -3.f * 2.f * yz + fsm::kShC3_4 * SHV(13) * -2.f * xy + fsm::kShC3_5 * SHV(14) * -2.f * yz +
+                    fsm::kShC3_6 * SHV(15) * -3.f * 2.f * xy;
+              rz += fsm::kShC3_1 * SHV(10) * xy + fsm::kShC3_2 * SHV(11) * 4.f * 2.f * yz + fsm::kShC3_3 * SHV(12) * 3.f * (2.f * zz - xx - yy) +
+                    fsm::kShC3_4 * SHV(13) * 4.f * 2.f * xz + fsm::kShC3_5 * SHV(14) * (xx - yy);
+            }
+          }
+        }
+#undef SHV
+        ddx += rx * g; ddy += ry * g; ddz += rz * g;
+      }
+      sh_written = true;
+      const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+      dm[0] += ((sum2 - dox * dox) * ddx - doy * dox * ddy - doz * dox * ddz) * inv32;
+      dm[1] += (-dox * doy * ddx + (sum2 - doy * doy) * ddy - doz * doy * ddz) * inv32;
+      dm[2] += (-dox * doz * ddx - doy * doz * ddy + (sum2 - doz * doz) * ddz) * inv32;
+    }
+    g_mean[0] += dm[0] * ss; g_mean[1] += dm[1] * ss; g_mean[2] += dm[2] * ss;
+  }
+  if (a.shs && a.dL_dshs && !sh_written) {
+    float* gsh = a.dL_dshs + (size_t)i * nsh;
+    for (int k = 0; k < nsh; k++) gsh[k] = 0.f;
+  }
+  a.dL_dmeans3D[3 * (size_t)i] = g_mean[0]; a.dL_dmeans3D[3 * (size_t)i + 1] = g_mean[1]; a.dL_dmeans3D[3 * (size_t)i + 2] = g_mean[2];
+  a.dL_dopacities[i] = g_op;
+  if (a.dL_dcolors) { a.dL_dcolors[3 * (size_t)i] = g_col[0]; a.dL_dcolors[3 * (size_t)i + 1] = g_col[1]; a.dL_dcolors[3 * (size_t)i + 2] = g_col[2]; }
+  if (a.dL_dcov3D) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)i + k] = g_cov[k];
+  }
+  if (a.scales && a.rotations && a.dL_dscales && a.dL_drotations) {
+    const float* q = a.rotations + 4 * (size_t)i;
+    const float* s = a.scales + 3 * (size_t)i;
+    const float r = q[0], x = q[1], y = q[2], z = q[3];
+    const float Rm[9] = {1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                         2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                         2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)};
+    const float mod = a.scale_modifier;
+    const float sv[3] = {mod * s[0], mod * s[1], mod * s[2]};
+    const float G[9] = {g_cov[0], 0.5f * g_cov[1], 0.5f * g_cov[2], 0.5f * g_cov[1], g_cov[3], 0.5f * g_cov[4],
+                        0.5f * g_cov[2], 0.5f * g_cov[4], g_cov[5]};
+    float dR[9];
+    float gsc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int aa = 0; aa < 3; aa++)
+#pragma unroll
+      for (int bb = 0; bb < 3; bb++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) acc += G[3 * aa + k] * (Rm[3 * k + bb] * sv[bb]);
+        const float dM = 2.f * acc;
+        gsc[bb] += Rm[3 * aa + bb] * dM;
+        dR[3 * aa + bb] = dM * sv[bb];
+      }
+    a.dL_dscales[3 * (size_t)i] = mod * gsc[0]; a.dL_dscales[3 * (size_t)i + 1] = mod * gsc[1]; a.dL_dscales[3 * (size_t)i + 2] = mod * gsc[2];
+    a.dL_drotations[4 * (size_t)i + 0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+    a.dL_drotations[4 * (size_t)i + 1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
+    a.dL_drotations[4 * (size_t)i + 2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
+    a.dL_drotations[4 * (size_t)i + 3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+  }
+}
+
+int launch_preprocess(const FsRasterFwdArgs& a, cudaStream_t s) {
+  const int gx = tiles_x(a.W), gy = tiles_y(a.H);
+  const size_t nt = (size_t)a.V * gx * gy;
+  int rc;
+  if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, nt * 4, s), "memset tile_count"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(a.tile_cursor, 0, nt * 4, s), "memset tile_cursor"))) return rc;
+  if (a.P > 0) {
+    dim3 grid((a.P + kThreads - 1) / kThreads, a.V);
+    preprocess_kernel<<<grid, kThreads, 0, s>>>(a, gx, gy);
+    if ((rc = check_cuda(cudaGetLastError(), "preprocess_kernel"))) return rc;
+  }
+  return FS_OK;
+}
+
+int launch_preprocess_bwd(const FsRasterBwdArgs& a, cudaStream_t s) {
+  if (a.P <= 0) return FS_OK;
+  preprocess_bwd_kernel<<<(a.P + kThreads - 1) / kThreads, kThreads, 0, s>>>(a);
+  return check_cuda(cudaGetLastError(), "preprocess_bwd_kernel");
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* vis, cudaStream_t s) {
+  if (P <= 0) return FS_OK;
+  mark_visible_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, s>>>(P, means3D, view, vis);
+  return check_cuda(cudaGetLastError(), "mark_visible_kernel");
+}
+
+}  // namespace fs

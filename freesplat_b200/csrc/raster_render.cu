@@ -1,0 +1,312 @@
+// raster_render.cu -- per-tile alpha blending and its gradient (SURVEY §8a R6, R7;
+// upstream forward.cu::renderCUDA / backward.cu::renderCUDA, with the depth channel of
+// the `-w-depth` fork: D += z*alpha*T).
+//
+// One CTA = one 16x16 tile of one view (grid = tiles x V), 8 warps; warp w owns an 8x4-pixel
+// sub-tile.  Per batch of 256 sorted instances the CTA stages the 48-byte projected records
+// (three coalesced 16-byte loads per instance, gathered by `point_list`) in shared memory;
+// every warp then tests 32 records at a time against its sub-tile with one ballot (the
+// record's conservative alpha>=1/255 extent, see raster_math.cuh::alpha_extent) and only
+// walks the set bits, front to back.  All 32 lanes of a warp process the SAME instance
+// (shared-memory broadcast reads), so the backward pass reduces the nine per-Gaussian
+// partial derivatives with a butterfly of warp shuffles before touching memory.
+//
+// Per pixel and instance the arithmetic is the canonical order of oracle/raster_oracle.c:
+//   t = fma(cb, dy, ca*dx) ; power = fma(cc*dy, dy, t*dx) ; alpha = min(.99, o*exp(power)).
+// exp() is MUFU.EX2 (ex2.approx.ftz) of power*log2(e): |rel err| < 1e-6.
+#include "common.cuh"
+
+namespace fs {
+
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(kThreads) render_fwd_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
+    const float* __restrict__ views, const uint32_t* __restrict__ status, int P, int H, int W, int gx, int ntiles,
+    float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
+    uint32_t* __restrict__ n_contrib) {
+  if (status[2]) return;
+  __shared__ float4 sA[kThreads], sB[kThreads], sC[kThreads];
+  const int tile = blockIdx.x, v = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile_x = tile % gx, tile_y = tile / gx;
+  const int x0 = tile_x * 16 + (warp & 1) * 8, y0 = tile_y * 16 + (warp >> 1) * 4;
+  const int px = x0 + (lane & 7), py = y0 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float pxf = (float)px, pyf = (float)py;
+  const float fx0 = (float)x0, fx1 = (float)(x0 + 7), fy0 = (float)y0, fy1 = (float)(y0 + 3);
+  const uint2 range = ranges[(size_t)v * ntiles + tile];
+  const float4* __restrict__ rec_v = rec + (size_t)v * P * 3;
+
+  float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+  uint32_t last = 0;
+  bool done = !inside;
+
+  for (uint32_t base = range.x; base < range.y; base += kThreads) {
+    if (__syncthreads_count(done) == kThreads) break;   // barrier also protects the smem reuse
+    const int n = min((int)kThreads, (int)(range.y - base));
+    if (tid < n) {
+      const uint32_t id = point_list[base + tid];
+      const float4* r = rec_v + 3 * (size_t)id;
+      sA[tid] = __ldg(r); sB[tid] = __ldg(r + 1); sC[tid] = __ldg(r + 2);
+    }
+    __syncthreads();
+    if (__all_sync(kFull, done)) continue;
+    for (int g = 0; g < n; g += 32) {
+      const int j = g + lane;
+      bool hit = false;
+      if (j < n) {
+        const float4 a = sA[j];
+        const float4 c = sC[j];
+        hit = (a.x - c.z <= fx1) && (a.x + c.z >= fx0) && (a.y - c.w <= fy1) && (a.y + c.w >= fy0);
+      }
+      unsigned m = __ballot_sync(kFull, hit);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const int jj = g + b;
+        const float4 a = sA[jj], bb = sB[jj], c = sC[jj];
+        if (!done) {
+          const float dx = a.x - pxf, dy = a.y - pyf;
+          const float ca = -0.5f * a.z, cb = -a.w, cc = -0.5f * bb.x;
+          const float t = fmaf(cb, dy, ca * dx);
+          const float power = fmaf(cc * dy, dy, t * dx);
+          if (power <= 0.f) {
+            const float alpha = fminf(0.99f, bb.y * fast_exp(power));
+            if (alpha >= 1.f / 255.f) {
+              const float test_T = T * (1.f - alpha);
+              if (test_T < 0.0001f) {
+                done = true;
+              } else {
+                const float w = alpha * T;
+                C0 = fmaf(bb.z, w, C0); C1 = fmaf(bb.w, w, C1); C2 = fmaf(c.x, w, C2);
+                Dp = fmaf(c.y, w, Dp);
+                T = test_T;
+                last = (base - range.x) + (uint32_t)jj + 1u;
+              }
+            }
+          }
+        }
+      }
+      if (__all_sync(kFull, done)) break;
+    }
+  }
+  if (inside) {
+    const float* bg = views + (size_t)v * kViewFloats + 35;
+    const size_t HW = (size_t)H * W, pix = (size_t)py * W + px;
+    float* oc = out_color + (size_t)v * 3 * HW;
+    oc[pix] = fmaf(T, bg[0], C0);
+    oc[HW + pix] = fmaf(T, bg[1], C1);
+    oc[2 * HW + pix] = fmaf(T, bg[2], C2);
+    out_depth[(size_t)v * HW + pix] = Dp;
+    final_T[(size_t)v * HW + pix] = T;
+    n_contrib[(size_t)v * HW + pix] = last;
+  }
+}
+
+// ------------------------------------------------------------------------------- backward
+// Butterfly reduction of 8 per-lane values across the warp: 9 shuffles instead of 40.
+// On return lane L holds, in r, the warp-wide sum of value number (L >> 2) (all 4 lanes of a
+// quad hold the same total).
+__device__ __forceinline__ float warp_reduce8(float v0, float v1, float v2, float v3, float v4, float v5, float v6,
+                                              float v7, int lane) {
+  // step 1 (xor 16): keep 4 of 8
+  const bool hi16 = lane & 16;
+  float a0 = hi16 ? v4 : v0, a1 = hi16 ? v5 : v1, a2 = hi16 ? v6 : v2, a3 = hi16 ? v7 : v3;
+  float s0 = hi16 ? v0 : v4, s1 = hi16 ? v1 : v5, s2 = hi16 ? v2 : v6, s3 = hi16 ? v3 : v7;
+  a0 += __shfl_xor_sync(kFull, s0, 16); a1 += __shfl_xor_sync(kFull, s1, 16);
+  a2 += __shfl_xor_sync(kFull, s2, 16); a3 += __shfl_xor_sync(kFull, s3, 16);
+  // step 2 (xor 8): keep 2 of 4
+  const bool hi8 = lane & 8;
+  float b0 = hi8 ? a2 : a0, b1 = hi8 ? a3 : a1;
+  float t0 = hi8 ? a0 : a2, t1 = hi8 ? a1 : a3;
+  b0 += __shfl_xor_sync(kFull, t0, 8); b1 += __shfl_xor_sync(kFull, t1, 8);
+  // step 3 (xor 4): keep 1 of 2
+  const bool hi4 = lane & 4;
+  float c0 = hi4 ? b1 : b0;
+  const float u0 = hi4 ? b0 : b1;
+  c0 += __shfl_xor_sync(kFull, u0, 4);
+  // steps 4,5: finish within the quad
+  c0 += __shfl_xor_sync(kFull, c0, 2);
+  c0 += __shfl_xor_sync(kFull, c0, 1);
+  return c0;   // value index = (bit4?4:0) + (bit3?2:0) + (bit2?1:0)
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// smem accumulators per staged instance: 10 floats (mean2D.xy, conic.xyw, opacity, rgb, depth),
+// padded to 11 to spread banks.
+constexpr int kAccStride = 11;
+
+template <bool kDepthGrad>
+__global__ void __launch_bounds__(kThreads) render_bwd_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
+    const float* __restrict__ views, const uint32_t* __restrict__ status, int P, int H, int W, int gx, int ntiles,
+    const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
+    const float* __restrict__ dL_ddepth, float* __restrict__ dL_dscreen) {
+  if (status[2]) return;
+  __shared__ float4 sA[kThreads], sB[kThreads], sC[kThreads];
+  __shared__ uint32_t sId[kThreads];
+  __shared__ float sAcc[kThreads * kAccStride];
+  const int tile = blockIdx.x, v = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile_x = tile % gx, tile_y = tile / gx;
+  const int x0 = tile_x * 16 + (warp & 1) * 8, y0 = tile_y * 16 + (warp >> 1) * 4;
+  const int px = x0 + (lane & 7), py = y0 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float pxf = (float)px, pyf = (float)py;
+  const float fx0 = (float)x0, fx1 = (float)(x0 + 7), fy0 = (float)y0, fy1 = (float)(y0 + 3);
+  const uint2 range = ranges[(size_t)v * ntiles + tile];
+  const int total = (int)(range.y - range.x);
+  if (total <= 0) return;
+  const float4* __restrict__ rec_v = rec + (size_t)v * P * 3;
+  const size_t HW = (size_t)H * W, pix = (size_t)py * W + px;
+  const float* bg = views + (size_t)v * kViewFloats + 35;
+
+  const float T_final = inside ? final_T[(size_t)v * HW + pix] : 0.f;
+  float T = T_final;
+  const int last = inside ? (int)n_contrib[(size_t)v * HW + pix] : 0;
+  float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f, dLd = 0.f;
+  if (inside) {
+    const float* g = dL_dcolor + (size_t)v * 3 * HW;
+    dLp0 = g[pix]; dLp1 = g[HW + pix]; dLp2 = g[2 * HW + pix];
+    if (kDepthGrad) dLd = dL_ddepth[(size_t)v * HW + pix];
+  }
+  const float bg_dot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f, last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;
+  const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
+  // highest list position (1-based) any pixel of this warp contributed to
+  const int warp_last = __reduce_max_sync(kFull, last);
+
+  // walk the tile's list back to front in batches of 256 (batch 0 holds the LAST instances)
+  for (int done_cnt = 0; done_cnt < total; done_cnt += kThreads) {
+    const int n = min((int)kThreads, total - done_cnt);
+    // staged slot k (0..n-1) holds list position pos = total-1-done_cnt-k  (0-based, front=0)
+    __syncthreads();
+    if (tid < n) {
+      const uint32_t id = point_list[range.x + (uint32_t)(total - 1 - done_cnt - tid)];
+      const float4* r = rec_v + 3 * (size_t)id;
+      sA[tid] = __ldg(r); sB[tid] = __ldg(r + 1); sC[tid] = __ldg(r + 2);
+      sId[tid] = id;
+    }
+#pragma unroll
+    for (int k = 0; k < kAccStride; k++) sAcc[tid * kAccStride + k] = 0.f;
+    __syncthreads();
+    const int pos_hi = total - 1 - done_cnt;          // list position of slot 0
+    if (pos_hi - (n - 1) < warp_last) {               // some slot in this batch can matter to this warp
+      for (int g = 0; g < n; g += 32) {
+        const int j = g + lane;
+        bool hit = false;
+        if (j < n) {
+          const float4 a = sA[j];
+          const float4 c = sC[j];
+          hit = (a.x - c.z <= fx1) && (a.x + c.z >= fx0) && (a.y - c.w <= fy1) && (a.y + c.w >= fy0) &&
+                (pos_hi - j < warp_last);
+        }
+        unsigned m = __ballot_sync(kFull, hit);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const int jj = g + b;
+          const int pos = pos_hi - jj;                // 0-based list position; contributor index = pos+1
+          const float4 a = sA[jj], bb = sB[jj], c = sC[jj];
+          float g_mx = 0.f, g_my = 0.f, g_cx = 0.f, g_cy = 0.f, g_cw = 0.f, g_op = 0.f, g_r = 0.f, g_g = 0.f, g_b = 0.f, g_d = 0.f;
+          if (pos < last) {
+            const float dx = a.x - pxf, dy = a.y - pyf;
+            const float ca = -0.5f * a.z, cb = -a.w, cc = -0.5f * bb.x;
+            const float t = fmaf(cb, dy, ca * dx);
+            const float power = fmaf(cc * dy, dy, t * dx);
+            if (power <= 0.f) {
+              const float G = fast_exp(power);
+              const float alpha = fminf(0.99f, bb.y * G);
+              if (alpha >= 1.f / 255.f) {
+                T = T / (1.f - alpha);
+                const float w = alpha * T;
+                float dL_dalpha;
+                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = bb.z;
+                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = bb.w;
+                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = c.x;
+                dL_dalpha = (bb.z - acc0) * dLp0 + (bb.w - acc1) * dLp1 + (c.x - acc2) * dLp2;
+                g_r = w * dLp0; g_g = w * dLp1; g_b = w * dLp2;
+                if (kDepthGrad) {
+                  accd = last_alpha * ld + (1.f - last_alpha) * accd; ld = c.y;
+                  dL_dalpha += (c.y - accd) * dLd;
+                  g_d = w * dLd;
+                }
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                const float dL_dG = bb.y * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                g_mx = dL_dG * (-gdx * a.z - gdy * a.w) * ddelx_dx;
+                g_my = dL_dG * (-gdy * bb.x - gdx * a.w) * ddely_dy;
+                g_cx = -0.5f * gdx * dx * dL_dG;
+                g_cy = -0.5f * gdx * dy * dL_dG;
+                g_cw = -0.5f * gdy * dy * dL_dG;
+                g_op = G * dL_dalpha;
+              }
+            }
+          }
+          const float r8 = warp_reduce8(g_mx, g_my, g_cx, g_cy, g_cw, g_op, g_r, g_g, lane);
+          const float rb = warp_sum(g_b);
+          float* accp = sAcc + jj * kAccStride;
+          if ((lane & 3) == 0) atomicAdd(accp + (lane >> 2), r8);
+          if (lane == 1) atomicAdd(accp + 8, rb);
+          if (kDepthGrad) {
+            const float rd = warp_sum(g_d);
+            if (lane == 2) atomicAdd(accp + 9, rd);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < n) {
+      const float* accp = sAcc + tid * kAccStride;
+      float* dst = dL_dscreen + ((size_t)v * P + sId[tid]) * 12;
+      // layout: mean2D.x, mean2D.y, conic.x, conic.y | conic.w, opacity, r, g | b, depth
+#pragma unroll
+      for (int k = 0; k < (kDepthGrad ? 10 : 9); k++) {
+        const float val = accp[k];
+        if (val != 0.f) atomicAdd(dst + k, val);
+      }
+    }
+  }
+}
+
+int launch_render_fwd(const FsRasterFwdArgs& a, cudaStream_t s) {
+  const int gx = tiles_x(a.W), gy = tiles_y(a.H);
+  dim3 grid(gx * gy, a.V);
+  render_fwd_kernel<<<grid, kThreads, 0, s>>>(reinterpret_cast<const uint2*>(a.ranges), a.point_list,
+                                               reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P, a.H, a.W, gx,
+                                               gx * gy, a.out_color, a.out_depth, a.final_T, a.n_contrib);
+  return check_cuda(cudaGetLastError(), "render_fwd_kernel");
+}
+
+int launch_render_bwd(const FsRasterBwdArgs& a, cudaStream_t s) {
+  const int gx = tiles_x(a.W), gy = tiles_y(a.H);
+  int rc;
+  if ((rc = check_cuda(cudaMemsetAsync(a.dL_dscreen, 0, (size_t)a.V * a.P * 12 * sizeof(float), s), "memset dL_dscreen"))) return rc;
+  dim3 grid(gx * gy, a.V);
+  if (a.has_depth_grad && a.dL_ddepth)
+    render_bwd_kernel<true><<<grid, kThreads, 0, s>>>(reinterpret_cast<const uint2*>(a.ranges), a.point_list,
+                                                       reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P, a.H, a.W,
+                                                       gx, gx * gy, a.final_T, a.n_contrib, a.dL_dcolor, a.dL_ddepth, a.dL_dscreen);
+  else
+    render_bwd_kernel<false><<<grid, kThreads, 0, s>>>(reinterpret_cast<const uint2*>(a.ranges), a.point_list,
+                                                        reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P, a.H, a.W,
+                                                        gx, gx * gy, a.final_T, a.n_contrib, a.dL_dcolor, a.dL_ddepth, a.dL_dscreen);
+  return check_cuda(cudaGetLastError(), "render_bwd_kernel");
+}
+
+}  // namespace fs

@@ -1,0 +1,144 @@
+/*
+ * freesplat_b200.h -- C ABI of libfreesplat_b200.so (sm_100a).
+ *
+ * Drop-in boundary for FreeSplat's data-parallel hot path.
+ * Plain pointers and sizes only: every pointer below is a DEVICE pointer unless
+ * its name ends in _host; `stream` is a cudaStream_t passed as void*.  The
+ * library allocates nothing on the hot path: the caller (PyTorch's caching
+ * allocator in freesplat_b200/*.py) owns all buffers.  Every entry point returns
+ * 0 on success or a negative FsStatus; no C++ exception crosses the boundary.
+ *
+ * What each entry point replaces in the reference:
+ *   fs_raster_forward / fs_raster_backward / fs_mark_visible
+ *       -> the pybind `_C.rasterize_gaussians`, `_C.rasterize_gaussians_backward`,
+ *          `_C.mark_visible` of the third-party module imported at
+ *          /root/reference/src/model/decoder/cuda_splatting.py:5-8 and called at
+ *          :114-127 (module source un-vendored, requirements.txt:17).
+ *   fs_cost_volume_forward / fs_cost_volume_backward
+ *       -> AVGFeatureVolumeManager.build_cost_volume,
+ *          /root/reference/src/model/encoder/modules/cost_volume.py:429-619
+ *          (called at src/model/encoder/encoder_freesplat.py:280-288).
+ *   fs_ptf_*  -> the index/merge part of EncoderFreeSplat.fuse_gaussians,
+ *          /root/reference/src/model/encoder/encoder_freesplat.py:431-522.
+ */
+#ifndef FREESPLAT_B200_H_
+#define FREESPLAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS_ABI_VERSION 1
+#define FS_TILE 16            /* BLOCK_X == BLOCK_Y == 16 (upstream config.h) */
+#define FS_VIEW_FLOATS 48     /* floats per FsView record                     */
+#define FS_REC_FLOATS 12      /* floats per projected-Gaussian record         */
+
+typedef enum FsStatus {
+  FS_OK = 0,
+  FS_ERR_INVALID_ARG = -1,
+  FS_ERR_CUDA = -2,        /* a CUDA runtime call failed: see fs_last_error() */
+  FS_ERR_UNSUPPORTED = -3
+} FsStatus;
+
+/* Per-view camera record, FS_VIEW_FLOATS floats, device memory.
+ *  [0:16)  viewmatrix  (world->camera, flat, TRANSPOSED as the reference passes it,
+ *                       cuda_splatting.py:85-87:  m[c*4+r] = M[r][c])
+ *  [16:32) projmatrix  (full projection P*V, same flat convention)
+ *  [32:35) campos      [35:38) bg colour
+ *  [38] tanfovx  [39] tanfovy
+ *  [40] scene_scale: means are multiplied by it and covariances by its square before
+ *       projection (the `scale_invariant` rescale of cuda_splatting.py:64-71 folded into
+ *       preprocess; 1.0 for the plain drop-in op)
+ *  [41:48) reserved (0)                                                            */
+
+/* Projected-Gaussian record written by preprocess, FS_REC_FLOATS floats
+ * (three float4 so the tile kernels fetch it with 3 coalesced 16-byte loads):
+ *  [0] x  [1] y (pixel)   [2] conic.x  [3] conic.y
+ *  [4] conic.z  [5] opacity  [6] r  [7] g
+ *  [8] b  [9] depth (p_view.z)  [10] hx  [11] hy
+ * hx,hy: conservative half-extent (pixels) of the region where alpha >= 1/255 can
+ * hold; used only to skip work that the reference's per-pixel test would reject. */
+
+/* ------------------------------------------------------------------ raster */
+typedef struct FsRasterFwdArgs {
+  /* sizes */
+  int32_t P;             /* Gaussians                                            */
+  int32_t V;             /* views rendered by this call (1 for the drop-in op)   */
+  int32_t H, W;          /* image size                                           */
+  int32_t sh_degree;     /* active SH degree D (0..3)                            */
+  int32_t M;             /* SH coefficients per channel in `shs` (0 if colours)  */
+  float scale_modifier;
+  int32_t prefiltered;   /* accepted for API parity; unused (as upstream)        */
+  int64_t capacity;      /* tile-instance capacity of keybuf / point_list        */
+  /* inputs */
+  const float* means3D;        /* [P,3]                                          */
+  const float* shs;            /* [P,M,3] or NULL                                */
+  const float* colors_precomp; /* [P,3]  or NULL                                 */
+  const float* opacities;      /* [P]                                            */
+  const float* scales;         /* [P,3]  or NULL                                 */
+  const float* rotations;      /* [P,4]  or NULL  (r,x,y,z)                      */
+  const float* cov3D_precomp;  /* [P,6]  or NULL  (xx,xy,xz,yy,yz,zz)            */
+  const float* views;          /* [V,FS_VIEW_FLOATS]                             */
+  /* outputs */
+  float* out_color;      /* [V,3,H,W]                                            */
+  float* out_depth;      /* [V,H,W]   sum_j z_j alpha_j T_j (un-normalised)      */
+  float* final_T;        /* [V,H,W]   transmittance (4th return = 1-final_T)     */
+  uint32_t* n_contrib;   /* [V,H,W]                                              */
+  int32_t* radii;        /* [V,P]                                                */
+  /* state kept for backward / parity checks */
+  float* rec;            /* [V,P,FS_REC_FLOATS]                                  */
+  float* cov3D;          /* [V,P,6] covariance actually used (scaled)            */
+  uint32_t* tiles_touched; /* [V,P]                                              */
+  uint8_t* clamped;      /* [V,P] bit c set <=> SH colour channel c clamped at 0 */
+  uint32_t* tile_count;  /* [V*tiles]   scratch (zeroed by the call)             */
+  uint32_t* tile_cursor; /* [V*tiles]   scratch (zeroed by the call)             */
+  uint32_t* ranges;      /* [V*tiles,2] absolute [start,end) into point_list     */
+  uint64_t* keybuf;      /* [capacity]  (depth_bits<<32 | gaussian) per instance,
+                            sorted ascending inside each tile range on return    */
+  uint32_t* point_list;  /* [capacity]  Gaussian index per sorted instance       */
+  uint32_t* status;      /* [4] {R_lo, R_hi, overflow(R>capacity), reserved}     */
+} FsRasterFwdArgs;
+
+typedef struct FsRasterBwdArgs {
+  int32_t P, V, H, W, sh_degree, M;
+  float scale_modifier;
+  int32_t has_depth_grad;      /* 0: dL_ddepth ignored (reference behaviour)     */
+  const float* means3D; const float* shs; const float* colors_precomp;
+  const float* opacities; const float* scales; const float* rotations;
+  const float* views;
+  /* forward state */
+  const float* rec; const float* cov3D; const int32_t* radii; const uint8_t* clamped;
+  const uint32_t* ranges; const uint32_t* point_list;
+  const float* final_T; const uint32_t* n_contrib; const uint32_t* status;
+  /* upstream gradients */
+  const float* dL_dcolor;      /* [V,3,H,W]                                      */
+  const float* dL_ddepth;      /* [V,H,W] or NULL                                */
+  /* scratch: per-(view,Gaussian) screen-space gradients, zeroed by the call     */
+  float* dL_dscreen;           /* [V,P,12]: mean2D.xy, conic.xyw, opacity, rgb, depth, pad */
+  /* outputs (summed over the V views)                                           */
+  float* dL_dmeans2D;          /* [V,P,3]  (x,y,0) per view, as upstream returns  */
+  float* dL_dmeans3D;          /* [P,3]                                          */
+  float* dL_dcov3D;            /* [P,6]  or NULL when scales/rotations are used  */
+  float* dL_dshs;              /* [P,M,3] or NULL                                */
+  float* dL_dcolors;           /* [P,3]  or NULL                                 */
+  float* dL_dopacities;        /* [P]                                            */
+  float* dL_dscales;           /* [P,3]  or NULL                                 */
+  float* dL_drotations;        /* [P,4]  or NULL                                 */
+} FsRasterBwdArgs;
+
+int fs_abi_version(void);
+const char* fs_last_error(void);      /* thread-local, valid until the next call  */
+int fs_device_sm_count(void);         /* negative FsStatus on failure             */
+
+int fs_raster_forward(const FsRasterFwdArgs* args, void* stream);
+int fs_raster_backward(const FsRasterBwdArgs* args, void* stream);
+/* visible[i] = (p_view.z > 0.2) for one view (upstream mark_visible / checkFrustum) */
+int fs_mark_visible(int32_t P, const float* means3D, const float* view /*FS_VIEW_FLOATS*/,
+                    uint8_t* visible, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FREESPLAT_B200_H_ */

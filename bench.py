@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py -- rendered views/s @ 640x480 of the B200 rasterizer hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the CPU restatement of the reference path
+
+Workload (BASELINE config 2, "ScanNet 2-views 640x480, ~300k Gaussians, forward raster only"):
+one scene of 307 200 pixel-aligned Gaussians (SH degree 2, precomputed covariances) rendered into
+T=3 target views (assets/evaluation_index_scannet_2views.json holds 3 targets per scene) at 640x480.
+A step = one pass of the hot path over that batch: preprocess -> tile binning -> render, all views.
+
+value  : views/s with the scene and camera records resident in HBM (CUDA events, per-step, L2 flushed
+         between steps by writing a 256 MiB buffer outside the timed events).
+e2e    : the same metric through the public call a user makes (`freesplat_b200.decoder.render_views`)
+         starting from PINNED HOST tensors: H2D of Gaussians + cameras, render, D2H of colour + depth.
+Multi-GPU: target views shard over ranks (each rank renders its own T views of the replicated
+Gaussian set; no data-path collective) -> weak scaling; value = all views / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, P, T_VIEWS = 480, 640, 307200, 3
+WORKLOAD = f"scannet_2views_{W}x{H}_P{P}_targets{T_VIEWS}_raster_fwd"
+METRIC = "rendered views/sec @640x480"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_scene(rank: int):
+    from freesplat_b200 import synth
+    sc = synth.pixel_aligned_scene(seed=0, h=H, w=W, n_context=2, n_target=T_VIEWS, keep=P)
+    if rank:
+        # view sharding: rank r renders a different set of target cameras of the same Gaussians
+        sc.extrinsics = synth.camera_path(T_VIEWS, spacing=0.08, t0=0.37 + 0.11 * rank)
+    return sc
+
+
+def cpu_reference_views_per_s(sc, n_views: int, repeats: int):
+    """Times the CPU restatement of the reference rasterizer (oracle/raster_oracle.c, all host cores)."""
+    from oracle import raster as oracle
+    from tests.helpers import view_inputs
+    inps = [view_inputs(sc, v)[0] for v in range(n_views)]
+    oracle.forward(**inps[0])  # warm (page in, OpenMP pool)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        for inp in inps:
+            oracle.forward(**inp)
+    dt = time.perf_counter() - t0
+    return n_views * repeats / dt, oracle.num_threads(), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc = make_scene(0)
+    from oracle import raster as oracle
+    from tests.helpers import view_inputs
+    inps = [view_inputs(sc, v)[0] for v in range(T_VIEWS)]
+    for _ in range(max(args.warmup, 1)):
+        oracle.forward(**inps[0])
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        for inp in inps:           # one step = the same T views of the same scene
+            oracle.forward(**inp)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    val = T_VIEWS * args.steps / total
+    cores = oracle.num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "views/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference's (CUDA-only, un-vendored) "
+                   "rasterizer: oracle/raster_oracle.c, OpenMP; the reference has no CPU implementation"},
+        "cpu_baseline": {"value": val, "unit": "views/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {T_VIEWS} views of the full workload"},
+        "e2e": {"value": val, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from freesplat_b200 import decoder, rasterizer
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    sc_cpu = make_scene(rank)
+    sc = sc_cpu.to(dev)
+    V = T_VIEWS
+    bg = torch.zeros((V, 3), device=dev)
+    row, col = torch.triu_indices(3, 3)
+    shs = sc.harmonics.transpose(1, 2).contiguous()
+    cov6 = sc.covariances[:, row, col].contiguous()
+    views, _ = decoder.camera_records(sc.extrinsics, sc.intrinsics, sc.near, sc.far, bg, True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(stage_events=None, check="deferred"):
+        return rasterizer.raster_forward_raw(sc.means, sc.opacities, views, H, W, shs=shs, cov3D_precomp=cov6,
+                                             sh_degree=2, check_overflow=check, stage_events=stage_events)
+
+    st = step(check="sync")          # sizes the workspace (R is only known on the device)
+    R = st.num_rendered()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing: per-step CUDA events, L2 flushed between steps -----------------
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        st = step(stage_events=ev[k])
+    barrier()
+    clocks = sampler.stop()
+    assert not st.overflowed()
+    step_ms = [e[0].elapsed_time(e[3]) for e in ev]
+    render_ms = [e[2].elapsed_time(e[3]) for e in ev]
+    pre_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    bin_ms = [e[1].elapsed_time(e[2]) for e in ev]
+    total_ms = sum(step_ms)
+
+    # ---- end to end from pinned host memory through the public API ------------------------------
+    pin = lambda t: t.contiguous().pin_memory()
+    h = dict(ext=pin(sc_cpu.extrinsics), K=pin(sc_cpu.intrinsics), near=pin(sc_cpu.near), far=pin(sc_cpu.far),
+             means=pin(sc_cpu.means), cov=pin(sc_cpu.covariances), sh=pin(sc_cpu.harmonics), op=pin(sc_cpu.opacities))
+    out_c = torch.empty((V, 3, H, W), dtype=torch.float32).pin_memory()
+    out_d = torch.empty((V, H, W), dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in h.values())
+    d2h = out_c.numel() * 4 + out_d.numel() * 4
+
+    def e2e_step():
+        d = {k: t.to(dev, non_blocking=True) for k, t in h.items()}
+        with torch.no_grad():
+            c, dp = decoder.render_views(d["ext"], d["K"], d["near"], d["far"], (H, W), bg, d["means"], d["cov"], d["sh"], d["op"])
+        out_c.copy_(c, non_blocking=True); out_d.copy_(dp, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        e0[k].record(); e2e_step(); e1[k].record()
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
+
+    # ---- max over ranks -------------------------------------------------------------------------
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peak, peak_src = _peaks()
+        HW = H * W
+        alg_bytes = 44.0 * R + 24.0 * HW * V          # render fwd = 44 R + 24 HW per view
+        rd = sum(render_ms) / len(render_ms)
+        achieved = alg_bytes / (rd * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * V * args.steps / (total_ms * 1e-3), "unit": "views/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "views_per_step_per_gpu": V, "gaussians": P, "tile_instances_R": R,
+                       "l2": "flushed between steps (256 MiB write)", "parallelism": f"view-sharded x{world}"},
+            "e2e": {"value": world * V * args.steps / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": 5 * args.steps,
+            "stage_ms": {"preprocess": sum(pre_ms) / len(pre_ms), "binning": sum(bin_ms) / len(bin_ms), "render": rd},
+            "roofline": {"kernel": "render_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "render is FP32/SFU-issue bound at this size (SURVEY §7), reported against HBM as BASELINE asks"},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            v, cores, dt = cpu_reference_views_per_s(sc_cpu, n_views=T_VIEWS, repeats=2)
+            line["cpu_baseline"] = {"value": v, "unit": "views/s", "cores": cores, "kind": "port",
+                                    "sample": f"2 x {T_VIEWS} views of the full workload ({dt:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,9 +62,10 @@ int fs_raster_forward(const FsRasterFwdArgs* a, void* stream) {
   FS_REQUIRE((long long)tiles_x(a->W) * tiles_y(a->H) * a->V < (1ll << 31), "too many tiles");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int rc;
-  if ((rc = launch_preprocess(*a, s))) return rc;
-  if ((rc = launch_binning(*a, s))) return rc;
-  if ((rc = launch_render_fwd(*a, s))) return rc;
+  const int stages = a->stages ? a->stages : (FS_STAGE_PREPROCESS | FS_STAGE_BINNING | FS_STAGE_RENDER);
+  if ((stages & FS_STAGE_PREPROCESS) && (rc = launch_preprocess(*a, s))) return rc;
+  if ((stages & FS_STAGE_BINNING) && (rc = launch_binning(*a, s))) return rc;
+  if ((stages & FS_STAGE_RENDER) && (rc = launch_render_fwd(*a, s))) return rc;
   return FS_OK;
 }
 

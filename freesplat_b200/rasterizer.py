@@ -95,7 +95,8 @@ def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
 
 def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_precomp=None, scales=None,
                        rotations=None, cov3D_precomp=None, sh_degree=0, scale_modifier=1.0, prefiltered=False,
-                       capacity: Optional[int] = None, check_overflow: str = "sync") -> RasterState:
+                       capacity: Optional[int] = None, check_overflow: str = "sync",
+                       stage_events=None) -> RasterState:
     """One launch sequence for V views (views: [V,48]).  Returns the RasterState.
 
     check_overflow: "sync"     read the device status word after enqueueing everything; re-run once
@@ -136,14 +137,22 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
             st.status = e(4, dtype=torch.int32)
             a = FsRasterFwdArgs(
                 P=P, V=V, H=H, W=W, sh_degree=sh_degree, M=M, scale_modifier=scale_modifier,
-                prefiltered=int(prefiltered), capacity=capacity,
+                prefiltered=int(prefiltered), stages=0, capacity=capacity,
                 means3D=ptr(means3D), shs=ptr(shs), colors_precomp=ptr(colors_precomp), opacities=ptr(opacities),
                 scales=ptr(scales), rotations=ptr(rotations), cov3D_precomp=ptr(cov3D_precomp), views=ptr(views),
                 out_color=ptr(st.color), out_depth=ptr(st.depth), final_T=ptr(st.final_T), n_contrib=ptr(st.n_contrib),
                 radii=ptr(st.radii), rec=ptr(st.rec), cov3D=ptr(st.cov3D), tiles_touched=ptr(st.tiles_touched),
                 clamped=ptr(st.clamped), tile_count=ptr(tile_count), tile_cursor=ptr(tile_cursor),
                 ranges=ptr(st.ranges), keybuf=ptr(st.keybuf), point_list=ptr(st.point_list), status=ptr(st.status))
-            check(L.fs_raster_forward(C.byref(a), C.c_void_p(stream)), "fs_raster_forward")
+            if stage_events is None:
+                check(L.fs_raster_forward(C.byref(a), C.c_void_p(stream)), "fs_raster_forward")
+            else:
+                # stage_events: list of 4 torch.cuda.Event recorded around preprocess | binning | render
+                for k, bit in enumerate((1, 2, 4)):
+                    stage_events[k].record()
+                    a.stages = bit
+                    check(L.fs_raster_forward(C.byref(a), C.c_void_p(stream)), "fs_raster_forward")
+                stage_events[3].record()
             if check_overflow != "sync":
                 return st
             s = st.status.cpu()

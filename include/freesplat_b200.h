@@ -71,6 +71,8 @@ typedef struct FsRasterFwdArgs {
   int32_t M;             /* SH coefficients per channel in `shs` (0 if colours)  */
   float scale_modifier;
   int32_t prefiltered;   /* accepted for API parity; unused (as upstream)        */
+  int32_t stages;        /* bit mask of FS_STAGE_*; 0 means all.  Lets the caller put
+                            CUDA events between stages (bench.py roofline timing)   */
   int64_t capacity;      /* tile-instance capacity of keybuf / point_list        */
   /* inputs */
   const float* means3D;        /* [P,3]                                          */
@@ -100,6 +102,10 @@ typedef struct FsRasterFwdArgs {
   uint32_t* point_list;  /* [capacity]  Gaussian index per sorted instance       */
   uint32_t* status;      /* [4] {R_lo, R_hi, overflow(R>capacity), reserved}     */
 } FsRasterFwdArgs;
+
+#define FS_STAGE_PREPROCESS 1  /* per-Gaussian projection + tile counting            */
+#define FS_STAGE_BINNING 2     /* tile scan, scatter, per-tile sort                  */
+#define FS_STAGE_RENDER 4      /* per-tile alpha blend                               */
 
 typedef struct FsRasterBwdArgs {
   int32_t P, V, H, W, sh_degree, M;

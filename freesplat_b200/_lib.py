@@ -35,8 +35,8 @@ class FsRasterBwdArgs(C.Structure):
         ("sh_degree", C.c_int32), ("M", C.c_int32), ("scale_modifier", C.c_float),
         ("has_depth_grad", C.c_int32),
         ("means3D", vp), ("shs", vp), ("colors_precomp", vp), ("opacities", vp),
-        ("scales", vp), ("rotations", vp), ("views", vp),
-        ("rec", vp), ("cov3D", vp), ("radii", vp), ("clamped", vp), ("ranges", vp),
+        ("scales", vp), ("rotations", vp), ("cov3D_precomp", vp), ("views", vp),
+        ("rec", vp), ("radii", vp), ("clamped", vp), ("ranges", vp),
         ("point_list", vp), ("final_T", vp), ("n_contrib", vp), ("status", vp),
         ("dL_dcolor", vp), ("dL_ddepth", vp), ("dL_dscreen", vp),
         ("dL_dmeans2D", vp), ("dL_dmeans3D", vp), ("dL_dcov3D", vp), ("dL_dshs", vp),

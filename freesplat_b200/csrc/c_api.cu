@@ -54,8 +54,7 @@ int fs_raster_forward(const FsRasterFwdArgs* a, void* stream) {
   FS_REQUIRE(a->sh_degree >= 0 && a->sh_degree <= 3, "sh_degree must be 0..3");
   FS_REQUIRE(a->shs == nullptr || ((a->sh_degree + 1) * (a->sh_degree + 1) <= a->M && a->M <= 16), "M too small for sh_degree (or > 16)");
   FS_REQUIRE(a->capacity >= 0 && a->capacity <= 0xffffffffll, "capacity out of range");
-  FS_REQUIRE(a->views && a->out_color && a->out_depth && a->final_T && a->n_contrib && a->radii && a->rec && a->cov3D &&
-                 a->tiles_touched && a->clamped && a->tile_count && a->tile_cursor && a->ranges && a->status,
+  FS_REQUIRE(a->views && a->out_color && a->out_depth && a->final_T && a->n_contrib && a->radii && a->rec && a->clamped && a->tile_count && a->tile_cursor && a->ranges && a->status,
              "NULL buffer");
   FS_REQUIRE(a->P == 0 || (a->means3D && a->opacities), "NULL input");
   FS_REQUIRE(a->capacity == 0 || (a->keybuf && a->point_list), "NULL key buffers");
@@ -72,7 +71,9 @@ int fs_raster_forward(const FsRasterFwdArgs* a, void* stream) {
 int fs_raster_backward(const FsRasterBwdArgs* a, void* stream) {
   FS_REQUIRE(a != nullptr, "args is NULL");
   FS_REQUIRE(a->P >= 0 && a->V >= 1 && a->V <= 65535 && a->H >= 1 && a->W >= 1, "bad sizes");
-  FS_REQUIRE(a->views && a->rec && a->cov3D && a->radii && a->clamped && a->ranges && a->final_T && a->n_contrib &&
+  FS_REQUIRE((a->cov3D_precomp != nullptr) != (a->scales != nullptr && a->rotations != nullptr),
+             "provide exactly one of cov3D_precomp / (scales, rotations)");
+  FS_REQUIRE(a->views && a->rec && a->radii && a->clamped && a->ranges && a->final_T && a->n_contrib &&
                  a->status && a->dL_dcolor && a->dL_dscreen && a->dL_dmeans2D && a->dL_dmeans3D && a->dL_dopacities,
              "NULL buffer");
   FS_REQUIRE(!a->has_depth_grad || a->dL_ddepth, "has_depth_grad set but dL_ddepth is NULL");

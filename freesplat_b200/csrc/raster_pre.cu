@@ -15,73 +15,102 @@
 
 namespace fs {
 
-__global__ void __launch_bounds__(kThreads) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy) {
-  const int i = blockIdx.x * kThreads + threadIdx.x;
-  const int v = blockIdx.y;
-  if (i >= a.P) return;
-  const size_t vi = (size_t)v * a.P + i;
-  const float* __restrict__ view = a.views + (size_t)v * kViewFloats;
-  const float* __restrict__ proj = view + 16;
-  const float tanx = view[38], tany = view[39], sscale = view[40];
-
-  float mean[3];
-  mean[0] = __ldg(a.means3D + 3 * (size_t)i + 0) * sscale;
-  mean[1] = __ldg(a.means3D + 3 * (size_t)i + 1) * sscale;
-  mean[2] = __ldg(a.means3D + 3 * (size_t)i + 2) * sscale;
-  float c6[6];
-  if (a.cov3D_precomp) {
-    const float2* cp = reinterpret_cast<const float2*>(a.cov3D_precomp + 6 * (size_t)i);
-    const float2 c01 = __ldg(cp), c23 = __ldg(cp + 1), c45 = __ldg(cp + 2);
-    c6[0] = c01.x; c6[1] = c01.y; c6[2] = c23.x; c6[3] = c23.y; c6[4] = c45.x; c6[5] = c45.y;
-  } else {
-    float s[3] = {__ldg(a.scales + 3 * (size_t)i), __ldg(a.scales + 3 * (size_t)i + 1), __ldg(a.scales + 3 * (size_t)i + 2)};
-    float q[4] = {__ldg(a.rotations + 4 * (size_t)i), __ldg(a.rotations + 4 * (size_t)i + 1),
-                  __ldg(a.rotations + 4 * (size_t)i + 2), __ldg(a.rotations + 4 * (size_t)i + 3)};
-    fsm::cov3d_from_scale_rot(s, a.scale_modifier, q, c6);
+// Shared-memory layout of preprocess_kernel (dynamic):
+//   float sh[256 * sh_stride]   SH rows of the block's 256 Gaussians, staged with coalesced loads
+//                               (a per-thread walk over a 108-byte-strided row costs 27 L1 wavefronts
+//                               per load instruction); sh_stride is odd => conflict-free reads.
+//   float4 out[256 * 3]         records of one view, written back as contiguous 16-byte chunks.
+// Each thread projects ITS Gaussian into all V views: the 148 input bytes are read once, not V times.
+__global__ void __launch_bounds__(kThreads) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy, int sh_stride) {
+  extern __shared__ float4 smem4[];
+  float4* s_out = smem4;                                   // [256*3]
+  float* s_sh = reinterpret_cast<float*>(smem4 + kThreads * 3);
+  const int tid = threadIdx.x;
+  const int block_base = blockIdx.x * kThreads;
+  const int i = block_base + tid;
+  const int nblk = min(kThreads, a.P - block_base);        // Gaussians handled by this block
+  const int M3 = a.M * 3;
+  if (a.shs) {
+    const float* src = a.shs + (size_t)block_base * M3;
+    const int total = nblk * M3;
+    for (int k = tid; k < total; k += kThreads) {
+      const int g = k / M3, c = k - g * M3;
+      s_sh[g * sh_stride + c] = __ldg(src + k);
+    }
   }
-  const float s2 = sscale * sscale;
+  __syncthreads();
+  const bool active = i < a.P;
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, opacity = 0.f;
+  float c6in[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    m0 = __ldg(a.means3D + 3 * (size_t)i + 0); m1 = __ldg(a.means3D + 3 * (size_t)i + 1); m2 = __ldg(a.means3D + 3 * (size_t)i + 2);
+    opacity = __ldg(a.opacities + i);
+    if (a.cov3D_precomp) {
+      const float2* cp = reinterpret_cast<const float2*>(a.cov3D_precomp + 6 * (size_t)i);
+      const float2 c01 = __ldg(cp), c23 = __ldg(cp + 1), c45 = __ldg(cp + 2);
+      c6in[0] = c01.x; c6in[1] = c01.y; c6in[2] = c23.x; c6in[3] = c23.y; c6in[4] = c45.x; c6in[5] = c45.y;
+    } else {
+      float sc[3] = {__ldg(a.scales + 3 * (size_t)i), __ldg(a.scales + 3 * (size_t)i + 1), __ldg(a.scales + 3 * (size_t)i + 2)};
+      float q[4] = {__ldg(a.rotations + 4 * (size_t)i), __ldg(a.rotations + 4 * (size_t)i + 1),
+                    __ldg(a.rotations + 4 * (size_t)i + 2), __ldg(a.rotations + 4 * (size_t)i + 3)};
+      fsm::cov3d_from_scale_rot(sc, a.scale_modifier, q, c6in);
+    }
+  }
+  for (int v = 0; v < a.V; v++) {
+    const size_t vi = (size_t)v * a.P + i;
+    const float* __restrict__ view = a.views + (size_t)v * kViewFloats;
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = make_float4(0.f, 0.f, -3.0e38f, -3.0e38f);
+    if (active) {
+      const float* __restrict__ proj = view + 16;
+      const float tanx = view[38], tany = view[39], sscale = view[40];
+      const float mean[3] = {m0 * sscale, m1 * sscale, m2 * sscale};
+      const float s2 = sscale * sscale;
+      float c6[6];
 #pragma unroll
-  for (int k = 0; k < 6; k++) c6[k] = c6[k] * s2;
-
-  const fsm::Projected pr = fsm::project_gaussian(mean, c6, view, proj, tanx, tany, a.H, a.W);
-
-  float4* __restrict__ rec = reinterpret_cast<float4*>(a.rec) + 3 * vi;
-  float2* __restrict__ covo = reinterpret_cast<float2*>(a.cov3D + 6 * vi);
-  covo[0] = make_float2(c6[0], c6[1]); covo[1] = make_float2(c6[2], c6[3]); covo[2] = make_float2(c6[4], c6[5]);
-
-  if (pr.radius == 0) {
-    a.radii[vi] = 0; a.tiles_touched[vi] = 0; a.clamped[vi] = 0;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    rec[0] = z; rec[1] = z; rec[2] = make_float4(0.f, 0.f, -3.0e38f, -3.0e38f);
-    return;
-  }
-  float rgb[3];
-  int clampmask = 0;
-  if (a.colors_precomp) {
-    rgb[0] = __ldg(a.colors_precomp + 3 * (size_t)i); rgb[1] = __ldg(a.colors_precomp + 3 * (size_t)i + 1);
-    rgb[2] = __ldg(a.colors_precomp + 3 * (size_t)i + 2);
-  } else {
-    float sh[48];
-    const int nf = ((a.sh_degree + 1) * (a.sh_degree + 1)) * 3;   // only the active coefficients are read
-    const float* shp = a.shs + (size_t)i * a.M * 3;
+      for (int k = 0; k < 6; k++) c6[k] = c6in[k] * s2;
+      const fsm::Projected pr = fsm::project_gaussian(mean, c6, view, proj, tanx, tany, a.H, a.W);
+      if (a.cov3D) {
+        float2* __restrict__ covo = reinterpret_cast<float2*>(a.cov3D + 6 * vi);
+        covo[0] = make_float2(c6[0], c6[1]); covo[1] = make_float2(c6[2], c6[3]); covo[2] = make_float2(c6[4], c6[5]);
+      }
+      int clampmask = 0;
+      uint32_t ntiles = 0;
+      if (pr.radius > 0) {
+        float rgb[3];
+        if (a.colors_precomp) {
+          rgb[0] = __ldg(a.colors_precomp + 3 * (size_t)i); rgb[1] = __ldg(a.colors_precomp + 3 * (size_t)i + 1);
+          rgb[2] = __ldg(a.colors_precomp + 3 * (size_t)i + 2);
+        } else {
+          float sh[48];
+          const int nf = ((a.sh_degree + 1) * (a.sh_degree + 1)) * 3;   // only the active coefficients are used
+          const float* shp = s_sh + tid * sh_stride;
 #pragma unroll
-    for (int k = 0; k < 48; k++) sh[k] = (k < nf) ? __ldg(shp + k) : 0.f;
-    clampmask = fsm::sh_to_rgb(a.sh_degree, mean, view + 32, sh, rgb);
+          for (int k = 0; k < 48; k++) sh[k] = (k < nf) ? shp[k] : 0.f;
+          clampmask = fsm::sh_to_rgb(a.sh_degree, mean, view + 32, sh, rgb);
+        }
+        float hx, hy;
+        fsm::alpha_extent(pr.con_x, pr.con_y, pr.con_z, opacity, &hx, &hy);
+        if (hx < 0.f) { hx = -3.0e38f; hy = -3.0e38f; }
+        r0 = make_float4(pr.px, pr.py, pr.con_x, pr.con_y);
+        r1 = make_float4(pr.con_z, opacity, rgb[0], rgb[1]);
+        r2 = make_float4(rgb[2], pr.depth, hx, hy);
+        ntiles = (uint32_t)((pr.x1 - pr.x0) * (pr.y1 - pr.y0));
+        // per-tile population count (tile ranges come from a scan over these counters)
+        uint32_t* __restrict__ cnt = a.tile_count + (size_t)v * gx * gy;
+        for (int ty = pr.y0; ty < pr.y1; ty++)
+          for (int tx = pr.x0; tx < pr.x1; tx++) atomicAdd(cnt + ty * gx + tx, 1u);
+      }
+      a.radii[vi] = pr.radius;
+      if (a.tiles_touched) a.tiles_touched[vi] = ntiles;
+      a.clamped[vi] = (uint8_t)clampmask;
+    }
+    // records: through shared memory so that the block writes contiguous 16-byte chunks
+    s_out[tid * 3 + 0] = r0; s_out[tid * 3 + 1] = r1; s_out[tid * 3 + 2] = r2;
+    __syncthreads();
+    float4* __restrict__ dst = reinterpret_cast<float4*>(a.rec) + 3 * ((size_t)v * a.P + block_base);
+    for (int k = tid; k < nblk * 3; k += kThreads) dst[k] = s_out[k];
+    __syncthreads();
   }
-  const float opacity = __ldg(a.opacities + i);
-  float hx, hy;
-  fsm::alpha_extent(pr.con_x, pr.con_y, pr.con_z, opacity, &hx, &hy);
-  if (hx < 0.f) { hx = -3.0e38f; hy = -3.0e38f; }
-  rec[0] = make_float4(pr.px, pr.py, pr.con_x, pr.con_y);
-  rec[1] = make_float4(pr.con_z, opacity, rgb[0], rgb[1]);
-  rec[2] = make_float4(rgb[2], pr.depth, hx, hy);
-  a.radii[vi] = pr.radius;
-  a.tiles_touched[vi] = (uint32_t)((pr.x1 - pr.x0) * (pr.y1 - pr.y0));
-  a.clamped[vi] = (uint8_t)clampmask;
-  // per-tile population count (tile ranges come from a scan over these counters)
-  uint32_t* __restrict__ cnt = a.tile_count + (size_t)v * gx * gy;
-  for (int ty = pr.y0; ty < pr.y1; ty++)
-    for (int tx = pr.x0; tx < pr.x1; tx++) atomicAdd(cnt + ty * gx + tx, 1u);
 }
 
 __global__ void __launch_bounds__(kThreads) mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -106,6 +135,13 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
   const int nsh = a.M * 3;
   bool sh_written = false;
   const float m0 = a.means3D[3 * (size_t)i], m1 = a.means3D[3 * (size_t)i + 1], m2 = a.means3D[3 * (size_t)i + 2];
+  float c6in[6];
+  if (a.cov3D_precomp) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) c6in[k] = a.cov3D_precomp[6 * (size_t)i + k];
+  } else {
+    fsm::cov3d_from_scale_rot(a.scales + 3 * (size_t)i, a.scale_modifier, a.rotations + 4 * (size_t)i, c6in);
+  }
 
   for (int v = 0; v < a.V; v++) {
     const size_t vi = (size_t)v * a.P + i;
@@ -121,7 +157,12 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
     g2d[0] = ga.x; g2d[1] = ga.y; g2d[2] = 0.f;
     g_op += gb.y;
     const float mean[3] = {m0 * ss, m1 * ss, m2 * ss};
-    const float* c6 = a.cov3D + 6 * vi;
+    float c6[6];
+    {
+      const float s2c = ss * ss;
+#pragma unroll
+      for (int k = 0; k < 6; k++) c6[k] = c6in[k] * s2c;     // same arithmetic as the forward pass
+    }
     const float pvx = fsm::dot4row(view, 0, mean[0], mean[1], mean[2]);
     const float pvy = fsm::dot4row(view, 1, mean[0], mean[1], mean[2]);
     const float pvz = fsm::dot4row(view, 2, mean[0], mean[1], mean[2]);
@@ -303,8 +344,13 @@ int launch_preprocess(const FsRasterFwdArgs& a, cudaStream_t s) {
   if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, nt * 4, s), "memset tile_count"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(a.tile_cursor, 0, nt * 4, s), "memset tile_cursor"))) return rc;
   if (a.P > 0) {
-    dim3 grid((a.P + kThreads - 1) / kThreads, a.V);
-    preprocess_kernel<<<grid, kThreads, 0, s>>>(a, gx, gy);
+    const int sh_stride = (a.M * 3) | 1;
+    const size_t smem = (size_t)kThreads * 3 * sizeof(float4) + (a.shs ? (size_t)kThreads * sh_stride * sizeof(float) : 0);
+    if (smem > 48 * 1024) {
+      if ((rc = check_cuda(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                           "cudaFuncSetAttribute(preprocess_kernel)"))) return rc;
+    }
+    preprocess_kernel<<<(a.P + kThreads - 1) / kThreads, kThreads, smem, s>>>(a, gx, gy, sh_stride);
     if ((rc = check_cuda(cudaGetLastError(), "preprocess_kernel"))) return rc;
   }
   return FS_OK;

@@ -96,7 +96,7 @@ def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
 def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_precomp=None, scales=None,
                        rotations=None, cov3D_precomp=None, sh_degree=0, scale_modifier=1.0, prefiltered=False,
                        capacity: Optional[int] = None, check_overflow: str = "sync",
-                       stage_events=None) -> RasterState:
+                       stage_events=None, debug_buffers: bool = False) -> RasterState:
     """One launch sequence for V views (views: [V,48]).  Returns the RasterState.
 
     check_overflow: "sync"     read the device status word after enqueueing everything; re-run once
@@ -128,8 +128,10 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
             st.color = e(V, 3, H, W); st.depth = e(V, H, W); st.final_T = e(V, H, W)
             st.n_contrib = e(V, H, W, dtype=torch.int32)
             st.radii = e(V, P, dtype=torch.int32)
-            st.rec = e(V, P, REC_FLOATS); st.cov3D = e(V, P, 6)
-            st.tiles_touched = e(V, P, dtype=torch.int32); st.clamped = e(V, P, dtype=torch.uint8)
+            st.rec = e(V, P, REC_FLOATS); st.clamped = e(V, P, dtype=torch.uint8)
+            # only the parity tests ask for these (the hot path neither writes nor reads them)
+            st.cov3D = e(V, P, 6) if debug_buffers else None
+            st.tiles_touched = e(V, P, dtype=torch.int32) if debug_buffers else None
             tile_count = e(nt, dtype=torch.int32); tile_cursor = e(nt, dtype=torch.int32)
             st.ranges = e(nt, 2, dtype=torch.int32)
             st.keybuf = e(max(capacity, 1), dtype=torch.int64)
@@ -166,7 +168,7 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
 
 
 def raster_backward_raw(st: RasterState, means3D, opacities, dL_dcolor, *, shs=None, colors_precomp=None,
-                        scales=None, rotations=None, dL_ddepth=None):
+                        scales=None, rotations=None, cov3D_precomp=None, dL_ddepth=None):
     """Gradients w.r.t. the op inputs, summed over the V views of `st`."""
     L = _lib.lib()
     dev = means3D.device
@@ -174,6 +176,7 @@ def raster_backward_raw(st: RasterState, means3D, opacities, dL_dcolor, *, shs=N
     means3D = _f32c(means3D, "means3D"); opacities = _f32c(opacities, "opacities").reshape(-1)
     shs = _f32c(shs, "shs"); colors_precomp = _f32c(colors_precomp, "colors_precomp")
     scales = _f32c(scales, "scales"); rotations = _f32c(rotations, "rotations")
+    cov3D_precomp = _f32c(cov3D_precomp, "cov3D_precomp")
     dL_dcolor = _f32c(dL_dcolor, "dL_dcolor"); dL_ddepth = _f32c(dL_ddepth, "dL_ddepth")
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
@@ -192,8 +195,8 @@ def raster_backward_raw(st: RasterState, means3D, opacities, dL_dcolor, *, shs=N
             P=P, V=V, H=H, W=W, sh_degree=st.sh_degree, M=M, scale_modifier=st.scale_modifier,
             has_depth_grad=int(dL_ddepth is not None),
             means3D=ptr(means3D), shs=ptr(shs), colors_precomp=ptr(colors_precomp), opacities=ptr(opacities),
-            scales=ptr(scales), rotations=ptr(rotations), views=ptr(st.views),
-            rec=ptr(st.rec), cov3D=ptr(st.cov3D), radii=ptr(st.radii), clamped=ptr(st.clamped), ranges=ptr(st.ranges),
+            scales=ptr(scales), rotations=ptr(rotations), cov3D_precomp=ptr(cov3D_precomp), views=ptr(st.views),
+            rec=ptr(st.rec), radii=ptr(st.radii), clamped=ptr(st.clamped), ranges=ptr(st.ranges),
             point_list=ptr(st.point_list), final_T=ptr(st.final_T), n_contrib=ptr(st.n_contrib), status=ptr(st.status),
             dL_dcolor=ptr(dL_dcolor), dL_ddepth=ptr(dL_ddepth), dL_dscreen=ptr(dscreen),
             dL_dmeans2D=ptr(g["means2D"]), dL_dmeans3D=ptr(g["means3D"]), dL_dcov3D=ptr(cov_buf), dL_dshs=ptr(g["shs"]),
@@ -216,7 +219,7 @@ class _RasterizeViews(torch.autograd.Function):
                                 check_overflow="deferred" if _ASYNC else "sync")
         ctx.st = st
         ctx.depth_grad = depth_grad
-        ctx.save_for_backward(means3D, shs, colors_precomp, opacities, scales, rotations)
+        ctx.save_for_backward(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp)
         ctx.mark_non_differentiable(st.radii)
         alpha = 1.0 - st.final_T
         st.keybuf = None  # sorted keys are only needed by the parity tests (raster_forward_raw)
@@ -224,13 +227,13 @@ class _RasterizeViews(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_color, g_radii, g_depth, g_alpha):
-        means3D, shs, colors_precomp, opacities, scales, rotations = ctx.saved_tensors
+        means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp = ctx.saved_tensors
         st = ctx.st
         if g_color is None:
             g_color = torch.zeros_like(st.color)
         dd = g_depth if (ctx.depth_grad and g_depth is not None) else None
         g = raster_backward_raw(st, means3D, opacities, g_color, shs=shs, colors_precomp=colors_precomp, scales=scales,
-                                rotations=rotations, dL_ddepth=dd)
+                                rotations=rotations, cov3D_precomp=cov3D_precomp, dL_ddepth=dd)
         gm2d = g["means2D"]
         return (g["means3D"], gm2d if st.V > 1 else gm2d[0], g["shs"], g["colors"],
                 g["opacities"].reshape(opacities.shape), g["scales"], g["rotations"], g["cov3D"], None,

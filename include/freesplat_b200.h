@@ -91,8 +91,9 @@ typedef struct FsRasterFwdArgs {
   int32_t* radii;        /* [V,P]                                                */
   /* state kept for backward / parity checks */
   float* rec;            /* [V,P,FS_REC_FLOATS]                                  */
-  float* cov3D;          /* [V,P,6] covariance actually used (scaled)            */
-  uint32_t* tiles_touched; /* [V,P]                                              */
+  float* cov3D;          /* [V,P,6] covariance actually used (scaled); NULL = not stored
+                            (backward recomputes it; only the parity tests ask for it) */
+  uint32_t* tiles_touched; /* [V,P] or NULL (parity tests only)                  */
   uint8_t* clamped;      /* [V,P] bit c set <=> SH colour channel c clamped at 0 */
   uint32_t* tile_count;  /* [V*tiles]   scratch (zeroed by the call)             */
   uint32_t* tile_cursor; /* [V*tiles]   scratch (zeroed by the call)             */
@@ -113,9 +114,10 @@ typedef struct FsRasterBwdArgs {
   int32_t has_depth_grad;      /* 0: dL_ddepth ignored (reference behaviour)     */
   const float* means3D; const float* shs; const float* colors_precomp;
   const float* opacities; const float* scales; const float* rotations;
+  const float* cov3D_precomp;  /* exactly one of cov3D_precomp / (scales, rotations), as in forward */
   const float* views;
   /* forward state */
-  const float* rec; const float* cov3D; const int32_t* radii; const uint8_t* clamped;
+  const float* rec; const int32_t* radii; const uint8_t* clamped;
   const uint32_t* ranges; const uint32_t* point_list;
   const float* final_T; const uint32_t* n_contrib; const uint32_t* status;
   /* upstream gradients */

@@ -17,15 +17,18 @@ def _bits(a):
 def run_cuda(scene, bg=(0.0, 0.0, 0.0), device="cuda:0", scale_invariant=True, capacity=None):
     from freesplat_b200 import decoder
     sc = scene.to(device)
-    V = sc.extrinsics.shape[0]
-    bgc = torch.tensor(bg, dtype=torch.float32, device=device)[None].expand(V, 3)
-    views, _ = decoder.camera_records(sc.extrinsics, sc.intrinsics, sc.near, sc.far, bgc, scale_invariant)
+    V = scene.extrinsics.shape[0]
+    # camera records are computed on the CPU and copied, so that the oracle and the kernels see
+    # bit-identical inputs (torch's CPU and CUDA inverse()/matmul differ in the last bits)
+    bgc = torch.tensor(bg, dtype=torch.float32)[None].expand(V, 3)
+    views, _ = decoder.camera_records(scene.extrinsics, scene.intrinsics, scene.near, scene.far, bgc, scale_invariant)
+    views = views.to(device)
     row, col = torch.triu_indices(3, 3)
     d_sh = sc.harmonics.shape[-1]
     st = rasterizer.raster_forward_raw(
         sc.means, sc.opacities, views, sc.image_shape[0], sc.image_shape[1],
         shs=sc.harmonics.transpose(1, 2).contiguous(), cov3D_precomp=sc.covariances[:, row, col].contiguous(),
-        sh_degree=int(round(d_sh ** 0.5)) - 1, capacity=capacity)
+        sh_degree=int(round(d_sh ** 0.5)) - 1, capacity=capacity, debug_buffers=True)
     return st, views
 
 
@@ -109,6 +112,7 @@ def compare_backward(scene, st, views, dL_dcolor, dL_ddepth=None, bg=(0.0, 0.0, 
     row, col = torch.triu_indices(3, 3)
     shs = sc.harmonics.transpose(1, 2).contiguous()
     g = rasterizer.raster_backward_raw(st, sc.means, sc.opacities, dL_dcolor.to(dev), shs=shs,
+                                       cov3D_precomp=sc.covariances[:, row, col].contiguous(),
                                        dL_ddepth=None if dL_ddepth is None else dL_ddepth.to(dev))
     P = st.P
     want = dict(means3D=np.zeros((P, 3)), cov3D=np.zeros((P, 6)), shs=np.zeros(tuple(shs.shape)), opacities=np.zeros((P, 1)))

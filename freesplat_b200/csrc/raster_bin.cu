@@ -78,54 +78,107 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(FsRasterFwdArgs a, in
   const int v = blockIdx.y;
   if (i >= a.P) return;
   const size_t vi = (size_t)v * a.P + i;
-  const int r = a.radii[vi];
-  if (r <= 0) return;
+  // latency-bound kernel: issue every load before the first use (radius, centre, depth are independent)
   const float4* rec = reinterpret_cast<const float4*>(a.rec) + 3 * vi;
-  const float4 r0 = __ldg(rec);
+  const int r = __ldg(a.radii + vi);
+  const float2 xy = __ldg(reinterpret_cast<const float2*>(rec));
   const float depth = __ldg(reinterpret_cast<const float*>(rec + 2) + 1);
+  if (r <= 0) return;
   int x0, y0, x1, y1;
-  fsm::get_rect(r0.x, r0.y, r, gx, gy, &x0, &y0, &x1, &y1);
+  fsm::get_rect(xy.x, xy.y, r, gx, gy, &x0, &y0, &x1, &y1);
   const unsigned long long key = ((unsigned long long)__float_as_uint(depth) << 32) | (unsigned long long)(uint32_t)i;
   const size_t tbase = (size_t)v * gx * gy;
   for (int ty = y0; ty < y1; ty++)
     for (int tx = x0; tx < x1; tx++) {
       const size_t t = tbase + (size_t)ty * gx + tx;
+      const uint32_t start = __ldg(a.ranges + 2 * t);           // independent of the atomic below
       const uint32_t slot = atomicAdd(a.tile_cursor + t, 1u);
-      const uint32_t pos = a.ranges[2 * t] + slot;
-      a.keybuf[pos] = key;
+      a.keybuf[start + slot] = key;
     }
 }
 
 // ---- 4. per-tile sort -------------------------------------------------------------------------
 // Bitonic network with ascending comparators only (first step of every merge is the mirrored
-// "flip" step), so virtual +inf padding above n needs no storage.
+// "flip" step), so virtual +inf padding above n needs no storage.  Compare-exchange c of a stage
+// touches only the aligned 64-element region [64*(c/32), +64) whenever the stage's block size is
+// <= 64, and warp w always owns CEs {32w..32w+31} (+256m): such stages only need __syncwarp().
+// For N = 512 that leaves 9 block-wide barriers out of 45 stages.  All index math is shifts/masks.
+__device__ __forceinline__ void stage_sync(bool block_wide) {
+  if (block_wide) __syncthreads(); else __syncwarp();
+}
+
 template <typename KeyPtr>
-__device__ __forceinline__ void bitonic_sort_block(KeyPtr keys, int n, int tid, int nthreads) {
-  int N = 1;
-  while (N < n) N <<= 1;
-  for (int k = 2; k <= N; k <<= 1) {
-    const int half = k >> 1;
-    for (int c = tid; c < (N >> 1); c += nthreads) {
-      const int b = c / half, off = c - b * half;
-      const int i = b * k + off, l = b * k + (k - 1 - off);
+__device__ __forceinline__ void bitonic_sort_block(KeyPtr keys, int n, int tid) {
+  int logN = 0;
+  while ((1 << logN) < n) logN++;
+  const int halfN = (1 << logN) >> 1;
+  int prevB = 1 << 30;                                   // "previous stage" before the first one: block-wide
+  for (int lk = 1; lk <= logN; lk++) {
+    const int k = 1 << lk, half = k >> 1;
+    stage_sync(k > 64 || prevB > 64);
+    for (int c = tid; c < halfN; c += kThreads) {        // flip step
+      const int b = c >> (lk - 1), off = c & (half - 1);
+      const int i = (b << lk) + off, l = (b << lk) + (k - 1 - off);
       if (l < n) {
         const unsigned long long ki = keys[i], kl = keys[l];
         if (ki > kl) { keys[i] = kl; keys[l] = ki; }
       }
     }
-    __syncthreads();
-    for (int j = half >> 1; j > 0; j >>= 1) {
-      for (int c = tid; c < (N >> 1); c += nthreads) {
-        const int b = c / j, off = c - b * j;
-        const int i = b * 2 * j + off, l = i + j;
+    prevB = k;
+    for (int lj = lk - 2; lj >= 0; lj--) {
+      const int j = 1 << lj, B = j << 1;
+      stage_sync(B > 64 || prevB > 64);
+      for (int c = tid; c < halfN; c += kThreads) {
+        const int b = c >> lj, off = c & (j - 1);
+        const int i = (b << (lj + 1)) + off, l = i + j;
         if (l < n) {
           const unsigned long long ki = keys[i], kl = keys[l];
           if (ki > kl) { keys[i] = kl; keys[l] = ki; }
         }
       }
-      __syncthreads();
+      prevB = B;
     }
   }
+  __syncthreads();
+}
+
+// Fully unrolled network for N = 2^LOGN <= 512 keys: one compare-exchange per thread and stage, all
+// shifts/masks compile-time constants (the generic loop spent ~64 instructions per stage, ncu r1b).
+template <int LOGN>
+__device__ __forceinline__ void bitonic_sort_fixed(unsigned long long* keys, int n, int tid) {
+  constexpr int HALF = (1 << LOGN) >> 1;
+  static_assert(HALF <= kThreads, "one compare-exchange per thread");
+  const bool has_ce = tid < HALF;
+  int prevB = 1 << 30;
+#pragma unroll
+  for (int lk = 1; lk <= LOGN; lk++) {
+    const int k = 1 << lk, half = k >> 1;
+    stage_sync(k > 64 || prevB > 64);
+    if (has_ce) {
+      const int b = tid >> (lk - 1), off = tid & (half - 1);
+      const int i = (b << lk) + off, l = (b << lk) + (k - 1 - off);
+      if (l < n) {
+        const unsigned long long ki = keys[i], kl = keys[l];
+        if (ki > kl) { keys[i] = kl; keys[l] = ki; }
+      }
+    }
+    prevB = k;
+#pragma unroll
+    for (int lj = lk - 2; lj >= 0; lj--) {
+      const int j = 1 << lj, B = j << 1;
+      stage_sync(B > 64 || prevB > 64);
+      if (has_ce) {
+        const int b = tid >> lj, off = tid & (j - 1);
+        const int i = (b << (lj + 1)) + off, l = i + j;
+        if (l < n) {
+          const unsigned long long ki = keys[i], kl = keys[l];
+          if (ki > kl) { keys[i] = kl; keys[l] = ki; }
+        }
+      }
+      prevB = B;
+    }
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kThreads) tile_sort_kernel(const uint32_t* __restrict__ ranges, unsigned long long* __restrict__ keybuf,
@@ -140,16 +193,19 @@ __global__ void __launch_bounds__(kThreads) tile_sort_kernel(const uint32_t* __r
   unsigned long long* g = keybuf + start;
   if (n <= kSortSmemKeys) {
     for (int k = tid; k < n; k += kThreads) skeys[k] = g[k];
-    __syncthreads();
-    bitonic_sort_block(skeys, n, tid, kThreads);
+    if (n <= 32) bitonic_sort_fixed<5>(skeys, n, tid);
+    else if (n <= 64) bitonic_sort_fixed<6>(skeys, n, tid);
+    else if (n <= 128) bitonic_sort_fixed<7>(skeys, n, tid);
+    else if (n <= 256) bitonic_sort_fixed<8>(skeys, n, tid);
+    else if (n <= 512) bitonic_sort_fixed<9>(skeys, n, tid);
+    else bitonic_sort_block(skeys, n, tid);
     for (int k = tid; k < n; k += kThreads) {
       const unsigned long long key = skeys[k];
       g[k] = key;
       point_list[start + k] = (uint32_t)(key & 0xffffffffull);
     }
   } else {
-    __syncthreads();
-    bitonic_sort_block(g, n, tid, kThreads);   // rare: very crowded tile, sort in L2/HBM
+    bitonic_sort_block(g, n, tid);             // rare: very crowded tile, sort in L2/HBM
     for (int k = tid; k < n; k += kThreads) point_list[start + k] = (uint32_t)(g[k] & 0xffffffffull);
   }
 }

@@ -21,7 +21,7 @@ namespace fs {
 //                               per load instruction); sh_stride is odd => conflict-free reads.
 //   float4 out[256 * 3]         records of one view, written back as contiguous 16-byte chunks.
 // Each thread projects ITS Gaussian into all V views: the 148 input bytes are read once, not V times.
-__global__ void __launch_bounds__(kThreads) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy, int sh_stride) {
+__global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy, int sh_stride) {
   extern __shared__ float4 smem4[];
   float4* s_out = smem4;                                   // [256*3]
   float* s_sh = reinterpret_cast<float*>(smem4 + kThreads * 3);
@@ -33,9 +33,14 @@ __global__ void __launch_bounds__(kThreads) preprocess_kernel(FsRasterFwdArgs a,
   if (a.shs) {
     const float* src = a.shs + (size_t)block_base * M3;
     const int total = nblk * M3;
+    // (g, c) = divmod(k, M3) maintained incrementally: a runtime integer division per element
+    // was the single largest cost of this kernel (ncu r1a: IABS/IMAD/ISETP chains).
+    const int qstep = kThreads / M3, rstep = kThreads - qstep * M3;
+    int g = tid / M3, c = tid - g * M3;
     for (int k = tid; k < total; k += kThreads) {
-      const int g = k / M3, c = k - g * M3;
       s_sh[g * sh_stride + c] = __ldg(src + k);
+      g += qstep; c += rstep;
+      if (c >= M3) { c -= M3; g++; }
     }
   }
   __syncthreads();

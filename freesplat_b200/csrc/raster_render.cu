@@ -27,13 +27,42 @@ __device__ __forceinline__ float fast_exp(float x) {
 constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------- forward
+// Explicit shared-memory addressing (ld.shared with a 32-bit address): the compiler's generic path
+// re-derived the shared window base (S2R SR_CgaCtaId + LEA chain) on every loop iteration.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// Staged per-instance data (56 B): the exponent coefficients are pre-multiplied by log2(e) so that
+// the per-pixel chain is  t = fma(cb,dy,ca*dx); p2 = fma(cc*dy,dy,t*dx); alpha = min(.99, o*ex2(p2)).
+struct __align__(16) RenderSmem {
+  float4 T[kThreads];   // x, y, hx, hy         (sub-tile overlap test)
+  float4 A[kThreads];   // x, y, ca, cb         (hot loop)
+  float4 C[kThreads];   // r, g, b, depth       (only when the pixel is actually hit)
+  float2 B[kThreads];   // cc, opacity          (hot loop)
+};
+
 __global__ void __launch_bounds__(kThreads) render_fwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
     const float* __restrict__ views, const uint32_t* __restrict__ status, int P, int H, int W, int gx, int ntiles,
     float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib) {
   if (status[2]) return;
-  __shared__ float4 sA[kThreads], sB[kThreads], sC[kThreads];
+  __shared__ RenderSmem sm;
   const int tile = blockIdx.x, v = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = tile % gx, tile_y = tile / gx;
@@ -44,69 +73,73 @@ __global__ void __launch_bounds__(kThreads) render_fwd_kernel(
   const float fx0 = (float)x0, fx1 = (float)(x0 + 7), fy0 = (float)y0, fy1 = (float)(y0 + 3);
   const uint2 range = ranges[(size_t)v * ntiles + tile];
   const float4* __restrict__ rec_v = rec + (size_t)v * P * 3;
+  const uint32_t aT = (uint32_t)__cvta_generic_to_shared(sm.T), aA = (uint32_t)__cvta_generic_to_shared(sm.A),
+                 aC = (uint32_t)__cvta_generic_to_shared(sm.C), aB = (uint32_t)__cvta_generic_to_shared(sm.B);
 
-  float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+  // T > 0: pixel still accumulating.  T < 0: finished (its final transmittance is in T_fin).
+  float T = inside ? 1.f : -1.f, T_fin = 1.f;
+  float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
   uint32_t last = 0;
-  bool done = !inside;
 
   for (uint32_t base = range.x; base < range.y; base += kThreads) {
-    if (__syncthreads_count(done) == kThreads) break;   // barrier also protects the smem reuse
+    if (__syncthreads_count(T < 0.f) == kThreads) break;   // barrier also protects the smem reuse
     const int n = min((int)kThreads, (int)(range.y - base));
     if (tid < n) {
       const uint32_t id = point_list[base + tid];
       const float4* r = rec_v + 3 * (size_t)id;
-      sA[tid] = __ldg(r); sB[tid] = __ldg(r + 1); sC[tid] = __ldg(r + 2);
+      const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+      sm.T[tid] = make_float4(r0.x, r0.y, r2.z, r2.w);
+      sm.A[tid] = make_float4(r0.x, r0.y, (-0.5f * r0.z) * kLog2e, (-r0.w) * kLog2e);
+      sm.B[tid] = make_float2((-0.5f * r1.x) * kLog2e, r1.y);
+      sm.C[tid] = make_float4(r1.z, r1.w, r2.x, r2.y);
     }
     __syncthreads();
-    if (__all_sync(kFull, done)) continue;
+    if (__all_sync(kFull, T < 0.f)) continue;
+    const uint32_t pos0 = base - range.x + 1u;      // contributor index of staged slot 0
     for (int g = 0; g < n; g += 32) {
       const int j = g + lane;
       bool hit = false;
       if (j < n) {
-        const float4 a = sA[j];
-        const float4 c = sC[j];
-        hit = (a.x - c.z <= fx1) && (a.x + c.z >= fx0) && (a.y - c.w <= fy1) && (a.y + c.w >= fy0);
+        const float4 q = lds128(aT + (uint32_t)j * 16u);
+        hit = (q.x - q.z <= fx1) && (q.x + q.z >= fx0) && (q.y - q.w <= fy1) && (q.y + q.w >= fy0);
       }
       unsigned m = __ballot_sync(kFull, hit);
       while (m) {
-        const int b = __ffs(m) - 1;
+        const uint32_t jj = (uint32_t)(g + __ffs(m) - 1);
         m &= m - 1;
-        const int jj = g + b;
-        const float4 a = sA[jj], bb = sB[jj], c = sC[jj];
-        if (!done) {
-          const float dx = a.x - pxf, dy = a.y - pyf;
-          const float ca = -0.5f * a.z, cb = -a.w, cc = -0.5f * bb.x;
-          const float t = fmaf(cb, dy, ca * dx);
-          const float power = fmaf(cc * dy, dy, t * dx);
-          if (power <= 0.f) {
-            const float alpha = fminf(0.99f, bb.y * fast_exp(power));
-            if (alpha >= 1.f / 255.f) {
-              const float test_T = T * (1.f - alpha);
-              if (test_T < 0.0001f) {
-                done = true;
-              } else {
-                const float w = alpha * T;
-                C0 = fmaf(bb.z, w, C0); C1 = fmaf(bb.w, w, C1); C2 = fmaf(c.x, w, C2);
-                Dp = fmaf(c.y, w, Dp);
-                T = test_T;
-                last = (base - range.x) + (uint32_t)jj + 1u;
-              }
-            }
-          }
-        }
+        const float4 a = lds128(aA + jj * 16u);
+        const float2 bo = lds64(aB + jj * 8u);
+        const float dx = a.x - pxf, dy = a.y - pyf;
+        const float t = fmaf(a.w, dy, a.z * dx);
+        const float p2 = fmaf(bo.x * dy, dy, t * dx);
+        const float alpha = fminf(0.99f, bo.y * ex2_approx(p2));
+        // branch-free accumulate: ~94% of the walked instances touch at least one lane, so a
+        // divergent branch here only added BSSY/BSYNC and register shuffling (ncu r1b).
+        const float4 c = lds128(aC + jj * 16u);
+        const bool pass = (p2 <= 0.f) && (alpha >= 1.f / 255.f) && (T > 0.f);
+        const float test_T = T * (1.f - alpha);
+        const bool fin = pass && (test_T < 0.0001f);
+        const bool acc = pass && !fin;
+        const float w = acc ? alpha * T : 0.f;
+        C0 = fmaf(c.x, w, C0); C1 = fmaf(c.y, w, C1); C2 = fmaf(c.z, w, C2);
+        Dp = fmaf(c.w, w, Dp);
+        T_fin = fin ? T : T_fin;
+        T = fin ? -1.f : (acc ? test_T : T);
+        last = acc ? pos0 + jj : last;
       }
-      if (__all_sync(kFull, done)) break;
+      if (__all_sync(kFull, T < 0.f)) break;
     }
   }
   if (inside) {
+    if (T > 0.f) T_fin = T;
     const float* bg = views + (size_t)v * kViewFloats + 35;
     const size_t HW = (size_t)H * W, pix = (size_t)py * W + px;
     float* oc = out_color + (size_t)v * 3 * HW;
-    oc[pix] = fmaf(T, bg[0], C0);
-    oc[HW + pix] = fmaf(T, bg[1], C1);
-    oc[2 * HW + pix] = fmaf(T, bg[2], C2);
+    oc[pix] = fmaf(T_fin, bg[0], C0);
+    oc[HW + pix] = fmaf(T_fin, bg[1], C1);
+    oc[2 * HW + pix] = fmaf(T_fin, bg[2], C2);
     out_depth[(size_t)v * HW + pix] = Dp;
-    final_T[(size_t)v * HW + pix] = T;
+    final_T[(size_t)v * HW + pix] = T_fin;
     n_contrib[(size_t)v * HW + pix] = last;
   }
 }

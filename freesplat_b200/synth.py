@@ -164,3 +164,48 @@ def random_scene(seed: int = 0, h: int = 256, w: int = 256, P: int = 10000, n_ta
     V = n_target
     return Scene(means, cov.contiguous(), sh.contiguous(), opac, scales, q, tgt, intrinsics(V),
                  torch.full((V,), NEAR), torch.full((V,), FAR), (h, w), tgt)
+
+
+# ------------------------------------------------------------------------------------------------
+# cost-volume inputs, built the way EncoderFreeSplat.forward does (encoder_freesplat.py:218-277)
+def cost_volume_inputs(seed: int = 0, n_views: int = 3, K: int | None = None, C: int = 48, Hf: int = 120, Wf: int = 160,
+                       spacing: float = 0.25):
+    """Returns dict(cur_feats [V,C,Hf,Wf], src_feats [V,K,C,Hf,Wf], src_extrinsics [V,K,4,4]
+    (src_cam_T_cur_cam), src_poses [V,K,4,4], src_Ks [V,K,4,4], cur_invK [V,4,4], min_depth, max_depth)."""
+    g = torch.Generator().manual_seed(seed)
+    V = n_views
+    K = V - 1 if K is None else K
+    ext = camera_path(V, spacing=spacing)                       # c2w
+    Kn = intrinsics(V).clone()
+    Kn[:, 0] *= Wf                                              # feature-resolution pixel intrinsics
+    Kn[:, 1] *= Hf
+    feats = torch.randn((V, C, Hf, Wf), generator=g)
+    # low-pass a little so that neighbouring pixels correlate (post-BN-like magnitude ~1)
+    feats = 0.6 * feats + 0.4 * F.avg_pool2d(feats, 3, stride=1, padding=1)
+    src_idx = []
+    for b in range(V):
+        others = [j for j in range(V) if j != b]
+        others.sort(key=lambda j: abs(j - b))
+        src_idx.append(others[:K])
+    src_idx = torch.tensor(src_idx)                             # [V,K]
+    src_ext = ext[src_idx]                                      # [V,K,4,4]
+    src_cam_T_cur_cam = src_ext.inverse() @ ext[:, None]
+    cur_cam_T_src_cam = ext.inverse()[:, None] @ src_ext
+    src_K = torch.eye(4)[None, None].repeat(V, K, 1, 1)
+    src_K[:, :, :3, :3] = Kn[src_idx]
+    cur_invK = torch.eye(4)[None].repeat(V, 1, 1)
+    cur_invK[:, :3, :3] = Kn.inverse()
+    return dict(cur_feats=feats.contiguous(), src_feats=feats[src_idx].contiguous(),
+                src_extrinsics=src_cam_T_cur_cam.contiguous(), src_poses=cur_cam_T_src_cam.contiguous(),
+                src_Ks=src_K, cur_invK=cur_invK,
+                min_depth=torch.tensor(NEAR).view(1, 1, 1, 1), max_depth=torch.tensor(FAR).view(1, 1, 1, 1))
+
+
+def cost_volume_mlp(seed: int = 0, C: int = 48):
+    """Seeded MLP weights in nn.Linear layout: (W0 [32,C+1], b0, W1 [32,32], b1, W2 [1,32], b2)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    def lin(o, i):
+        bound = 1.0 / math.sqrt(i)
+        return (torch.rand((o, i), generator=g) * 2 - 1) * bound, (torch.rand((o,), generator=g) * 2 - 1) * bound
+    W0, b0 = lin(32, C + 1); W1, b1 = lin(32, 32); W2, b2 = lin(1, 32)
+    return [W0, b0, W1, b1, W2, b2]

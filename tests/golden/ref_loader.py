@@ -1,0 +1,86 @@
+"""Loads pieces of the (Python) reference from /root/reference WITHOUT importing its package
+(kornia / timm / jaxtyping are absent here).  Only used by the golden-vector generators in this
+directory, which run in the build container; nothing here is read on the GPU box."""
+from __future__ import annotations
+
+import ast
+import importlib.util
+import os
+import sys
+import types
+
+REF = os.environ.get("FREESPLAT_REFERENCE", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF, "src", "model", "encoder"))
+
+
+def _exec_lines(path, first, last, ns):
+    src = open(path).read().splitlines()
+    # keep the file's line numbers (torch.jit.script re-reads the source through inspect)
+    code = "\n" * (first - 1) + "\n".join(src[first - 1:last])
+    exec(compile(code, path, "exec"), ns)
+
+
+def load_cost_volume_module():
+    """Returns the reference's cost_volume module (AVGFeatureVolumeManager etc.), unmodified."""
+    import torch  # noqa: F401
+    # stub package sr_utils.geometry_utils built from the reference's own source lines 11-89
+    gu = types.ModuleType("sr_utils.geometry_utils")
+    ns = gu.__dict__
+    exec("import numpy as np\nimport torch\nimport torch.jit as jit\nimport torch.nn.functional as F\nfrom torch import Tensor\n", ns)
+    _exec_lines(os.path.join(REF, "sr_utils", "geometry_utils.py"), 11, 89, ns)
+    pkg = types.ModuleType("sr_utils"); pkg.__path__ = []
+    pkg.geometry_utils = gu
+    # generic_utils.upsample (sr_utils/generic_utils.py:97-106), the one symbol networks.py imports
+    ge = types.ModuleType("sr_utils.generic_utils")
+    exec("import torch\nfrom torch import nn\n", ge.__dict__)
+    _exec_lines(os.path.join(REF, "sr_utils", "generic_utils.py"), 97, 106, ge.__dict__)
+    pkg.generic_utils = ge
+    sys.modules["sr_utils"] = pkg; sys.modules["sr_utils.geometry_utils"] = gu
+    sys.modules["sr_utils.generic_utils"] = ge
+    try:
+        import torchvision  # noqa: F401
+    except Exception:   # networks.py does `from torchvision import models` but never uses it on this path
+        tv = types.ModuleType("torchvision"); tv.models = types.ModuleType("torchvision.models")
+        sys.modules["torchvision"] = tv; sys.modules["torchvision.models"] = tv.models
+    moddir = os.path.join(REF, "src", "model", "encoder", "modules")
+    parent = types.ModuleType("refmods"); parent.__path__ = [moddir]
+    sys.modules["refmods"] = parent
+    for name in ("networks", "cost_volume"):
+        # networks imports .layers (plain torch) -- load it too
+        pass
+    def load(name):
+        spec = importlib.util.spec_from_file_location(f"refmods.{name}", os.path.join(moddir, f"{name}.py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"refmods.{name}"] = m
+        spec.loader.exec_module(m)
+        return m
+    load("layers")
+    load("networks")
+    return load("cost_volume")
+
+
+def load_fuse_gaussians():
+    """Returns (fuse_gaussians, positional_encoding, GRU) extracted from encoder_freesplat.py /
+    networks.py by AST (the module itself needs timm / jaxtyping to import)."""
+    import torch
+    import torch.nn as nn
+    from einops import rearrange, repeat
+    path = os.path.join(REF, "src", "model", "encoder", "encoder_freesplat.py")
+    tree = ast.parse(open(path).read())
+    ns = {"torch": torch, "nn": nn, "rearrange": rearrange, "repeat": repeat}
+    wanted = []
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "positional_encoding":
+            wanted.append(node)
+        if isinstance(node, ast.ClassDef) and node.name == "EncoderFreeSplat":
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name == "fuse_gaussians":
+                    wanted.append(sub)
+    mod = ast.Module(body=wanted, type_ignores=[])
+    exec(compile(mod, path, "exec"), ns)
+    load_cost_volume_module()
+    GRU = sys.modules["refmods.networks"].GRU
+    return ns["fuse_gaussians"], ns["positional_encoding"], GRU

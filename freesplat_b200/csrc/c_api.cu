@@ -89,4 +89,25 @@ int fs_mark_visible(int32_t P, const float* means3D, const float* view, uint8_t*
   return launch_mark_visible(P, means3D, view, visible, reinterpret_cast<cudaStream_t>(stream));
 }
 
+static int check_cv(const FsCostVolumeArgs* a) {
+  FS_REQUIRE(a != nullptr, "args is NULL");
+  FS_REQUIRE(a->B >= 1 && a->K >= 1 && a->K <= 16 && a->H >= 1 && a->W >= 1 && a->D >= 1, "bad sizes (K must be 1..16)");
+  FS_REQUIRE(a->C == 48, "matching feature width must be 48 (encoder_freesplat.py:160)");
+  FS_REQUIRE((long long)a->H * a->W < (1ll << 30) && a->B <= 65535 && a->D <= 65535 * 8, "feature map too large");
+  FS_REQUIRE(a->cur_feats && a->src_feats && a->proj && a->cur_invK && a->planes && a->mlp, "NULL input");
+  return FS_OK;
+}
+
+int fs_cost_volume_forward(const FsCostVolumeArgs* a, void* stream) {
+  if (int rc = check_cv(a)) return rc;
+  FS_REQUIRE(a->out != nullptr, "out is NULL");
+  return launch_cost_volume_fwd(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_cost_volume_backward(const FsCostVolumeArgs* a, void* stream) {
+  if (int rc = check_cv(a)) return rc;
+  FS_REQUIRE(a->dL_dout && a->dL_dcur && a->dL_dsrc && a->dL_dmlp, "NULL gradient buffer");
+  return launch_cost_volume_bwd(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -25,6 +25,9 @@ int launch_render_bwd(const FsRasterBwdArgs& a, cudaStream_t s);     // raster_r
 int launch_preprocess_bwd(const FsRasterBwdArgs& a, cudaStream_t s); // raster_pre.cu
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* vis, cudaStream_t s);
 
+int launch_cost_volume_fwd(const FsCostVolumeArgs& a, cudaStream_t s);  // cost_volume.cu
+int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s);  // cost_volume.cu
+
 __host__ __device__ inline int tiles_x(int W) { return (W + FS_TILE - 1) / FS_TILE; }
 __host__ __device__ inline int tiles_y(int H) { return (H + FS_TILE - 1) / FS_TILE; }
 

@@ -136,6 +136,31 @@ typedef struct FsRasterBwdArgs {
   float* dL_drotations;        /* [P,4]  or NULL                                 */
 } FsRasterBwdArgs;
 
+/* ------------------------------------------------------------- cost volume */
+/* Fused plane-sweep feature volume (cost_volume.py:429-619).  C must be 48 and the MLP
+ * 49 -> 32 -> 32 -> 1 (cost_volume.py:423-426, encoder_freesplat.py:157-160).               */
+typedef struct FsCostVolumeArgs {
+  int32_t B;               /* reference views (b*v of the encoder)                           */
+  int32_t K;               /* source views per reference view (<= 16)                        */
+  int32_t C, H, W;         /* matching channels (48) and feature-map size                    */
+  int32_t D;               /* depth planes                                                   */
+  const float* cur_feats;  /* [B,C,H,W]                                                      */
+  const float* src_feats;  /* [B,K,C,H,W]                                                    */
+  const float* proj;       /* [B,K,3,4]  rows 0..2 of src_Ks @ src_extrinsics (geometry_utils.py:78) */
+  const float* cur_invK;   /* [B,3,3]    upper-left block of cur_invK                        */
+  const float* planes;     /* [D]        plane depths (cost_volume.py:98-134)                */
+  const float* mlp;        /* packed nn.Linear weights: W0[32,49] b0[32] W1[32,32] b1[32] W2[1,32] b2[1] */
+  float* out;              /* [B,D,H,W]                                                      */
+  /* backward only */
+  const float* dL_dout;    /* [B,D,H,W]                                                      */
+  float* dL_dcur;          /* [B,C,H,W]   (written)                                          */
+  float* dL_dsrc;          /* [B,K,C,H,W] (zeroed by the call, then accumulated)             */
+  float* dL_dmlp;          /* packed like `mlp` (zeroed by the call, then accumulated)       */
+} FsCostVolumeArgs;
+
+int fs_cost_volume_forward(const FsCostVolumeArgs* args, void* stream);
+int fs_cost_volume_backward(const FsCostVolumeArgs* args, void* stream);
+
 int fs_abi_version(void);
 const char* fs_last_error(void);      /* thread-local, valid until the next call  */
 int fs_device_sm_count(void);         /* negative FsStatus on failure             */

@@ -48,6 +48,7 @@ class FsRasterBwdArgs(C.Structure):
 EXPORTS = [
     "fs_abi_version", "fs_last_error", "fs_device_sm_count",
     "fs_raster_forward", "fs_raster_backward", "fs_mark_visible",
+    "fs_cost_volume_forward", "fs_cost_volume_backward",
 ]
 
 _lib = None

@@ -76,25 +76,40 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(FsRasterFwdArgs a, in
   if (a.status[2]) return;
   const int i = blockIdx.x * kThreads + threadIdx.x;
   const int v = blockIdx.y;
-  if (i >= a.P) return;
-  const size_t vi = (size_t)v * a.P + i;
-  // latency-bound kernel: issue every load before the first use (radius, centre, depth are independent)
-  const float4* rec = reinterpret_cast<const float4*>(a.rec) + 3 * vi;
-  const int r = __ldg(a.radii + vi);
-  const float2 xy = __ldg(reinterpret_cast<const float2*>(rec));
-  const float depth = __ldg(reinterpret_cast<const float*>(rec + 2) + 1);
-  if (r <= 0) return;
-  int x0, y0, x1, y1;
-  fsm::get_rect(xy.x, xy.y, r, gx, gy, &x0, &y0, &x1, &y1);
-  const unsigned long long key = ((unsigned long long)__float_as_uint(depth) << 32) | (unsigned long long)(uint32_t)i;
-  const size_t tbase = (size_t)v * gx * gy;
-  for (int ty = y0; ty < y1; ty++)
-    for (int tx = x0; tx < x1; tx++) {
-      const size_t t = tbase + (size_t)ty * gx + tx;
-      const uint32_t start = __ldg(a.ranges + 2 * t);           // independent of the atomic below
-      const uint32_t slot = atomicAdd(a.tile_cursor + t, 1u);
-      a.keybuf[start + slot] = key;
+  const int lane = threadIdx.x & 31;
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  unsigned long long key = 0ull;
+  if (i < a.P) {
+    const size_t vi = (size_t)v * a.P + i;
+    // issue every load before the first use (radius, centre, depth are independent)
+    const float4* rec = reinterpret_cast<const float4*>(a.rec) + 3 * vi;
+    const int r = __ldg(a.radii + vi);
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(rec));
+    const float depth = __ldg(reinterpret_cast<const float*>(rec + 2) + 1);
+    if (r > 0) {
+      fsm::get_rect(xy.x, xy.y, r, gx, gy, &x0, &y0, &x1, &y1);
+      key = ((unsigned long long)__float_as_uint(depth) << 32) | (unsigned long long)(uint32_t)i;
     }
+  }
+  const int my_tiles = (x1 - x0) * (y1 - y0);
+  const int maxn = __reduce_max_sync(0xffffffffu, my_tiles);
+  const size_t tbase = (size_t)v * gx * gy;
+  int tx = x0, ty = y0;
+  // warp-aggregated slot allocation: lanes bound for the same tile share one atomic
+  for (int k = 0; k < maxn; k++) {
+    const bool on = k < my_tiles;
+    const int tile = on ? ty * gx + tx : -1 - lane;
+    const unsigned grp = __match_any_sync(0xffffffffu, tile);
+    const int leader = __ffs(grp) - 1;
+    uint32_t base = 0;
+    if (on && lane == leader) base = atomicAdd(a.tile_cursor + tbase + tile, (uint32_t)__popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (on) {
+      const uint32_t start = __ldg(a.ranges + 2 * (tbase + tile));
+      a.keybuf[start + base + (uint32_t)__popc(grp & ((1u << lane) - 1u))] = key;
+    }
+    if (++tx == x1) { tx = x0; ty++; }
+  }
 }
 
 // ---- 4. per-tile sort -------------------------------------------------------------------------

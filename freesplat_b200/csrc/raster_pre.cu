@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(FsRasterFwdArgs
     const size_t vi = (size_t)v * a.P + i;
     const float* __restrict__ view = a.views + (size_t)v * kViewFloats;
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = make_float4(0.f, 0.f, -3.0e38f, -3.0e38f);
+    int my_tiles = 0, rx0 = 0, ry0 = 0, rw = 1;
     if (active) {
       const float* __restrict__ proj = view + 16;
       const float tanx = view[38], tany = view[39], sscale = view[40];
@@ -100,14 +101,27 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(FsRasterFwdArgs
         r1 = make_float4(pr.con_z, opacity, rgb[0], rgb[1]);
         r2 = make_float4(rgb[2], pr.depth, hx, hy);
         ntiles = (uint32_t)((pr.x1 - pr.x0) * (pr.y1 - pr.y0));
-        // per-tile population count (tile ranges come from a scan over these counters)
-        uint32_t* __restrict__ cnt = a.tile_count + (size_t)v * gx * gy;
-        for (int ty = pr.y0; ty < pr.y1; ty++)
-          for (int tx = pr.x0; tx < pr.x1; tx++) atomicAdd(cnt + ty * gx + tx, 1u);
+        rx0 = pr.x0; ry0 = pr.y0; rw = pr.x1 - pr.x0;
       }
       a.radii[vi] = pr.radius;
       if (a.tiles_touched) a.tiles_touched[vi] = ntiles;
       a.clamped[vi] = (uint8_t)clampmask;
+      my_tiles = (int)ntiles;
+    }
+    // per-tile population count (tile ranges come from a scan over these counters).  Neighbouring
+    // Gaussians mostly land in the same tile, so lanes are grouped by tile (match.any) and one lane
+    // per group issues a single add: same-address atomics no longer serialise 32 deep.
+    {
+      uint32_t* __restrict__ cnt = a.tile_count + (size_t)v * gx * gy;
+      const int maxn = __reduce_max_sync(0xffffffffu, my_tiles);
+      int tx = rx0, ty = ry0;
+      for (int k = 0; k < maxn; k++) {
+        const bool on = k < my_tiles;
+        const int tile = on ? ty * gx + tx : -1 - (int)(threadIdx.x & 31);
+        const unsigned grp = __match_any_sync(0xffffffffu, tile);
+        if (on && (int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(cnt + tile, (uint32_t)__popc(grp));
+        if (++tx == rx0 + rw) { tx = rx0; ty++; }
+      }
     }
     // records: through shared memory so that the block writes contiguous 16-byte chunks
     s_out[tid * 3 + 0] = r0; s_out[tid * 3 + 1] = r1; s_out[tid * 3 + 2] = r2;

@@ -209,3 +209,55 @@ def cost_volume_mlp(seed: int = 0, C: int = 48):
         return (torch.rand((o, i), generator=g) * 2 - 1) * bound, (torch.rand((o,), generator=g) * 2 - 1) * bound
     W0, b0 = lin(32, C + 1); W1, b1 = lin(32, 32); W2, b2 = lin(1, 32)
     return [W0, b0, W1, b1, W2, b2]
+
+
+# ------------------------------------------------------------------------------------------------
+# Pixel-wise Triplet Fusion inputs, shaped as EncoderFreeSplat.forward passes them to fuse_gaussians
+# (encoder_freesplat.py:299-368): a smooth analytic surface seen by V cameras, so that neighbouring
+# views really do observe the same points (depth-consistent matches) -- plus noise so some do not.
+def _surface_depth(c2w: torch.Tensor, K_norm: torch.Tensor, h: int, w: int, iters: int = 12) -> torch.Tensor:
+    fx, fy, cx, cy = K_norm[0, 0] * w, K_norm[1, 1] * h, K_norm[0, 2] * w, K_norm[1, 2] * h
+    ii, jj = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    dcam = torch.stack([(jj - cx) / fx, (ii - cy) / fy, torch.ones_like(ii)], -1).reshape(-1, 3)   # z = 1 rays
+    dw = dcam @ c2w[:3, :3].T
+    o = c2w[:3, 3]
+    g = lambda x, y: 2.6 + 0.35 * torch.sin(1.7 * x + 0.3) * torch.cos(1.3 * y) + 0.15 * x
+    t = torch.full((h * w,), 2.6)
+    for _ in range(iters):
+        pt = o + t[:, None] * dw
+        t = (g(pt[:, 0], pt[:, 1]) - o[2]) / dw[:, 2]
+    return t.reshape(h, w)            # camera-space depth (ray has z = 1 in camera coordinates)
+
+
+def ptf_inputs(seed: int = 0, n_views: int = 3, h: int = 24, w: int = 32, feat_dim: int = 64, noise: float = 0.04,
+               spacing: float = 0.2):
+    g = torch.Generator().manual_seed(seed)
+    V = n_views
+    ext = camera_path(V, spacing=spacing)
+    Kn = intrinsics(V)
+    depths, coords = [], []
+    for v in range(V):
+        d = _surface_depth(ext[v], Kn[v], h, w)
+        d = d + noise * torch.randn((h, w), generator=g) * (torch.rand((h, w), generator=g) < 0.5)
+        depths.append(d)
+        coords.append(backproject(d, Kn[v], ext[v]))
+    depths = torch.stack(depths)                                    # [V,h,w]
+    coords = torch.stack(coords)                                    # [V,hw,3]
+    feats = torch.randn((1, V, h * w, feat_dim), generator=g) * 0.5
+    dens = torch.sigmoid(torch.randn((1, V, h * w, 1, 1), generator=g))
+    wemb = torch.rand((1, V, h * w, 1, 1), generator=g)
+    return dict(gaussians=[feats], coords=[coords[None, :, :, None, None, :].contiguous()], densities=dens,
+                weight_emb=wemb, depths=depths[:, None].contiguous(), extrinsics=ext[None].contiguous(),
+                intrinsics=Kn[None].contiguous(), image_shape=(h, w))
+
+
+def gru_state(seed: int = 0):
+    """Seeded weights of networks.GRU (176->64->64 x2, 152->64->64), as a state_dict."""
+    g = torch.Generator().manual_seed(2000 + seed)
+    sd = {}
+    for name, din in (("mlp_z", 176), ("mlp_r", 176), ("mlp_n", 152)):
+        for idx, (o, i) in ((0, (64, din)), (2, (64, 64))):
+            b = 1.0 / math.sqrt(i)
+            sd[f"{name}.{idx}.weight"] = (torch.rand((o, i), generator=g) * 2 - 1) * b
+            sd[f"{name}.{idx}.bias"] = (torch.rand((o,), generator=g) * 2 - 1) * b
+    return sd

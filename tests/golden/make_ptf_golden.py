@@ -1,0 +1,40 @@
+"""Generates tests/golden/ptf_*.npz by running the REFERENCE's own fuse_gaussians
+(/root/reference/src/model/encoder/encoder_freesplat.py:431-522, extracted unmodified by ref_loader,
+with the reference's GRU from modules/networks.py:188-214) on seeded inputs.
+Run in the build container:  python tests/golden/make_ptf_golden.py"""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from freesplat_b200 import synth  # noqa: E402
+from tests.golden import ref_loader  # noqa: E402
+
+CASES = {"ptf_v3": (0, 3, 16, 24), "ptf_v4": (1, 4, 12, 20), "ptf_v2_far": (2, 2, 16, 16)}
+
+
+def main():
+    fuse, pe, GRU = ref_loader.load_fuse_gaussians()
+    for name, (seed, V, h, w) in CASES.items():
+        inp = synth.ptf_inputs(seed, V, h, w, spacing=0.9 if "far" in name else 0.2)
+        gru = GRU()
+        gru.load_state_dict(synth.gru_state(seed))
+        self = SimpleNamespace(gru=gru)
+        with torch.no_grad():
+            feats, coords, extr, depths = fuse(self, inp["gaussians"], inp["coords"], inp["densities"], inp["weight_emb"],
+                                               inp["depths"], inp["extrinsics"], inp["intrinsics"], inp["image_shape"])
+        np.savez_compressed(
+            os.path.join(ROOT, "tests", "golden", name + ".npz"), meta=np.array([seed, V, h, w]),
+            in_feats=inp["gaussians"][0].numpy(), in_coords=inp["coords"][0].numpy(), in_dens=inp["densities"].numpy(),
+            in_wemb=inp["weight_emb"].numpy(), in_depths=inp["depths"].numpy(), in_ext=inp["extrinsics"].numpy(),
+            in_K=inp["intrinsics"].numpy(), out_feats=feats.numpy(), out_coords=coords.numpy(), out_ext=extr.numpy(),
+            out_depths=depths.numpy())
+        print(name, "N_out", feats.shape[1], "of", V * h * w)
+
+
+if __name__ == "__main__":
+    main()

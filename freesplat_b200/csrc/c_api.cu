@@ -110,4 +110,25 @@ int fs_cost_volume_backward(const FsCostVolumeArgs* a, void* stream) {
   return launch_cost_volume_bwd(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+static int check_ptf(const FsPtfArgs* a) {
+  FS_REQUIRE(a != nullptr, "args is NULL");
+  FS_REQUIRE(a->H >= 1 && a->W >= 1 && a->F >= 1 && a->n_upper >= 0, "bad sizes");
+  FS_REQUIRE((long long)a->H * a->W < (1ll << 30), "image too large");
+  FS_REQUIRE(a->coords && a->counts_in && a->v_depth && a->E_inv && a->K_px && a->zbuf && a->pix && a->zeta && a->match &&
+                 a->append && a->block_counts && a->pair_j && a->pair_p && a->counts_out, "NULL buffer");
+  return FS_OK;
+}
+
+int fs_ptf_match(const FsPtfArgs* a, void* stream) {
+  if (int rc = check_ptf(a)) return rc;
+  return launch_ptf_match(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_ptf_merge(const FsPtfArgs* a, void* stream) {
+  if (int rc = check_ptf(a)) return rc;
+  FS_REQUIRE(a->feats && a->dens && a->wemb && a->ext && a->depth && a->v_feats && a->v_coords && a->v_dens && a->v_wemb &&
+                 a->v_ext && a->o_feats && a->o_coords && a->o_dens && a->o_wemb && a->o_ext && a->o_depth, "NULL state buffer");
+  return launch_ptf_merge(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -28,6 +28,9 @@ int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t*
 int launch_cost_volume_fwd(const FsCostVolumeArgs& a, cudaStream_t s);  // cost_volume.cu
 int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s);  // cost_volume.cu
 
+int launch_ptf_match(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
+int launch_ptf_merge(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
+
 __host__ __device__ inline int tiles_x(int W) { return (W + FS_TILE - 1) / FS_TILE; }
 __host__ __device__ inline int tiles_y(int H) { return (H + FS_TILE - 1) / FS_TILE; }
 

@@ -161,6 +161,52 @@ typedef struct FsCostVolumeArgs {
 int fs_cost_volume_forward(const FsCostVolumeArgs* args, void* stream);
 int fs_cost_volume_backward(const FsCostVolumeArgs* args, void* stream);
 
+/* --------------------------------------------------------------------- PTF */
+/* One fold step of EncoderFreeSplat.fuse_gaussians (encoder_freesplat.py:443-519): global state of
+ * N Gaussians (SoA) + view i  ->  new state.  fs_ptf_match projects / z-buffers / matches and leaves
+ * the matched pairs (pair_j, pair_p) and the counters on the device; the caller runs the GRU
+ * (networks.py:188-214, plain GEMMs) on those pairs and then calls fs_ptf_merge, which writes the new
+ * state in the reference's order: [kept] ++ [fused] ++ [unmatched pixels of view i].            */
+typedef struct FsPtfArgs {
+  int32_t H, W;            /* image size of view i (pixel grid of the candidates)            */
+  int32_t F;               /* latent feature width (64)                                      */
+  int32_t n_upper;         /* host-side upper bound of N (grid sizing); N itself is counts_in[0] */
+  float depth_thres;       /* 0.1 (encoder_freesplat.py:432)                                 */
+  /* current global state, capacity >= n_upper */
+  const float* feats;      /* [N,F]  */
+  const float* coords;     /* [N,3]  */
+  const float* dens;       /* [N]    */
+  const float* wemb;       /* [N]    */
+  const float* ext;        /* [N,16] per-Gaussian (averaged) camera-to-world matrix          */
+  const float* depth;      /* [N]    */
+  const int32_t* counts_in;/* [>=1]  counts_in[0] = N                                        */
+  /* view i */
+  const float* v_feats;    /* [HW,F] */
+  const float* v_coords;   /* [HW,3] */
+  const float* v_dens;     /* [HW]   */
+  const float* v_wemb;     /* [HW]   */
+  const float* v_depth;    /* [HW]   predicted depth map of view i                           */
+  const float* v_ext;      /* [16]   camera-to-world of view i                               */
+  const float* E_inv;      /* [16]   its inverse (row-major)                                 */
+  const float* K_px;       /* [9]    pixel-space intrinsics of view i                        */
+  /* scratch */
+  uint32_t* zbuf;          /* [HW]   */
+  int32_t* pix;            /* [n_upper] */
+  float* zeta;             /* [n_upper] */
+  uint8_t* match;          /* [n_upper] */
+  uint8_t* append;         /* [HW]   */
+  int32_t* block_counts;   /* [3*ceil(max(n_upper,HW)/1024)] */
+  int32_t* pair_j;         /* [n_upper] matched global index, ascending                      */
+  int32_t* pair_p;         /* [n_upper] partner pixel of view i                              */
+  int32_t* counts_out;     /* [8] {N_in, n_keep, n_match, n_append, N_out, ...}              */
+  /* merge inputs / outputs */
+  const float* gru_out;    /* [n_match,F] fused features of the matched pairs                */
+  float* o_feats; float* o_coords; float* o_dens; float* o_wemb; float* o_ext; float* o_depth;
+} FsPtfArgs;
+
+int fs_ptf_match(const FsPtfArgs* args, void* stream);
+int fs_ptf_merge(const FsPtfArgs* args, void* stream);
+
 int fs_abi_version(void);
 const char* fs_last_error(void);      /* thread-local, valid until the next call  */
 int fs_device_sm_count(void);         /* negative FsStatus on failure             */

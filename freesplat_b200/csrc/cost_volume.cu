@@ -194,10 +194,266 @@ int launch_cost_volume_fwd(const FsCostVolumeArgs& a, cudaStream_t s) {
 
 }  // namespace fs
 
+// =================================================================================== backward
+// Gradients w.r.t. cur_feats, src_feats and the MLP parameters (poses / intrinsics get none in the
+// reference's training path).  Per block: 128 reference pixels x a chunk of planes.
+//   phase A (thread = pixel): recompute the forward row, back-propagate through the MLP in registers
+//            -> dx[49]; scatter d(warped) to dL_dsrc with red.global.add (neighbouring lanes hit
+//            neighbouring texels), accumulate dL_dcur in registers; park the row's (dz1, x, dz2, a1, g*a2, g)
+//            in shared memory;
+//   phase B (thread = (output o, input slice)): dW += sum over the 128 rows of the outer products,
+//            operands broadcast from shared memory as float4, ~21 accumulators per thread kept in
+//            registers across all planes; one atomicAdd per parameter and block at the end.
 namespace fs {
-int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s) {
-  (void)a; (void)s;
-  set_error("fs_cost_volume_backward: not implemented yet");
-  return FS_ERR_UNSUPPORTED;
+
+constexpr int kRowStride = 196;                  // floats per parked row (16-byte aligned segments)
+constexpr int kOffDz1 = 0, kOffX = 32, kOffDz2 = 84, kOffA1 = 116, kOffGa2 = 148, kOffG = 180;
+
+struct CvBwdSmem {
+  float W0t[kCvIn][kCvHid];
+  float W1t[kCvHid][kCvHid];
+  float W0[kCvHid][kCvIn + 3];                   // row-major copy for dx = W0^T dz1 (padded to 52)
+  float W1[kCvHid][kCvHid];
+  float W2[kCvHid];
+  float b0[kCvHid];
+  float b1[kCvHid];
+  float b2;
+  float proj[16 * 12];
+};
+
+__device__ __forceinline__ float dleaky(float z) { return z > 0.f ? 1.f : 0.01f; }
+
+__global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolumeArgs a, int planes_per_block) {
+  extern __shared__ __align__(16) unsigned char cv_smem_raw[];
+  CvBwdSmem& sm = *reinterpret_cast<CvBwdSmem*>(cv_smem_raw);
+  float* rows = reinterpret_cast<float*>(cv_smem_raw + ((sizeof(CvBwdSmem) + 15) / 16) * 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z;
+  const int H = a.H, W = a.W, K = a.K;
+  const size_t HW = (size_t)H * W;
+  {
+    const float* w = a.mlp;
+    for (int k = tid; k < kCvHid * kCvIn; k += kCvThreads) { const int o = k / kCvIn, i = k - o * kCvIn; sm.W0t[i][o] = w[k]; sm.W0[o][i] = w[k]; }
+    for (int k = tid; k < kCvHid * 3; k += kCvThreads) sm.W0[k / 3][kCvIn + (k % 3)] = 0.f;
+    w += kCvHid * kCvIn;
+    for (int k = tid; k < kCvHid; k += kCvThreads) sm.b0[k] = w[k];
+    w += kCvHid;
+    for (int k = tid; k < kCvHid * kCvHid; k += kCvThreads) { const int o = k / kCvHid, i = k - o * kCvHid; sm.W1t[i][o] = w[k]; sm.W1[o][i] = w[k]; }
+    w += kCvHid * kCvHid;
+    for (int k = tid; k < kCvHid; k += kCvThreads) sm.b1[k] = w[k];
+    w += kCvHid;
+    for (int k = tid; k < kCvHid; k += kCvThreads) sm.W2[k] = w[k];
+    w += kCvHid;
+    if (tid == 0) sm.b2 = w[0];
+    for (int k = tid; k < K * 12; k += kCvThreads) sm.proj[k] = a.proj[(size_t)b * K * 12 + k];
+  }
+  __syncthreads();
+  const int p = blockIdx.x * kCvThreads + tid;
+  const bool active = p < (int)HW;
+  const int pc = active ? p : 0;
+  const int v = pc / W, u = pc - v * W;
+  const float uvx = 1.0f / (float)W, uvy = 1.0f / (float)H;
+  const float* ik = a.cur_invK + (size_t)b * 9;
+  const float pu = (float)u + 0.5f, pv = (float)v + 0.5f;
+  const float r0 = fmaf(ik[1], pv, ik[0] * pu) + ik[2];
+  const float r1 = fmaf(ik[4], pv, ik[3] * pu) + ik[5];
+  const float r2 = fmaf(ik[7], pv, ik[6] * pu) + ik[8];
+  float cur[kCvC], dcur[kCvC];
+  {
+    const float* cb = a.cur_feats + (size_t)b * kCvC * HW + pc;
+#pragma unroll
+    for (int c = 0; c < kCvC; c++) { cur[c] = __ldg(cb + (size_t)c * HW); dcur[c] = 0.f; }
+  }
+  const float* src_b = a.src_feats + (size_t)b * K * kCvC * HW;
+  float* dsrc_b = a.dL_dsrc + (size_t)b * K * kCvC * HW;
+  const unsigned all = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+  const int d0 = blockIdx.y * planes_per_block, d1 = min(a.D, d0 + planes_per_block);
+  float* myrow = rows + (size_t)tid * kRowStride;
+
+  // phase-B accumulators.  warp 0..2: dW0[o=lane][16*warp .. +16) and dW1[lane][4*warp .. +4);
+  // warp 3: dW0[lane][48], dW1[lane][12..32), db0[lane], db1[lane], dW2[lane] (+ db2 in lane 0)
+  float accA[16], accB[20], acc_b0 = 0.f, acc_b1 = 0.f, acc_w2 = 0.f, acc_b2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; k++) accA[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 20; k++) accB[k] = 0.f;
+
+  for (int d = d0; d < d1; d++) {
+    // ------------------------------------------------------------------ phase A
+    float g = 0.f;
+    if (active) g = __ldg(a.dL_dout + ((size_t)b * a.D + d) * HW + p);
+    {
+      const float zd = __ldg(a.planes + d);
+      const float X0 = zd * r0, X1 = zd * r1, X2 = zd * r2;
+      float x[kCvC];
+      float dsum;
+      unsigned geo, zero;
+      gather_sources(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, all, x, dsum, geo, zero);
+      const unsigned valid = geo & ~zero;
+      if (zero) { float ds2; unsigned g2, z2; gather_sources(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, valid, x, ds2, g2, z2); }
+      const float rn = 1.0f / ((float)__popc(valid) + 1e-8f);
+      float z1[kCvHid], z2v[kCvHid];
+#pragma unroll
+      for (int o = 0; o < kCvHid; o++) z1[o] = sm.b0[o];
+#pragma unroll
+      for (int i = 0; i < kCvC; i++) {
+        x[i] = x[i] * rn;
+#pragma unroll
+        for (int o = 0; o < kCvHid; o++) z1[o] = fmaf(sm.W0t[i][o], x[i], z1[o]);
+      }
+      const float xdot = dsum * rn;
+#pragma unroll
+      for (int o = 0; o < kCvHid; o++) z1[o] = fmaf(sm.W0t[kCvC][o], xdot, z1[o]);
+#pragma unroll
+      for (int o = 0; o < kCvHid; o++) z2v[o] = sm.b1[o];
+#pragma unroll
+      for (int i = 0; i < kCvHid; i++) {
+        const float hi = leaky(z1[i]);
+#pragma unroll
+        for (int o = 0; o < kCvHid; o++) z2v[o] = fmaf(sm.W1t[i][o], hi, z2v[o]);
+      }
+      // park x, a1, g*a2, g ; then dz2, dz1
+#pragma unroll
+      for (int i = 0; i < kCvC; i++) myrow[kOffX + i] = x[i];
+      myrow[kOffX + kCvC] = xdot; myrow[kOffX + 49] = 0.f; myrow[kOffX + 50] = 0.f; myrow[kOffX + 51] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kCvHid; i++) { myrow[kOffA1 + i] = leaky(z1[i]); myrow[kOffGa2 + i] = g * leaky(z2v[i]); }
+      myrow[kOffG] = g;
+      // dz2 = g * W2 * lk'(z2)
+#pragma unroll
+      for (int i = 0; i < kCvHid; i++) { z2v[i] = g * sm.W2[i] * dleaky(z2v[i]); myrow[kOffDz2 + i] = z2v[i]; }
+      // da1[i] = sum_o W1[o][i] dz2[o] ; dz1 = da1 * lk'(z1)
+      float da1[kCvHid];
+#pragma unroll
+      for (int i = 0; i < kCvHid; i++) da1[i] = 0.f;
+#pragma unroll
+      for (int o = 0; o < kCvHid; o++) {
+#pragma unroll
+        for (int i = 0; i < kCvHid; i++) da1[i] = fmaf(sm.W1[o][i], z2v[o], da1[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < kCvHid; i++) { z1[i] = da1[i] * dleaky(z1[i]); myrow[kOffDz1 + i] = z1[i]; }
+      // dx[i] = sum_o W0[o][i] dz1[o]   (x[] reused as dx[])
+      float dxdot = 0.f;
+#pragma unroll
+      for (int i = 0; i < kCvC; i++) x[i] = 0.f;
+#pragma unroll
+      for (int o = 0; o < kCvHid; o++) {
+#pragma unroll
+        for (int i = 0; i < kCvC; i++) x[i] = fmaf(sm.W0[o][i], z1[o], x[i]);
+        dxdot = fmaf(sm.W0[o][kCvC], z1[o], dxdot);
+      }
+      // ---- back through the masked means: dw_k[c] = [valid_k] dx[c]/n + [geo_k] cur[c] dxdot/n
+      if (active && g != 0.f) {
+        const float gd = dxdot * rn;
+        for (int k = 0; k < K; k++) {
+          if (!((geo >> k) & 1u)) continue;
+          Taps t;
+          make_taps(sm.proj + 12 * k, X0, X1, X2, H, W, uvx, uvy, t);
+          const float fv = ((valid >> k) & 1u) ? rn : 0.f;
+          const float* __restrict__ s = src_b + (size_t)k * kCvC * HW;
+          float* __restrict__ ds = dsrc_b + (size_t)k * kCvC * HW;
+#pragma unroll
+          for (int c = 0; c < kCvC; c++) {
+            const float gw = fmaf(x[c], fv, cur[c] * gd);
+            float* dc = ds + (size_t)c * HW;
+            if (t.w00 != 0.f) atomicAdd(dc + t.o00, t.w00 * gw);
+            if (t.w01 != 0.f) atomicAdd(dc + t.o01, t.w01 * gw);
+            if (t.w10 != 0.f) atomicAdd(dc + t.o10, t.w10 * gw);
+            if (t.w11 != 0.f) atomicAdd(dc + t.o11, t.w11 * gw);
+            // d dot_k / d cur[c] = w_k[c]  (re-gathered: cheaper than keeping K x 48 registers)
+            const float* __restrict__ sc = s + (size_t)c * HW;
+            const float wk = fmaf(t.w11, __ldg(sc + t.o11), fmaf(t.w10, __ldg(sc + t.o10), fmaf(t.w01, __ldg(sc + t.o01), t.w00 * __ldg(sc + t.o00))));
+            dcur[c] = fmaf(gd, wk, dcur[c]);
+          }
+        }
+      }
+      if (!active || g == 0.f) {   // rows that must not contribute to the parameter gradients
+        if (!active) {
+#pragma unroll
+          for (int i = 0; i < kCvHid; i++) { myrow[kOffDz1 + i] = 0.f; myrow[kOffDz2 + i] = 0.f; myrow[kOffGa2 + i] = 0.f; }
+          myrow[kOffG] = 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ phase B
+    if (warp < 3) {
+      for (int r = 0; r < kCvThreads; r++) {
+        const float* row = rows + (size_t)r * kRowStride;
+        const float dz1 = row[kOffDz1 + lane], dz2 = row[kOffDz2 + lane];
+        const float4* xr = reinterpret_cast<const float4*>(row + kOffX + 16 * warp);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const float4 xv = xr[q];
+          accA[4 * q + 0] = fmaf(dz1, xv.x, accA[4 * q + 0]); accA[4 * q + 1] = fmaf(dz1, xv.y, accA[4 * q + 1]);
+          accA[4 * q + 2] = fmaf(dz1, xv.z, accA[4 * q + 2]); accA[4 * q + 3] = fmaf(dz1, xv.w, accA[4 * q + 3]);
+        }
+        const float4 av = *reinterpret_cast<const float4*>(row + kOffA1 + 4 * warp);
+        accB[0] = fmaf(dz2, av.x, accB[0]); accB[1] = fmaf(dz2, av.y, accB[1]);
+        accB[2] = fmaf(dz2, av.z, accB[2]); accB[3] = fmaf(dz2, av.w, accB[3]);
+      }
+    } else {
+      for (int r = 0; r < kCvThreads; r++) {
+        const float* row = rows + (size_t)r * kRowStride;
+        const float dz1 = row[kOffDz1 + lane], dz2 = row[kOffDz2 + lane];
+        accA[0] = fmaf(dz1, row[kOffX + kCvC], accA[0]);
+        acc_b0 += dz1; acc_b1 += dz2;
+        acc_w2 += row[kOffGa2 + lane];
+        acc_b2 += row[kOffG];
+        const float4* ar = reinterpret_cast<const float4*>(row + kOffA1 + 12);
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+          const float4 av = ar[q];
+          accB[4 * q + 0] = fmaf(dz2, av.x, accB[4 * q + 0]); accB[4 * q + 1] = fmaf(dz2, av.y, accB[4 * q + 1]);
+          accB[4 * q + 2] = fmaf(dz2, av.z, accB[4 * q + 2]); accB[4 * q + 3] = fmaf(dz2, av.w, accB[4 * q + 3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- flush dL_dcur (several plane chunks add to the same pixel) ----
+  if (active) {
+    float* dc = a.dL_dcur + (size_t)b * kCvC * HW + p;
+#pragma unroll
+    for (int c = 0; c < kCvC; c++) if (dcur[c] != 0.f) atomicAdd(dc + (size_t)c * HW, dcur[c]);
+  }
+  // ---- flush parameter gradients: packed layout W0[32,49] b0[32] W1[32,32] b1[32] W2[32] b2[1] ----
+  float* gW0 = a.dL_dmlp;
+  float* gb0 = gW0 + kCvHid * kCvIn;
+  float* gW1 = gb0 + kCvHid;
+  float* gb1 = gW1 + kCvHid * kCvHid;
+  float* gW2 = gb1 + kCvHid;
+  float* gb2 = gW2 + kCvHid;
+  if (warp < 3) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) atomicAdd(gW0 + lane * kCvIn + 16 * warp + k, accA[k]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) atomicAdd(gW1 + lane * kCvHid + 4 * warp + k, accB[k]);
+  } else {
+    atomicAdd(gW0 + lane * kCvIn + kCvC, accA[0]);
+#pragma unroll
+    for (int k = 0; k < 20; k++) atomicAdd(gW1 + lane * kCvHid + 12 + k, accB[k]);
+    atomicAdd(gb0 + lane, acc_b0); atomicAdd(gb1 + lane, acc_b1); atomicAdd(gW2 + lane, acc_w2);
+    if (lane == 0) atomicAdd(gb2, acc_b2);
+  }
 }
+
+int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s) {
+  const size_t HW = (size_t)a.H * a.W;
+  const int ppb = 16;
+  int rc;
+  const size_t n_src = (size_t)a.B * a.K * kCvC * HW, n_cur = (size_t)a.B * kCvC * HW;
+  const size_t n_mlp = kCvHid * kCvIn + kCvHid + kCvHid * kCvHid + kCvHid + kCvHid + 1;
+  if ((rc = check_cuda(cudaMemsetAsync(a.dL_dsrc, 0, n_src * sizeof(float), s), "memset dL_dsrc"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(a.dL_dcur, 0, n_cur * sizeof(float), s), "memset dL_dcur"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(a.dL_dmlp, 0, n_mlp * sizeof(float), s), "memset dL_dmlp"))) return rc;
+  const size_t smem = ((sizeof(CvBwdSmem) + 15) / 16) * 16 + (size_t)kCvThreads * kRowStride * sizeof(float);
+  if ((rc = check_cuda(cudaFuncSetAttribute(cost_volume_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute(cost_volume_bwd_kernel)"))) return rc;
+  dim3 grid((unsigned)((HW + kCvThreads - 1) / kCvThreads), (unsigned)((a.D + ppb - 1) / ppb), (unsigned)a.B);
+  cost_volume_bwd_kernel<<<grid, kCvThreads, smem, s>>>(a, ppb);
+  return check_cuda(cudaGetLastError(), "cost_volume_bwd_kernel");
+}
+
 }  // namespace fs

@@ -76,3 +76,23 @@ def test_exact_zero_dot_rule():
     with torch.no_grad():
         out = m(**{k: v.to(dev) for k, v in inp.items()})
     assert _close(out.cpu().numpy(), want.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_backward_vs_reference_golden(path):
+    """Gradients of sum(out * wts) w.r.t. cur_feats, src_feats and the six MLP tensors against the
+    reference's own autograd (grid_sample backward etc.), stored in the golden file."""
+    z = np.load(path)
+    seed, V, K, C, Hf, Wf, D = [int(x) for x in z["meta"]]
+    dev = "cuda:0"
+    t = lambda k: torch.from_numpy(z[k]).to(dev)
+    m = _module(Hf, Wf, D, [torch.from_numpy(z[f"mlp{i}"]) for i in range(6)], dev)
+    cur = t("cur_feats").requires_grad_(True); src = t("src_feats").requires_grad_(True)
+    out = m(cur_feats=cur, src_feats=src, src_extrinsics=t("src_extrinsics"), src_poses=t("src_poses"), src_Ks=t("src_Ks"),
+            cur_invK=t("cur_invK"), min_depth=t("min_depth"), max_depth=t("max_depth"))
+    (out * t("wts")).sum().backward()
+    params = [m.mlp.net[0].weight, m.mlp.net[0].bias, m.mlp.net[2].weight, m.mlp.net[2].bias, m.mlp.net[4].weight, m.mlp.net[4].bias]
+    for name, got, want in [("cur", cur.grad, z["g_cur"]), ("src", src.grad, z["g_src"])] + \
+            [(f"mlp{i}", p.grad, z[f"g_mlp{i}"]) for i, p in enumerate(params)]:
+        assert got is not None, name
+        assert _close(got.cpu().numpy(), want) < 2e-4, (name, _close(got.cpu().numpy(), want))

@@ -1,0 +1,63 @@
+"""Times the cost volume (fwd, fwd+bwd) and PTF at BASELINE config-3/4 sizes on cuda:0; JSON to gpurun_out/."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+from freesplat_b200 import ptf, synth  # noqa: E402
+from freesplat_b200.cost_volume import AVGFeatureVolumeManager  # noqa: E402
+
+dev = "cuda:0"
+res = {}
+
+
+def timeit(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+for V, K in ((3, 2), (10, 8)):
+    Hf, Wf, D = 120, 160, 128
+    inp = {k: v.to(dev) for k, v in synth.cost_volume_inputs(0, V, K, 48, Hf, Wf).items()}
+    m = AVGFeatureVolumeManager(Hf, Wf, num_depth_bins=D, matching_dim_size=48).to(dev)
+    with torch.no_grad():
+        f = timeit(lambda: m(**inp))
+    cur = inp["cur_feats"].clone().requires_grad_(True); src = inp["src_feats"].clone().requires_grad_(True)
+    inp2 = dict(inp, cur_feats=cur, src_feats=src)
+
+    def fb():
+        out = m(**inp2)
+        out.sum().backward()
+    fbt = timeit(fb, n=3, warm=1)
+    rows = V * D * Hf * Wf
+    res[f"cost_volume_V{V}_K{K}"] = {"fwd_ms": f, "fwd_bwd_ms": fbt, "fwd_tflops": rows * (2 * 2624 + K * 480) / (f * 1e-3) / 1e12,
+                                     "alg_bytes_fwd": ((1 + K) * 48 * Hf * Wf * 4 + D * Hf * Wf * 4) * V}
+
+from test_ptf_gpu import GRU  # noqa: E402
+for V in (3, 10):
+    h, w = 480, 640
+    inp = synth.ptf_inputs(0, V, h, w)
+    from ptf_helpers import flat_inputs  # noqa: E402
+    feats, coords, dens, wemb, depths, ext, K, hw = flat_inputs(inp)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    g = GRU(); g.load_state_dict(synth.gru_state(0)); g = g.to(dev)
+    args = [t(x) for x in (feats, coords, dens, wemb, depths, ext, K)]
+    with torch.no_grad():
+        out = ptf.fuse_views(g, *args, hw)
+        ms = timeit(lambda: ptf.fuse_views(g, *args, hw), n=3, warm=1)
+    N = out[0].shape[0]
+    res[f"ptf_V{V}_640x480"] = {"ms": ms, "N_out": N, "ratio": N / (V * h * w),
+                                "alg_bytes": 280 * h * w * V + 344 * N}
+print(json.dumps(res, indent=1))
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_ops.json"), "w"), indent=1)

@@ -55,10 +55,97 @@ class _State:
         self.feats, self.coords, self.dens, self.wemb, self.ext, self.depth = e(cap, F), e(cap, 3), e(cap), e(cap), e(cap, 16), e(cap)
 
 
+def _ptf_args(h, w, F, n_upper, depth_thres, state, cin, view, scratch, counts_out, out=None, gru_out=None):
+    feats, coords, dens, wemb, ext, depth = state
+    v_feats, v_coords, v_dens, v_wemb, v_depth, v_ext, E_inv, K_px = view
+    zbuf, pix, zeta, match, append, block_counts, pair_j, pair_p = scratch
+    o = out if out is not None else (None,) * 6
+    return FsPtfArgs(
+        H=h, W=w, F=F, n_upper=n_upper, depth_thres=depth_thres,
+        feats=ptr(feats), coords=ptr(coords), dens=ptr(dens), wemb=ptr(wemb), ext=ptr(ext), depth=ptr(depth),
+        counts_in=ptr(cin), v_feats=ptr(v_feats), v_coords=ptr(v_coords), v_dens=ptr(v_dens), v_wemb=ptr(v_wemb),
+        v_depth=ptr(v_depth), v_ext=ptr(v_ext), E_inv=ptr(E_inv), K_px=ptr(K_px),
+        zbuf=ptr(zbuf), pix=ptr(pix), zeta=ptr(zeta), match=ptr(match), append=ptr(append), block_counts=ptr(block_counts),
+        pair_j=ptr(pair_j), pair_p=ptr(pair_p), counts_out=ptr(counts_out), gru_out=ptr(gru_out),
+        o_feats=ptr(o[0]), o_coords=ptr(o[1]), o_dens=ptr(o[2]), o_wemb=ptr(o[3]), o_ext=ptr(o[4]), o_depth=ptr(o[5]))
+
+
+class _PtfMerge(torch.autograd.Function):
+    """Differentiable wrapper of fs_ptf_merge (training path).  forward = the compaction / merge kernel;
+    backward routes gradients through the saved index maps (kept -> old state, appended -> view i,
+    fused -> both, including the derivative of the density-weighted means w.r.t. the densities)."""
+
+    @staticmethod
+    def forward(ctx, feats, coords, dens, wemb, ext, depth, v_feats, v_coords, v_dens, v_wemb, v_depth, gru_out, meta):
+        L = _lib.lib()
+        (h, w, depth_thres, cin, v_ext, E_inv, K_px, scratch, counts_row, c) = meta
+        N, nk, M, na, N_out = c[0], c[1], c[2], c[3], c[4]
+        dev = feats.device
+        F = feats.shape[1]
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        out = (e(N_out, F), e(N_out, 3), e(N_out), e(N_out), e(N_out, 16), e(N_out))
+        state = tuple(t.contiguous() for t in (feats, coords, dens, wemb, ext, depth))
+        view = (v_feats.contiguous(), v_coords.contiguous(), v_dens.contiguous(), v_wemb.contiguous(), v_depth.contiguous(),
+                v_ext, E_inv, K_px)
+        a = _ptf_args(h, w, F, N, depth_thres, state, cin, view, scratch, counts_row, out,
+                      None if gru_out is None else gru_out.contiguous())
+        with torch.cuda.device(dev):
+            check(L.fs_ptf_merge(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs_ptf_merge")
+        zbuf, pix, zeta, match, append, block_counts, pair_j, pair_p = scratch
+        keep_idx = torch.nonzero(match[:N] == 0).squeeze(1)
+        app_idx = torch.nonzero(append).squeeze(1)
+        pj, pp = pair_j[:M].long(), pair_p[:M].long()
+        ctx.sizes = (N, nk, M, na, h * w, F)
+        ctx.save_for_backward(keep_idx, app_idx, pj, pp, coords, dens, ext, depth, v_coords, v_dens, v_depth, v_ext,
+                              out[1], out[4], out[5])
+        ctx.has_gru = gru_out is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gF, gX, gD, gW, gE, gZ):
+        (keep_idx, app_idx, pj, pp, coords, dens, ext, depth, v_coords, v_dens, v_depth, v_ext, oX, oE, oZ) = ctx.saved_tensors
+        N, nk, M, na, HW, F = ctx.sizes
+        dev = coords.device
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        g_feats, g_coords, g_dens, g_wemb, g_ext, g_depth = z(N, F), z(N, 3), z(N), z(N), z(N, 16), z(N)
+        gv_feats, gv_coords, gv_dens, gv_wemb, gv_depth = z(HW, F), z(HW, 3), z(HW), z(HW), z(HW)
+        # kept rows and appended rows are plain copies
+        g_feats[keep_idx] = gF[:nk]; g_coords[keep_idx] = gX[:nk]; g_dens[keep_idx] = gD[:nk]; g_wemb[keep_idx] = gW[:nk]
+        g_ext[keep_idx] = gE[:nk]; g_depth[keep_idx] = gZ[:nk]
+        s0 = nk + M
+        gv_feats[app_idx] = gF[s0:]; gv_coords[app_idx] = gX[s0:]; gv_dens[app_idx] = gD[s0:]; gv_wemb[app_idx] = gW[s0:]
+        gv_depth[app_idx] = gZ[s0:]
+        g_gru = None
+        if M > 0:
+            sl = slice(nk, s0)
+            g_gru = gF[sl] if ctx.has_gru else None
+            w0, w1 = dens[pj], v_dens[pp]
+            ws = w0 + w1
+            r0, r1 = w0 / ws, w1 / ws
+            gw0 = gD[sl].clone(); gw1 = gD[sl].clone()                    # dens' = w0 + w1
+            # coords
+            g = gX[sl]
+            g_coords[pj] = g * r0[:, None]; gv_coords.index_add_(0, pp, g * r1[:, None])
+            gw0 += (g * (coords[pj] - oX[sl])).sum(-1) / ws; gw1 += (g * (v_coords[pp] - oX[sl])).sum(-1) / ws
+            # depth
+            g = gZ[sl]
+            g_depth[pj] = g * r0; gv_depth.index_add_(0, pp, g * r1)
+            gw0 += g * (depth[pj] - oZ[sl]) / ws; gw1 += g * (v_depth[pp] - oZ[sl]) / ws
+            # extrinsics (view i's matrix is a constant)
+            g = gE[sl]
+            g_ext[pj] = g * r0[:, None]
+            gw0 += (g * (ext[pj] - oE[sl])).sum(-1) / ws; gw1 += (g * (v_ext[None] - oE[sl])).sum(-1) / ws
+            g_dens[pj] = gw0; gv_dens.index_add_(0, pp, gw1)
+            g_wemb[pj] = gW[sl]; gv_wemb.index_add_(0, pp, gW[sl])          # wemb' = wemb_j + wemb_p
+        return (g_feats, g_coords, g_dens, g_wemb, g_ext, g_depth, gv_feats, gv_coords, gv_dens, gv_wemb, gv_depth, g_gru, None)
+
+
 def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, image_shape, depth_thres=0.1,
                E_inv=None, return_debug=False):
     """Flat form: feats [V,HW,F], coords [V,HW,3], dens/wemb [V,HW], depths [V,HW], extrinsics [V,4,4] (c2w),
-    intrinsics [V,3,3] (normalised).  Returns (feats [N,F], coords [N,3], ext [N,4,4], depth [N]) (+ debug)."""
+    intrinsics [V,3,3] (normalised).  Returns (feats [N,F], coords [N,3], ext [N,4,4], depth [N]) (+ debug).
+    With autograd enabled and differentiable inputs the result is differentiable w.r.t. feats, coords, dens,
+    wemb, depths and the GRU parameters (index decisions are piecewise constant, as in the reference)."""
     L = _lib.lib()
     if not feats.is_cuda:
         raise _lib.FreeSplatB200Error("fuse_gaussians needs CUDA tensors (no CPU fallback exists)")
@@ -70,16 +157,15 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
     assert HW == h * w
     cap = V * HW
     stream = torch.cuda.current_stream(dev).cuda_stream
-    K_px = intrinsics.clone()
+    need_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in (feats, coords, dens, wemb, depths))
+                                             or any(p.requires_grad for p in gru.parameters()))
+    K_px = intrinsics.detach().clone()
     K_px[:, :1, :] *= w                       # encoder_freesplat.py:445-447
     K_px[:, 1:2, :] *= h
     if E_inv is None:
-        E_inv = torch.linalg.inv(extrinsics)  # extrinsic.inverse() (:454)
+        E_inv = torch.linalg.inv(extrinsics.detach())  # extrinsic.inverse() (:454)
     E_inv = f32(E_inv)
-    ext16 = extrinsics.reshape(V, 16)
-    cur, nxt = _State(cap, F, dev), _State(cap, F, dev)
-    cur.feats[:HW] = feats[0]; cur.coords[:HW] = coords[0]; cur.dens[:HW] = dens[0]; cur.wemb[:HW] = wemb[0]
-    cur.ext[:HW] = ext16[0]; cur.depth[:HW] = depths[0]
+    ext16 = extrinsics.detach().reshape(V, 16).contiguous()
     i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
     counts = torch.zeros((V + 1, 8), dtype=torch.int32, device=dev)
     counts[0, 0] = HW
@@ -88,45 +174,53 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
     match, append = torch.empty(cap, dtype=torch.uint8, device=dev), torch.empty(HW, dtype=torch.uint8, device=dev)
     nb = (cap + 1023) // 1024 + 1
     block_counts, pair_j, pair_p = i32(3 * nb), i32(cap), i32(cap)
-    n_upper = HW
+    scratch = (zbuf, pix, zeta, match, append, block_counts, pair_j, pair_p)
+    if need_grad:
+        state = (feats[0], coords[0], dens[0], wemb[0], ext16[0][None].expand(HW, 16).contiguous(), depths[0])
+        nxt = None
+    else:
+        cur, nxt = _State(cap, F, dev), _State(cap, F, dev)
+        cur.feats[:HW] = feats[0]; cur.coords[:HW] = coords[0]; cur.dens[:HW] = dens[0]; cur.wemb[:HW] = wemb[0]
+        cur.ext[:HW] = ext16[0]; cur.depth[:HW] = depths[0]
+        state = (cur.feats, cur.coords, cur.dens, cur.wemb, cur.ext, cur.depth)
     N = HW
     debug = []
     with torch.cuda.device(dev):
         for i in range(1, V):
             cin = counts[i - 1, 4:5]                      # N of the current state, on the device
-            a = FsPtfArgs(
-                H=h, W=w, F=F, n_upper=n_upper, depth_thres=depth_thres,
-                feats=ptr(cur.feats), coords=ptr(cur.coords), dens=ptr(cur.dens), wemb=ptr(cur.wemb), ext=ptr(cur.ext),
-                depth=ptr(cur.depth), counts_in=cin.data_ptr(),
-                v_feats=ptr(feats[i]), v_coords=ptr(coords[i]), v_dens=ptr(dens[i]), v_wemb=ptr(wemb[i]),
-                v_depth=ptr(depths[i]), v_ext=ptr(ext16[i]), E_inv=ptr(E_inv[i]), K_px=ptr(K_px[i]),
-                zbuf=ptr(zbuf), pix=ptr(pix), zeta=ptr(zeta), match=ptr(match), append=ptr(append),
-                block_counts=ptr(block_counts), pair_j=ptr(pair_j), pair_p=ptr(pair_p), counts_out=counts[i].data_ptr(),
-                gru_out=None, o_feats=ptr(nxt.feats), o_coords=ptr(nxt.coords), o_dens=ptr(nxt.dens), o_wemb=ptr(nxt.wemb),
-                o_ext=ptr(nxt.ext), o_depth=ptr(nxt.depth))
+            view = (feats[i], coords[i], dens[i], wemb[i], depths[i], ext16[i], E_inv[i], K_px[i])
+            det = tuple(t.detach() for t in state)
+            vdet = tuple(t.detach() for t in view)
+            out_bufs = None if need_grad else (nxt.feats, nxt.coords, nxt.dens, nxt.wemb, nxt.ext, nxt.depth)
+            a = _ptf_args(h, w, F, N, depth_thres, det, cin, vdet, scratch, counts[i], out_bufs)
             check(L.fs_ptf_match(C.byref(a), C.c_void_p(stream)), "fs_ptf_match")
             c = counts[i].tolist()                         # the one host read of this step
             M, N_out = c[2], c[4]
             gru_out = None
             if M > 0:
                 pj, pp = pair_j[:M].long(), pair_p[:M].long()
-                hidden = cur.feats[pj]                     # global latent   (networks.py:201 `hidden_feat`)
+                hidden = state[0][pj]                      # global latent   (networks.py:201 `hidden_feat`)
                 inp = feats[i][pp]                         # view-i latent   (`input_feat`)
-                e_in = positional_encoding(torch.stack([cur.dens[pj], wemb[i][pp]], -1), 6)
-                e_h = positional_encoding(torch.stack([dens[i][pp], cur.wemb[pj]], -1), 6)
+                e_in = positional_encoding(torch.stack([state[2][pj], wemb[i][pp]], -1), 6)
+                e_h = positional_encoding(torch.stack([dens[i][pp], state[3][pj]], -1), 6)
                 gru_out = gru(inp[None, :, None, :], hidden[None, :, None, :], e_in[None, :, None, :],
                               e_h[None, :, None, :])[0, :, 0, :].float().contiguous()
-            a.gru_out = ptr(gru_out)
-            check(L.fs_ptf_merge(C.byref(a), C.c_void_p(stream)), "fs_ptf_merge")
             if return_debug:
                 debug.append(dict(pix=pix[:N].clone(), zeta=zeta[:N].clone(), match=match[:N].clone(),
                                   append=append.clone(), zbuf=zbuf.clone(), counts=c))
-            cur, nxt = nxt, cur
+            if need_grad:
+                meta = (h, w, depth_thres, cin, ext16[i], E_inv[i], K_px[i], scratch, counts[i], c)
+                state = _PtfMerge.apply(state[0][:N], state[1][:N], state[2][:N], state[3][:N], state[4][:N], state[5][:N],
+                                        feats[i], coords[i], dens[i], wemb[i], depths[i], gru_out, meta)
+            else:
+                a.gru_out = ptr(gru_out)
+                check(L.fs_ptf_merge(C.byref(a), C.c_void_p(stream)), "fs_ptf_merge")
+                cur, nxt = nxt, cur
+                state = (cur.feats, cur.coords, cur.dens, cur.wemb, cur.ext, cur.depth)
             N = N_out
-            n_upper = N
-    out = (cur.feats[:N], cur.coords[:N], cur.ext[:N].reshape(N, 4, 4), cur.depth[:N])
+    out = (state[0][:N], state[1][:N], state[4][:N].reshape(N, 4, 4), state[5][:N])
     if return_debug:
-        return out, debug, (cur.dens[:N], cur.wemb[:N])
+        return out, debug, (state[2][:N], state[3][:N])
     return out
 
 

@@ -24,15 +24,27 @@ def main():
         gru = GRU()
         gru.load_state_dict(synth.gru_state(seed))
         self = SimpleNamespace(gru=gru)
-        with torch.no_grad():
-            feats, coords, extr, depths = fuse(self, inp["gaussians"], inp["coords"], inp["densities"], inp["weight_emb"],
-                                               inp["depths"], inp["extrinsics"], inp["intrinsics"], inp["image_shape"])
+        # inputs that receive gradients in training (encoder outputs) + the GRU parameters
+        gi = {k: inp[k].clone().requires_grad_(True) for k in ("densities", "weight_emb", "depths")}
+        g_feats = inp["gaussians"][0].clone().requires_grad_(True)
+        g_coords = inp["coords"][0].clone().requires_grad_(True)
+        feats, coords, extr, depths = fuse(self, [g_feats], [g_coords], gi["densities"], gi["weight_emb"],
+                                           gi["depths"], inp["extrinsics"], inp["intrinsics"], inp["image_shape"])
+        gen = torch.Generator().manual_seed(500 + seed)
+        wF, wX = torch.randn(feats.shape, generator=gen), torch.randn(coords.shape, generator=gen)
+        wE, wZ = torch.randn(extr.shape, generator=gen), torch.randn(depths.shape, generator=gen)
+        ((feats * wF).sum() + (coords * wX).sum() + (extr * wE).sum() + (depths * wZ).sum()).backward()
+        grads = dict(g_in_feats=g_feats.grad, g_in_coords=g_coords.grad, g_in_dens=gi["densities"].grad,
+                     g_in_wemb=gi["weight_emb"].grad, g_in_depths=gi["depths"].grad)
+        grads.update({"g_gru." + k: v.grad for k, v in gru.named_parameters()})
+        feats, coords, extr, depths = feats.detach(), coords.detach(), extr.detach(), depths.detach()
         np.savez_compressed(
             os.path.join(ROOT, "tests", "golden", name + ".npz"), meta=np.array([seed, V, h, w]),
             in_feats=inp["gaussians"][0].numpy(), in_coords=inp["coords"][0].numpy(), in_dens=inp["densities"].numpy(),
             in_wemb=inp["weight_emb"].numpy(), in_depths=inp["depths"].numpy(), in_ext=inp["extrinsics"].numpy(),
             in_K=inp["intrinsics"].numpy(), out_feats=feats.numpy(), out_coords=coords.numpy(), out_ext=extr.numpy(),
-            out_depths=depths.numpy())
+            out_depths=depths.numpy(), wF=wF.numpy(), wX=wX.numpy(), wE=wE.numpy(), wZ=wZ.numpy(),
+            **{k: v.numpy() for k, v in grads.items()})
         print(name, "N_out", feats.shape[1], "of", V * h * w)
 
 

@@ -108,3 +108,30 @@ def test_no_match_and_single_view():
     assert np.array_equal(bits(X_.cpu().numpy()), bits(np.concatenate([coords[0], coords[1]])))
     F1, X1, _, _ = _run(feats[:1], coords[:1], dens[:1], wemb[:1], depths[:1], ext[:1], K[:1], hw, 4)
     assert F1.shape[0] == 256 and np.array_equal(bits(X1.cpu().numpy()), bits(coords[0]))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_backward_vs_reference_golden(path):
+    """d(sum(out*w))/d(feats, coords, densities, weights, depths, GRU parameters) against the reference's own autograd."""
+    from freesplat_b200 import ptf
+    z = np.load(path)
+    seed = int(z["meta"][0])
+    feats, coords, dens, wemb, depths, ext, K, hw = flat_inputs(z)
+    dev = "cuda:0"
+    t = lambda a, g=True: torch.from_numpy(np.ascontiguousarray(a)).to(dev).requires_grad_(g)
+    tf, tx, td, tw, tz = t(feats), t(coords), t(dens), t(wemb), t(depths)
+    gru = _gru(seed, dev)
+    F_, X_, E_, Z_ = ptf.fuse_views(gru, tf, tx, td, tw, tz, t(ext, False), t(K, False), hw, E_inv=t(torch_inverses(ext), False))
+    w = lambda k: torch.from_numpy(z[k]).to(dev)
+    loss = (F_ * w("wF")[0]).sum() + (X_ * w("wX")[0]).sum() + (E_ * w("wE")[0]).sum() + (Z_ * w("wZ")[0]).sum()
+    loss.backward()
+    V = feats.shape[0]
+    pairs = [("feats", tf.grad, z["g_in_feats"][0]), ("coords", tx.grad, z["g_in_coords"][0, :, :, 0, 0, :]),
+             ("dens", td.grad, z["g_in_dens"][0, :, :, 0, 0]), ("wemb", tw.grad, z["g_in_wemb"][0, :, :, 0, 0]),
+             ("depths", tz.grad, z["g_in_depths"].reshape(V, -1))]
+    pairs += [("gru." + n, p.grad, z["g_gru." + n]) for n, p in gru.named_parameters()]
+    for name, got, want in pairs:
+        assert got is not None, name
+        scale = np.abs(want).max() + 1e-12
+        err = np.abs(got.cpu().numpy() - want).max() / scale
+        assert err < 2e-4, (name, err)

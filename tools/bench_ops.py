@@ -59,5 +59,25 @@ for V in (3, 10):
     N = out[0].shape[0]
     res[f"ptf_V{V}_640x480"] = {"ms": ms, "N_out": N, "ratio": N / (V * h * w),
                                 "alg_bytes": 280 * h * w * V + 344 * N}
+# ---- raster fwd + bwd (BASELINE config 3: 4 target views, MSE loss on colour) ----
+from freesplat_b200 import decoder  # noqa: E402
+sc = synth.pixel_aligned_scene(seed=0, h=480, w=640, n_context=3, n_target=4, keep=460800).to(dev)
+bg = torch.zeros((4, 3), device=dev)
+means = sc.means.clone().requires_grad_(True); cov = sc.covariances.clone().requires_grad_(True)
+sh = sc.harmonics.clone().requires_grad_(True); op = sc.opacities.clone().requires_grad_(True)
+target = torch.rand((4, 3, 480, 640), device=dev)
+
+
+def raster_fb():
+    c, d = decoder.render_views(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (480, 640), bg, means, cov, sh, op)
+    ((c - target) ** 2).mean().backward()
+
+
+def raster_f():
+    with torch.no_grad():
+        decoder.render_views(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (480, 640), bg, means, cov, sh, op)
+
+
+res["raster_cfg3_P460800_T4"] = {"fwd_ms": timeit(raster_f, n=10, warm=3), "fwd_bwd_ms": timeit(raster_fb, n=10, warm=3)}
 print(json.dumps(res, indent=1))
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_ops.json"), "w"), indent=1)

@@ -14,6 +14,7 @@ raise: there is no PyTorch fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -28,6 +29,7 @@ class FsCostVolumeArgs(C.Structure):
         ("cur_feats", C.c_void_p), ("src_feats", C.c_void_p), ("proj", C.c_void_p), ("cur_invK", C.c_void_p),
         ("planes", C.c_void_p), ("mlp", C.c_void_p), ("out", C.c_void_p),
         ("dL_dout", C.c_void_p), ("dL_dcur", C.c_void_p), ("dL_dsrc", C.c_void_p), ("dL_dmlp", C.c_void_p),
+        ("mlp_mode", C.c_int32),
     ]
 
 
@@ -55,10 +57,14 @@ def unpack_mlp(flat: torch.Tensor):
     return out
 
 
+# 0: tensor cores (tcgen05, 3xTF32) ; 1: fp32 CUDA-core MLP (kept to validate mode 0)
+MLP_MODE = int(os.environ.get("FREESPLAT_B200_CV_MLP_MODE", "0"))
+
+
 def _args(cur, src, proj, invk, planes, mlp):
     B, K, Cc, H, W = src.shape
     return FsCostVolumeArgs(B=B, K=K, C=Cc, H=H, W=W, D=planes.numel(), cur_feats=ptr(cur), src_feats=ptr(src),
-                            proj=ptr(proj), cur_invK=ptr(invk), planes=ptr(planes), mlp=ptr(mlp))
+                            proj=ptr(proj), cur_invK=ptr(invk), planes=ptr(planes), mlp=ptr(mlp), mlp_mode=MLP_MODE)
 
 
 class _CostVolumeFn(torch.autograd.Function):

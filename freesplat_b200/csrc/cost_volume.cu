@@ -184,12 +184,265 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_kernel(FsCostVolum
   }
 }
 
+// =========================================================================== tensor-core forward
+// Same gather, but the 49->32->32 contraction runs on the 5th-generation tensor cores:
+//   * each CTA owns 128 rows (= 128 reference pixels at one plane) -> UMMA M = 128, N = 32, K = 8 (tf32);
+//   * thread r writes row r of the A operand into shared memory in the canonical K-major /
+//     SWIZZLE_NONE core-matrix layout ([k-step][row-group of 8][k-chunk of 16 B][row][16 B]:
+//     SBO = 256 B, LBO = 128 B), weights (B operand, nn.Linear layout is already K-major) likewise;
+//   * fp32 accuracy by the 3xTF32 split: x = hi + lo (both tf32), D = Ahi*Bhi + Ahi*Blo + Alo*Bhi accumulated in
+//     TMEM (fp32), |error| ~ 2^-22: inside the 1e-4 parity budget (tests/test_cost_volume_gpu.py);
+//   * one elected thread issues the tcgen05.mma batch and commits to an mbarrier; every warp then reads ITS
+//     32 TMEM lanes with tcgen05.ld.32x32b.x32 -- lane = row, so "thread = row" holds on both sides;
+//   * layer 2 re-uses the A buffer; the last layer (32 -> 1) stays on the CUDA cores (32 FMA per row).
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  constexpr uint64_t kLbo = 128 >> 4, kSbo = 256 >> 4;
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | (kLbo << 16) | (kSbo << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, N = 32, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+constexpr int kK1 = 56, kSteps1 = kK1 / 8, kSteps2 = kCvHid / 8;   // layer-1 K padded 49 -> 56
+constexpr int kABytesPerStep = 128 / 8 * 256;                      // 16 row groups x 256 B = 4096
+constexpr int kBBytesPerStep = kCvHid / 8 * 256;                   // 4 row groups x 256 B = 1024
+
+struct __align__(128) Smem {
+  unsigned char A_hi[kSteps1 * kABytesPerStep];     // 28 KB (layer 2 re-uses the first 16 KB)
+  unsigned char A_lo[kSteps1 * kABytesPerStep];
+  unsigned char B0_hi[kSteps1 * kBBytesPerStep];    // 7 KB
+  unsigned char B0_lo[kSteps1 * kBBytesPerStep];
+  unsigned char B1_hi[kSteps2 * kBBytesPerStep];    // 4 KB
+  unsigned char B1_lo[kSteps2 * kBBytesPerStep];
+  float b0[kCvHid], b1[kCvHid], W2[kCvHid];
+  float b2;
+  float proj[16 * 12];
+  unsigned long long bar;
+  uint32_t tmem_base;
+};
+
+// byte offset of element (row, k) inside an operand tile (k counted in tf32 elements)
+__device__ __forceinline__ uint32_t op_off(int row, int k, int bytes_per_step) {
+  return (uint32_t)((k >> 3) * bytes_per_step + (row >> 3) * 256 + ((k >> 2) & 1) * 128 + (row & 7) * 16 + (k & 3) * 4);
+}
+
+__device__ __forceinline__ void split_store4(unsigned char* hi, unsigned char* lo, uint32_t off, float v0, float v1, float v2, float v3) {
+  uint4 h, l;
+  h.x = to_tf32(v0); h.y = to_tf32(v1); h.z = to_tf32(v2); h.w = to_tf32(v3);
+  l.x = to_tf32(v0 - __uint_as_float(h.x)); l.y = to_tf32(v1 - __uint_as_float(h.y));
+  l.z = to_tf32(v2 - __uint_as_float(h.z)); l.w = to_tf32(v3 - __uint_as_float(h.w));
+  *reinterpret_cast<uint4*>(hi + off) = h;
+  *reinterpret_cast<uint4*>(lo + off) = l;
+}
+
+__global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_tc_kernel(FsCostVolumeArgs a, int planes_per_block) {
+  extern __shared__ __align__(128) unsigned char tc_smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(tc_smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.z;
+  const int H = a.H, W = a.W, K = a.K;
+  const size_t HW = (size_t)H * W;
+  // ---- one-time setup: weights as tf32 hi/lo B tiles, biases, projections, mbarrier, TMEM ----
+  {
+    const float* w0 = a.mlp;                                // [32][49]
+    for (int e = tid; e < kCvHid * kK1; e += kCvThreads) {
+      const int n = e / kK1, k = e - n * kK1;
+      const float v = k < kCvIn ? w0[n * kCvIn + k] : 0.f;
+      const uint32_t hi = to_tf32(v), lo = to_tf32(v - __uint_as_float(hi));
+      const uint32_t off = op_off(n, k, kBBytesPerStep);
+      *reinterpret_cast<uint32_t*>(sm.B0_hi + off) = hi; *reinterpret_cast<uint32_t*>(sm.B0_lo + off) = lo;
+    }
+    const float* pb0 = w0 + kCvHid * kCvIn;
+    const float* w1 = pb0 + kCvHid;                         // [32][32]
+    for (int e = tid; e < kCvHid * kCvHid; e += kCvThreads) {
+      const int n = e / kCvHid, k = e - n * kCvHid;
+      const float v = w1[e];
+      const uint32_t hi = to_tf32(v), lo = to_tf32(v - __uint_as_float(hi));
+      const uint32_t off = op_off(n, k, kBBytesPerStep);
+      *reinterpret_cast<uint32_t*>(sm.B1_hi + off) = hi; *reinterpret_cast<uint32_t*>(sm.B1_lo + off) = lo;
+    }
+    const float* pb1 = w1 + kCvHid * kCvHid;
+    const float* w2 = pb1 + kCvHid;
+    for (int k = tid; k < kCvHid; k += kCvThreads) { sm.b0[k] = pb0[k]; sm.b1[k] = pb1[k]; sm.W2[k] = w2[k]; }
+    if (tid == 0) sm.b2 = w2[kCvHid];
+    for (int k = tid; k < K * 12; k += kCvThreads) sm.proj[k] = a.proj[(size_t)b * K * 12 + k];
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(64u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's 32 TMEM lanes
+  const uint32_t bar = smem_u32(&sm.bar);
+  const uint32_t aA_hi = smem_u32(sm.A_hi), aA_lo = smem_u32(sm.A_lo);
+  const uint32_t aB0_hi = smem_u32(sm.B0_hi), aB0_lo = smem_u32(sm.B0_lo), aB1_hi = smem_u32(sm.B1_hi), aB1_lo = smem_u32(sm.B1_lo);
+  uint32_t phase = 0;
+
+  const int p = blockIdx.x * kCvThreads + tid;
+  const bool active = p < (int)HW;
+  const int pc = active ? p : 0;
+  const int v = pc / W, u = pc - v * W;
+  const float uvx = 1.0f / (float)W, uvy = 1.0f / (float)H;
+  const float* ik = a.cur_invK + (size_t)b * 9;
+  const float pu = (float)u + 0.5f, pv = (float)v + 0.5f;
+  const float r0 = fmaf(ik[1], pv, ik[0] * pu) + ik[2];
+  const float r1 = fmaf(ik[4], pv, ik[3] * pu) + ik[5];
+  const float r2 = fmaf(ik[7], pv, ik[6] * pu) + ik[8];
+  float cur[kCvC];
+  {
+    const float* cb = a.cur_feats + (size_t)b * kCvC * HW + pc;
+#pragma unroll
+    for (int c = 0; c < kCvC; c++) cur[c] = __ldg(cb + (size_t)c * HW);
+  }
+  const float* src_b = a.src_feats + (size_t)b * K * kCvC * HW;
+  const unsigned all = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+  const int d0 = blockIdx.y * planes_per_block, d1 = min(a.D, d0 + planes_per_block);
+  const uint32_t my_off = (uint32_t)((tid >> 3) * 256 + (tid & 7) * 16);   // row part of op_off
+
+  for (int d = d0; d < d1; d++) {
+    const float zd = __ldg(a.planes + d);
+    const float X0 = zd * r0, X1 = zd * r1, X2 = zd * r2;
+    {
+      float x[kCvC];
+      float dsum;
+      unsigned geo, zero;
+      gather_sources(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, all, x, dsum, geo, zero);
+      const unsigned valid = geo & ~zero;
+      if (zero) { float ds2; unsigned g2, z2; gather_sources(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, valid, x, ds2, g2, z2); }
+      const float rn = 1.0f / ((float)__popc(valid) + 1e-8f);
+      // ---- A operand of layer 1: row tid, k = 0..55 (x*rn, dot*rn, zero padding), hi/lo tf32 ----
+#pragma unroll
+      for (int q = 0; q < kCvC / 4; q++) {
+        const uint32_t off = (uint32_t)((q >> 1) * kABytesPerStep + (q & 1) * 128) + my_off;
+        split_store4(sm.A_hi, sm.A_lo, off, x[4 * q] * rn, x[4 * q + 1] * rn, x[4 * q + 2] * rn, x[4 * q + 3] * rn);
+      }
+      split_store4(sm.A_hi, sm.A_lo, (uint32_t)(6 * kABytesPerStep) + my_off, dsum * rn, 0.f, 0.f, 0.f);
+      split_store4(sm.A_hi, sm.A_lo, (uint32_t)(6 * kABytesPerStep + 128) + my_off, 0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int s = 0; s < kSteps1; s++) {
+        const uint64_t dah = make_desc(aA_hi + s * kABytesPerStep), dal = make_desc(aA_lo + s * kABytesPerStep);
+        const uint64_t dbh = make_desc(aB0_hi + s * kBBytesPerStep), dbl = make_desc(aB0_lo + s * kBBytesPerStep);
+        mma_tf32(tmem, dal, dbh, s > 0 ? 1u : 0u);
+        mma_tf32(tmem, dah, dbl, 1u);
+        mma_tf32(tmem, dah, dbh, 1u);
+      }
+      commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      float h[kCvHid];
+      tmem_ld32(t_row, h);
+      // ---- A operand of layer 2: leaky(h + b0), K = 32 ----
+#pragma unroll
+      for (int q = 0; q < kCvHid / 4; q++) {
+        const uint32_t off = (uint32_t)((q >> 1) * kABytesPerStep + (q & 1) * 128) + my_off;
+        split_store4(sm.A_hi, sm.A_lo, off, leaky(h[4 * q] + sm.b0[4 * q]), leaky(h[4 * q + 1] + sm.b0[4 * q + 1]),
+                     leaky(h[4 * q + 2] + sm.b0[4 * q + 2]), leaky(h[4 * q + 3] + sm.b0[4 * q + 3]));
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int s = 0; s < kSteps2; s++) {
+        const uint64_t dah = make_desc(aA_hi + s * kABytesPerStep), dal = make_desc(aA_lo + s * kABytesPerStep);
+        const uint64_t dbh = make_desc(aB1_hi + s * kBBytesPerStep), dbl = make_desc(aB1_lo + s * kBBytesPerStep);
+        mma_tf32(tmem + 32u, dal, dbh, s > 0 ? 1u : 0u);
+        mma_tf32(tmem + 32u, dah, dbl, 1u);
+        mma_tf32(tmem + 32u, dah, dbh, 1u);
+      }
+      commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      float h[kCvHid];
+      tmem_ld32(t_row + 32u, h);
+      float y = sm.b2;
+#pragma unroll
+      for (int i = 0; i < kCvHid; i++) y = fmaf(sm.W2[i], leaky(h[i] + sm.b1[i]), y);
+      if (active) a.out[((size_t)b * a.D + d) * HW + p] = y;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
+}
+
+}  // namespace tc
+
 int launch_cost_volume_fwd(const FsCostVolumeArgs& a, cudaStream_t s) {
   const size_t HW = (size_t)a.H * a.W;
   const int ppb = 8;
   dim3 grid((unsigned)((HW + kCvThreads - 1) / kCvThreads), (unsigned)((a.D + ppb - 1) / ppb), (unsigned)a.B);
-  cost_volume_fwd_kernel<<<grid, kCvThreads, 0, s>>>(a, ppb);
-  return check_cuda(cudaGetLastError(), "cost_volume_fwd_kernel");
+  if (a.mlp_mode == 1) {   // fp32 CUDA-core MLP: validation path for the tensor-core kernel
+    cost_volume_fwd_kernel<<<grid, kCvThreads, 0, s>>>(a, ppb);
+    return check_cuda(cudaGetLastError(), "cost_volume_fwd_kernel");
+  }
+  const size_t smem = sizeof(tc::Smem) + 128;
+  if (int rc = check_cuda(cudaFuncSetAttribute(tc::cost_volume_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(cost_volume_fwd_tc_kernel)")) return rc;
+  tc::cost_volume_fwd_tc_kernel<<<grid, kCvThreads, smem, s>>>(a, ppb);
+  return check_cuda(cudaGetLastError(), "cost_volume_fwd_tc_kernel");
 }
 
 }  // namespace fs

@@ -1,0 +1,70 @@
+"""Host-to-host rendering pipeline: the public entry point for callers whose Gaussians and cameras live in
+(pinned) host memory.  Three CUDA streams -- H2D copies, the kernels, D2H copies -- and double-buffered
+device / host staging, so the copy engines of step k+1 / k-1 run under the kernels of step k.
+(The reference has no counterpart: it renders view by view with a blocking D2H inside the op.)"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import decoder
+
+
+class HostRenderPipeline:
+    KEYS = ("extrinsics", "intrinsics", "near", "far", "means", "covariances", "harmonics", "opacities")
+
+    def __init__(self, device, image_shape: Tuple[int, int], n_views: int, depth: int = 2, background=(0.0, 0.0, 0.0)):
+        self.dev = torch.device(device)
+        self.h, self.w = image_shape
+        self.V = n_views
+        self.depth = depth
+        self.s_h2d, self.s_run, self.s_d2h = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self.bg = torch.tensor(background, dtype=torch.float32, device=self.dev)[None].expand(n_views, 3).contiguous()
+        self.dev_in: List[Optional[Dict[str, torch.Tensor]]] = [None] * depth
+        self.out_c = [torch.empty((n_views, 3, self.h, self.w), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.out_d = [torch.empty((n_views, self.h, self.w), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.ev_in_free = [torch.cuda.Event() for _ in range(depth)]     # device inputs of slot may be overwritten
+        self.ev_copied = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]        # kernels of slot finished
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]         # host outputs of slot are valid
+        self.n = 0
+
+    def submit(self, host: Dict[str, torch.Tensor]) -> int:
+        """host: pinned CPU tensors named as KEYS (one scene, V target views).  Returns the slot index;
+        call wait(slot) before reading the host outputs `out_c[slot]`, `out_d[slot]`."""
+        slot = self.n % self.depth
+        first_use = self.n < self.depth
+        self.n += 1
+        with torch.cuda.stream(self.s_h2d):
+            if not first_use:
+                self.s_h2d.wait_event(self.ev_in_free[slot])
+            if self.dev_in[slot] is None:
+                self.dev_in[slot] = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.dev) for k in self.KEYS}
+            for k in self.KEYS:
+                self.dev_in[slot][k].copy_(host[k], non_blocking=True)
+            self.ev_copied[slot].record(self.s_h2d)
+        with torch.cuda.stream(self.s_run), torch.no_grad():
+            self.s_run.wait_event(self.ev_copied[slot])
+            if not first_use:
+                self.s_run.wait_event(self.ev_out[slot])          # previous results of this slot were copied out
+            d = self.dev_in[slot]
+            c, dp = decoder.render_views(d["extrinsics"], d["intrinsics"], d["near"], d["far"], (self.h, self.w), self.bg,
+                                         d["means"], d["covariances"], d["harmonics"], d["opacities"])
+            self.ev_done[slot].record(self.s_run)
+            self.ev_in_free[slot].record(self.s_run)
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(self.ev_done[slot])
+            self.out_c[slot].copy_(c, non_blocking=True)
+            self.out_d[slot].copy_(dp, non_blocking=True)
+            c.record_stream(self.s_d2h); dp.record_stream(self.s_d2h)
+            self.ev_out[slot].record(self.s_d2h)
+        return slot
+
+    def wait(self, slot: int):
+        self.ev_out[slot].synchronize()
+        return self.out_c[slot], self.out_d[slot]
+
+    def drain(self):
+        for s in (self.s_h2d, self.s_run, self.s_d2h):
+            s.synchronize()

@@ -156,6 +156,8 @@ typedef struct FsCostVolumeArgs {
   float* dL_dcur;          /* [B,C,H,W]   (written)                                          */
   float* dL_dsrc;          /* [B,K,C,H,W] (zeroed by the call, then accumulated)             */
   float* dL_dmlp;          /* packed like `mlp` (zeroed by the call, then accumulated)       */
+  int32_t mlp_mode;        /* forward: 0 = tcgen05 tensor cores (3xTF32, fp32-accurate), 1 = fp32 CUDA cores
+                              (validation of mode 0)                                         */
 } FsCostVolumeArgs;
 
 int fs_cost_volume_forward(const FsCostVolumeArgs* args, void* stream);

@@ -96,3 +96,28 @@ def test_backward_vs_reference_golden(path):
             [(f"mlp{i}", p.grad, z[f"g_mlp{i}"]) for i, p in enumerate(params)]:
         assert got is not None, name
         assert _close(got.cpu().numpy(), want) < 2e-4, (name, _close(got.cpu().numpy(), want))
+
+
+def test_tensor_core_and_fp32_mlp_agree():
+    """mode 0 (tcgen05, 3xTF32 split) vs mode 1 (fp32 CUDA cores) on the same inputs; both vs the oracle."""
+    from freesplat_b200 import cost_volume as cvm
+    from oracle import cost_volume as ocv
+    dev = "cuda:0"
+    V, K, Hf, Wf, D = 2, 1, 40, 52, 24          # H*W not a multiple of 128: exercises the padded rows
+    inp = synth.cost_volume_inputs(7, V, K, 48, Hf, Wf)
+    mlp = [w * 3.0 for w in synth.cost_volume_mlp(7)]          # larger weights: stresses the split precision
+    want = ocv.forward(inp["cur_feats"], inp["src_feats"], inp["src_extrinsics"], inp["src_Ks"], inp["cur_invK"],
+                       inp["min_depth"], inp["max_depth"], mlp, D).numpy()
+    m = _module(Hf, Wf, D, mlp, dev)
+    outs = {}
+    old = cvm.MLP_MODE
+    try:
+        for mode in (0, 1):
+            cvm.MLP_MODE = mode
+            with torch.no_grad():
+                outs[mode] = m(**{k: v.to(dev) for k, v in inp.items()}).cpu().numpy()
+    finally:
+        cvm.MLP_MODE = old
+    assert _close(outs[1], want) < 1e-4
+    assert _close(outs[0], want) < 1e-4
+    assert _close(outs[0], outs[1]) < 5e-5

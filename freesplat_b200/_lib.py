@@ -19,7 +19,8 @@ class FsRasterFwdArgs(C.Structure):
     _fields_ = [
         ("P", C.c_int32), ("V", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("sh_degree", C.c_int32), ("M", C.c_int32), ("scale_modifier", C.c_float),
-        ("prefiltered", C.c_int32), ("stages", C.c_int32), ("capacity", C.c_int64),
+        ("prefiltered", C.c_int32), ("stages", C.c_int32), ("sh_layout", C.c_int32), ("cov_stride", C.c_int32),
+        ("capacity", C.c_int64),
         ("means3D", vp), ("shs", vp), ("colors_precomp", vp), ("opacities", vp),
         ("scales", vp), ("rotations", vp), ("cov3D_precomp", vp), ("views", vp),
         ("out_color", vp), ("out_depth", vp), ("final_T", vp), ("n_contrib", vp), ("radii", vp),
@@ -33,7 +34,7 @@ class FsRasterBwdArgs(C.Structure):
     _fields_ = [
         ("P", C.c_int32), ("V", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("sh_degree", C.c_int32), ("M", C.c_int32), ("scale_modifier", C.c_float),
-        ("has_depth_grad", C.c_int32),
+        ("has_depth_grad", C.c_int32), ("sh_layout", C.c_int32), ("cov_stride", C.c_int32),
         ("means3D", vp), ("shs", vp), ("colors_precomp", vp), ("opacities", vp),
         ("scales", vp), ("rotations", vp), ("cov3D_precomp", vp), ("views", vp),
         ("rec", vp), ("radii", vp), ("clamped", vp), ("ranges", vp),

@@ -50,7 +50,12 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(FsRasterFwdArgs
   if (active) {
     m0 = __ldg(a.means3D + 3 * (size_t)i + 0); m1 = __ldg(a.means3D + 3 * (size_t)i + 1); m2 = __ldg(a.means3D + 3 * (size_t)i + 2);
     opacity = __ldg(a.opacities + i);
-    if (a.cov3D_precomp) {
+    if (a.cov3D_precomp && a.cov_stride == 9) {
+      // full row-major 3x3 matrices (the reference's Gaussians.covariances): upper triangle = cov6
+      const float* cp = a.cov3D_precomp + 9 * (size_t)i;
+      c6in[0] = __ldg(cp); c6in[1] = __ldg(cp + 1); c6in[2] = __ldg(cp + 2); c6in[3] = __ldg(cp + 4); c6in[4] = __ldg(cp + 5);
+      c6in[5] = __ldg(cp + 8);
+    } else if (a.cov3D_precomp) {
       const float2* cp = reinterpret_cast<const float2*>(a.cov3D_precomp + 6 * (size_t)i);
       const float2 c01 = __ldg(cp), c23 = __ldg(cp + 1), c45 = __ldg(cp + 2);
       c6in[0] = c01.x; c6in[1] = c01.y; c6in[2] = c23.x; c6in[3] = c23.y; c6in[4] = c45.x; c6in[5] = c45.y;
@@ -91,7 +96,8 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(FsRasterFwdArgs
           const int nf = ((a.sh_degree + 1) * (a.sh_degree + 1)) * 3;   // only the active coefficients are used
           const float* shp = s_sh + tid * sh_stride;
 #pragma unroll
-          for (int k = 0; k < 48; k++) sh[k] = (k < nf) ? shp[k] : 0.f;
+          for (int k = 0; k < 48; k++)   // sh[coef*3 + ch]; layout 1 = [P,3,M] (the reference's Gaussians.harmonics)
+            sh[k] = (k < nf) ? (a.sh_layout ? shp[(k % 3) * a.M + k / 3] : shp[k]) : 0.f;
           clampmask = fsm::sh_to_rgb(a.sh_degree, mean, view + 32, sh, rgb);
         }
         float hx, hy;
@@ -155,7 +161,10 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
   bool sh_written = false;
   const float m0 = a.means3D[3 * (size_t)i], m1 = a.means3D[3 * (size_t)i + 1], m2 = a.means3D[3 * (size_t)i + 2];
   float c6in[6];
-  if (a.cov3D_precomp) {
+  if (a.cov3D_precomp && a.cov_stride == 9) {
+    const float* cp = a.cov3D_precomp + 9 * (size_t)i;
+    c6in[0] = cp[0]; c6in[1] = cp[1]; c6in[2] = cp[2]; c6in[3] = cp[4]; c6in[4] = cp[5]; c6in[5] = cp[8];
+  } else if (a.cov3D_precomp) {
 #pragma unroll
     for (int k = 0; k < 6; k++) c6in[k] = a.cov3D_precomp[6 * (size_t)i + k];
   } else {
@@ -279,10 +288,11 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
         const float g = ((cm >> ch) & 1) ? 0.f : grgb[ch];
         for (int k = 0; k < a.M; k++) {
           const float val = (k < nb) ? basis[k] * g : 0.f;
-          if (sh_written) gsh[k * 3 + ch] += val; else gsh[k * 3 + ch] = val;
+          float* dst = a.sh_layout ? gsh + ch * a.M + k : gsh + k * 3 + ch;
+          if (sh_written) *dst += val; else *dst = val;
         }
         float rx = 0.f, ry = 0.f, rz = 0.f;
-#define SHV(k) sh[(k) * 3 + ch]
+#define SHV(k) (a.sh_layout ? sh[ch * a.M + (k)] : sh[(k) * 3 + ch])
         if (D > 0) {
           rx = -fsm::kShC1 * SHV(3); ry = -fsm::kShC1 * SHV(1); rz = fsm::kShC1 * SHV(2);
           if (D > 1) {
@@ -320,7 +330,10 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
   a.dL_dmeans3D[3 * (size_t)i] = g_mean[0]; a.dL_dmeans3D[3 * (size_t)i + 1] = g_mean[1]; a.dL_dmeans3D[3 * (size_t)i + 2] = g_mean[2];
   a.dL_dopacities[i] = g_op;
   if (a.dL_dcolors) { a.dL_dcolors[3 * (size_t)i] = g_col[0]; a.dL_dcolors[3 * (size_t)i + 1] = g_col[1]; a.dL_dcolors[3 * (size_t)i + 2] = g_col[2]; }
-  if (a.dL_dcov3D) {
+  if (a.dL_dcov3D && a.cov_stride == 9) {      // gradient of the upper-triangle gather: lower triangle gets 0
+    float* g = a.dL_dcov3D + 9 * (size_t)i;
+    g[0] = g_cov[0]; g[1] = g_cov[1]; g[2] = g_cov[2]; g[3] = 0.f; g[4] = g_cov[3]; g[5] = g_cov[4]; g[6] = 0.f; g[7] = 0.f; g[8] = g_cov[5];
+  } else if (a.dL_dcov3D) {
 #pragma unroll
     for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)i + k] = g_cov[k];
   }

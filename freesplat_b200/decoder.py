@@ -84,25 +84,28 @@ def camera_records(extrinsics, intrinsics, near, far, background_color, scale_in
 
 def render_views(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
                  gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant=True,
-                 use_sh=True, depth_grad=False):
+                 use_sh=True, depth_grad=False, check_overflow=None):
     """One scene, V target views.
 
     extrinsics [V,4,4], intrinsics [V,3,3], near/far [V], background_color [V,3],
     gaussian_means [G,3], gaussian_covariances [G,3,3], gaussian_sh_coefficients [G,3,d_sh],
     gaussian_opacities [G]  ->  (color [V,3,H,W], depth [V,H,W]) in the SCALED scene units
-    (the caller divides by 1/near as decoder_splatting_cuda.py:62 does)."""
+    (the caller divides by 1/near as decoder_splatting_cuda.py:62 does).
+
+    The Gaussian tensors are consumed in the reference's own layouts ([G,3,3] covariances, [G,3,d_sh]
+    harmonics): the kernels index them in place, so none of the per-call `rearrange` / `triu` gather
+    copies of cuda_splatting.py:75,116,126 exist here, nor their mirror images in the backward pass."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
     h, w = image_shape
     n = gaussian_sh_coefficients.shape[-1]
     degree = isqrt(n) - 1
-    shs = gaussian_sh_coefficients.transpose(1, 2).contiguous()          # [G, d_sh, 3]
-    row, col = torch.triu_indices(3, 3)
-    cov6 = gaussian_covariances[:, row, col].contiguous()
     views, _ = camera_records(extrinsics, intrinsics, near, far, background_color, scale_invariant)
     color, radii, depth, _ = rasterize_views(
         gaussian_means, gaussian_opacities, views, h, w,
-        shs=shs if use_sh else None, colors_precomp=None if use_sh else shs[:, 0, :],
-        cov3D_precomp=cov6, sh_degree=degree, depth_grad=depth_grad)
+        shs=gaussian_sh_coefficients if use_sh else None,
+        colors_precomp=None if use_sh else gaussian_sh_coefficients[:, :, 0],
+        cov3D_precomp=gaussian_covariances, sh_degree=degree, depth_grad=depth_grad, sh_layout=1, cov_stride=9,
+        check_overflow=check_overflow)
     return color, depth
 
 

@@ -50,7 +50,8 @@ class HostRenderPipeline:
                 self.s_run.wait_event(self.ev_out[slot])          # previous results of this slot were copied out
             d = self.dev_in[slot]
             c, dp = decoder.render_views(d["extrinsics"], d["intrinsics"], d["near"], d["far"], (self.h, self.w), self.bg,
-                                         d["means"], d["covariances"], d["harmonics"], d["opacities"])
+                                         d["means"], d["covariances"], d["harmonics"], d["opacities"],
+                                         check_overflow="deferred" if self.n > self.depth else "sync")
             self.ev_done[slot].record(self.s_run)
             self.ev_in_free[slot].record(self.s_run)
         with torch.cuda.stream(self.s_d2h):

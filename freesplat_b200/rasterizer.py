@@ -73,7 +73,7 @@ class RasterState:
     """Tensors a forward call leaves behind (saved for backward; the parity comparables)."""
     __slots__ = ("P", "V", "H", "W", "M", "sh_degree", "scale_modifier", "views", "rec", "cov3D", "radii",
                  "clamped", "tiles_touched", "ranges", "point_list", "keybuf", "final_T", "n_contrib", "status",
-                 "capacity", "color", "depth")
+                 "capacity", "color", "depth", "sh_layout", "cov_stride")
 
     def num_rendered(self) -> int:
         s = self.status.cpu()
@@ -96,7 +96,8 @@ def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
 def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_precomp=None, scales=None,
                        rotations=None, cov3D_precomp=None, sh_degree=0, scale_modifier=1.0, prefiltered=False,
                        capacity: Optional[int] = None, check_overflow: str = "sync",
-                       stage_events=None, debug_buffers: bool = False) -> RasterState:
+                       stage_events=None, debug_buffers: bool = False, sh_layout: int = 0,
+                       cov_stride: int = 6) -> RasterState:
     """One launch sequence for V views (views: [V,48]).  Returns the RasterState.
 
     check_overflow: "sync"     read the device status word after enqueueing everything; re-run once
@@ -110,7 +111,7 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
     dev = means3D.device
     P = means3D.shape[0]
     V = views.shape[0]
-    M = 0 if shs is None else shs.shape[1]
+    M = 0 if shs is None else (shs.shape[2] if sh_layout else shs.shape[1])
     gx, gy = (W + 15) // 16, (H + 15) // 16
     nt = V * gx * gy
     key = (dev.index, P, V, H, W)
@@ -124,6 +125,7 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
             st.P, st.V, st.H, st.W, st.M, st.sh_degree, st.scale_modifier = P, V, H, W, M, sh_degree, scale_modifier
             st.views = views
             st.capacity = capacity
+            st.sh_layout, st.cov_stride = sh_layout, cov_stride
             e = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=dev)
             st.color = e(V, 3, H, W); st.depth = e(V, H, W); st.final_T = e(V, H, W)
             st.n_contrib = e(V, H, W, dtype=torch.int32)
@@ -139,7 +141,7 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
             st.status = e(4, dtype=torch.int32)
             a = FsRasterFwdArgs(
                 P=P, V=V, H=H, W=W, sh_degree=sh_degree, M=M, scale_modifier=scale_modifier,
-                prefiltered=int(prefiltered), stages=0, capacity=capacity,
+                prefiltered=int(prefiltered), stages=0, sh_layout=sh_layout, cov_stride=cov_stride, capacity=capacity,
                 means3D=ptr(means3D), shs=ptr(shs), colors_precomp=ptr(colors_precomp), opacities=ptr(opacities),
                 scales=ptr(scales), rotations=ptr(rotations), cov3D_precomp=ptr(cov3D_precomp), views=ptr(views),
                 out_color=ptr(st.color), out_depth=ptr(st.depth), final_T=ptr(st.final_T), n_contrib=ptr(st.n_contrib),
@@ -184,8 +186,8 @@ def raster_backward_raw(st: RasterState, means3D, opacities, dL_dcolor, *, shs=N
         use_sr = scales is not None and rotations is not None
         g = dict(
             means2D=e(V, P, 3), means3D=e(P, 3), opacities=e(P, 1),
-            cov3D=None if use_sr else e(P, 6),
-            shs=None if shs is None else e(P, M, 3),
+            cov3D=None if use_sr else e(P, st.cov_stride if st.cov_stride == 9 else 6),
+            shs=None if shs is None else e(*shs.shape),
             colors=None if colors_precomp is None else e(P, 3),
             scales=e(P, 3) if use_sr else None, rotations=e(P, 4) if use_sr else None)
         # the kernel needs somewhere to accumulate dL/dcov even when it is not returned
@@ -193,7 +195,7 @@ def raster_backward_raw(st: RasterState, means3D, opacities, dL_dcolor, *, shs=N
         dscreen = e(V, P, 12)
         a = FsRasterBwdArgs(
             P=P, V=V, H=H, W=W, sh_degree=st.sh_degree, M=M, scale_modifier=st.scale_modifier,
-            has_depth_grad=int(dL_ddepth is not None),
+            has_depth_grad=int(dL_ddepth is not None), sh_layout=st.sh_layout, cov_stride=st.cov_stride,
             means3D=ptr(means3D), shs=ptr(shs), colors_precomp=ptr(colors_precomp), opacities=ptr(opacities),
             scales=ptr(scales), rotations=ptr(rotations), cov3D_precomp=ptr(cov3D_precomp), views=ptr(st.views),
             rec=ptr(st.rec), radii=ptr(st.radii), clamped=ptr(st.clamped), ranges=ptr(st.ranges),
@@ -212,11 +214,13 @@ class _RasterizeViews(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, views,
-                H, W, sh_degree, scale_modifier, prefiltered, depth_grad):
+                H, W, sh_degree, scale_modifier, prefiltered, depth_grad, sh_layout=0, cov_stride=6, check_overflow=None):
+        if check_overflow is None:
+            check_overflow = "deferred" if _ASYNC else "sync"
         st = raster_forward_raw(means3D, opacities, views, H, W, shs=shs, colors_precomp=colors_precomp,
                                 scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp, sh_degree=sh_degree,
                                 scale_modifier=scale_modifier, prefiltered=prefiltered,
-                                check_overflow="deferred" if _ASYNC else "sync")
+                                check_overflow=check_overflow, sh_layout=sh_layout, cov_stride=cov_stride)
         ctx.st = st
         ctx.depth_grad = depth_grad
         ctx.save_for_backward(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp)
@@ -236,14 +240,19 @@ class _RasterizeViews(torch.autograd.Function):
                                 rotations=rotations, cov3D_precomp=cov3D_precomp, dL_ddepth=dd)
         gm2d = g["means2D"]
         return (g["means3D"], gm2d if st.V > 1 else gm2d[0], g["shs"], g["colors"],
-                g["opacities"].reshape(opacities.shape), g["scales"], g["rotations"], g["cov3D"], None,
-                None, None, None, None, None, None)
+                g["opacities"].reshape(opacities.shape), g["scales"], g["rotations"],
+                None if g["cov3D"] is None else g["cov3D"].reshape(cov3D_precomp.shape), None,
+                None, None, None, None, None, None, None, None, None)
 
 
 def rasterize_views(means3D, opacities, views, image_height, image_width, *, shs=None, colors_precomp=None,
                     scales=None, rotations=None, cov3D_precomp=None, means2D=None, sh_degree=0, scale_modifier=1.0,
-                    prefiltered=False, depth_grad=False):
-    """Batched op: -> (color[V,3,H,W], radii[V,P], depth[V,H,W], alpha[V,H,W])."""
+                    prefiltered=False, depth_grad=False, sh_layout=0, cov_stride=6, check_overflow=None):
+    """Batched op: -> (color[V,3,H,W], radii[V,P], depth[V,H,W], alpha[V,H,W]).
+
+    sh_layout=1 reads `shs` as [P,3,M] and cov_stride=9 reads `cov3D_precomp` as full [P,3,3] matrices -- the
+    layouts of the reference's Gaussians dataclass -- in place (gradients come back in the same layouts).
+    check_overflow="deferred" skips the host read of the device status word (see raster_forward_raw)."""
     if (shs is None) == (colors_precomp is None):
         raise Exception("Please provide excatly one of either SHs or precomputed colors!")
     if ((scales is None or rotations is None) and cov3D_precomp is None) or \
@@ -253,7 +262,8 @@ def rasterize_views(means3D, opacities, views, image_height, image_width, *, shs
         V = views.shape[0]
         means2D = torch.zeros((V, means3D.shape[0], 3), dtype=torch.float32, device=means3D.device)
     return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                 views, image_height, image_width, sh_degree, scale_modifier, prefiltered, depth_grad)
+                                 views, image_height, image_width, sh_degree, scale_modifier, prefiltered, depth_grad,
+                                 sh_layout, cov_stride, check_overflow)
 
 
 class GaussianRasterizer(torch.nn.Module):

@@ -73,6 +73,9 @@ typedef struct FsRasterFwdArgs {
   int32_t prefiltered;   /* accepted for API parity; unused (as upstream)        */
   int32_t stages;        /* bit mask of FS_STAGE_*; 0 means all.  Lets the caller put
                             CUDA events between stages (bench.py roofline timing)   */
+  int32_t sh_layout;     /* 0: shs is [P,M,3] (upstream op) ; 1: [P,3,M] (the reference's
+                            Gaussians.harmonics, read in place: no transpose copy)       */
+  int32_t cov_stride;    /* 6: cov3D_precomp is [P,6] ; 9: full row-major [P,3,3]         */
   int64_t capacity;      /* tile-instance capacity of keybuf / point_list        */
   /* inputs */
   const float* means3D;        /* [P,3]                                          */
@@ -112,6 +115,8 @@ typedef struct FsRasterBwdArgs {
   int32_t P, V, H, W, sh_degree, M;
   float scale_modifier;
   int32_t has_depth_grad;      /* 0: dL_ddepth ignored (reference behaviour)     */
+  int32_t sh_layout;           /* as in FsRasterFwdArgs; dL_dshs uses the same layout           */
+  int32_t cov_stride;          /* 6 or 9; dL_dcov3D uses the same stride                        */
   const float* means3D; const float* shs; const float* colors_precomp;
   const float* opacities; const float* scales; const float* rotations;
   const float* cov3D_precomp;  /* exactly one of cov3D_precomp / (scales, rotations), as in forward */

@@ -100,13 +100,13 @@ static int check_cv(const FsCostVolumeArgs* a) {
 
 int fs_cost_volume_forward(const FsCostVolumeArgs* a, void* stream) {
   if (int rc = check_cv(a)) return rc;
-  FS_REQUIRE(a->out != nullptr, "out is NULL");
+  FS_REQUIRE(a->out != nullptr && a->src_packed != nullptr, "out / src_packed is NULL");
   return launch_cost_volume_fwd(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fs_cost_volume_backward(const FsCostVolumeArgs* a, void* stream) {
   if (int rc = check_cv(a)) return rc;
-  FS_REQUIRE(a->dL_dout && a->dL_dcur && a->dL_dsrc && a->dL_dmlp, "NULL gradient buffer");
+  FS_REQUIRE(a->dL_dout && a->dL_dcur && a->dL_dsrc && a->dL_dmlp && a->src_packed, "NULL gradient / scratch buffer");
   return launch_cost_volume_bwd(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 

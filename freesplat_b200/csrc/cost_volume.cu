@@ -97,6 +97,50 @@ __device__ __forceinline__ void gather_sources(const float* __restrict__ src_b, 
   }
 }
 
+// ---- channel-packed source maps ---------------------------------------------------------------
+// The NCHW gather costs one 32-bit load + its address arithmetic per (tap, channel): ~4300 instructions per
+// warp and voxel row (ncu r1).  cv_pack_kernel re-lays every source map as [C/4][H*W][4] once per call, so a tap
+// fetches four channels with ONE 16-byte load (neighbouring lanes -> neighbouring 16-byte words: 512 contiguous
+// bytes per warp instruction): 4x fewer load and address instructions for the same FMA count.
+__global__ void __launch_bounds__(256) cv_pack_kernel(const float* __restrict__ src, float4* __restrict__ dst, size_t HW, size_t total) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;            // over maps * 12 * HW
+  if (i >= total) return;
+  const size_t pix = i % HW, mg = i / HW;                              // mg = map*12 + group
+  const float* s = src + (mg * 4) * HW + pix;                          // channel 4*group of that map
+  dst[i] = make_float4(__ldg(s), __ldg(s + HW), __ldg(s + 2 * HW), __ldg(s + 3 * HW));
+}
+
+__device__ __forceinline__ void gather_sources_packed(const float4* __restrict__ srcp_b, const float* __restrict__ proj, int K, int H,
+                                                      int W, size_t HW, float X0, float X1, float X2, float uvx, float uvy,
+                                                      const float (&cur)[kCvC], unsigned use_mask, float (&fsum)[kCvC], float& dsum,
+                                                      unsigned& geo_mask, unsigned& zero_mask) {
+#pragma unroll
+  for (int c = 0; c < kCvC; c++) fsum[c] = 0.f;
+  dsum = 0.f; geo_mask = 0u; zero_mask = 0u;
+  for (int k = 0; k < K; k++) {
+    if (!((use_mask >> k) & 1u)) continue;
+    Taps t;
+    if (!make_taps(proj + 12 * k, X0, X1, X2, H, W, uvx, uvy, t)) continue;
+    geo_mask |= 1u << k;
+    const float4* __restrict__ s = srcp_b + (size_t)k * (kCvC / 4) * HW;
+    float dot = 0.f;
+#pragma unroll
+    for (int g = 0; g < kCvC / 4; g++) {
+      const float4* __restrict__ sg = s + (size_t)g * HW;
+      const float4 a = __ldg(sg + t.o00), b = __ldg(sg + t.o01), c = __ldg(sg + t.o10), d = __ldg(sg + t.o11);
+      const float w0 = fmaf(t.w11, d.x, fmaf(t.w10, c.x, fmaf(t.w01, b.x, t.w00 * a.x)));
+      const float w1 = fmaf(t.w11, d.y, fmaf(t.w10, c.y, fmaf(t.w01, b.y, t.w00 * a.y)));
+      const float w2 = fmaf(t.w11, d.z, fmaf(t.w10, c.z, fmaf(t.w01, b.z, t.w00 * a.z)));
+      const float w3 = fmaf(t.w11, d.w, fmaf(t.w10, c.w, fmaf(t.w01, b.w, t.w00 * a.w)));
+      dot = fmaf(w0, cur[4 * g], dot); dot = fmaf(w1, cur[4 * g + 1], dot);
+      dot = fmaf(w2, cur[4 * g + 2], dot); dot = fmaf(w3, cur[4 * g + 3], dot);
+      fsum[4 * g] += w0; fsum[4 * g + 1] += w1; fsum[4 * g + 2] += w2; fsum[4 * g + 3] += w3;
+    }
+    if (dot == 0.f) zero_mask |= 1u << k;
+    dsum += dot;
+  }
+}
+
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
 
 __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_kernel(FsCostVolumeArgs a, int planes_per_block) {
@@ -137,7 +181,7 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_kernel(FsCostVolum
 #pragma unroll
     for (int c = 0; c < kCvC; c++) cur[c] = __ldg(cb + (size_t)c * HW);
   }
-  const float* src_b = a.src_feats + (size_t)b * K * kCvC * HW;
+  const float4* src_b = reinterpret_cast<const float4*>(a.src_packed) + (size_t)b * K * (kCvC / 4) * HW;
   const unsigned all = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
   const int d0 = blockIdx.y * planes_per_block, d1 = min(a.D, d0 + planes_per_block);
   for (int d = d0; d < d1; d++) {
@@ -146,11 +190,11 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_kernel(FsCostVolum
     float x[kCvC];
     float dsum;
     unsigned geo, zero;
-    gather_sources(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, all, x, dsum, geo, zero);
+    gather_sources_packed(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, all, x, dsum, geo, zero);
     unsigned valid = geo & ~zero;
     if (zero) {   // measure-zero case: redo with the exact set of valid sources (keeps the reference's dot != 0 rule)
       float ds2; unsigned g2, z2;
-      gather_sources(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, valid, x, ds2, g2, z2);
+      gather_sources_packed(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, valid, x, ds2, g2, z2);
     }
     const float rn = 1.0f / ((float)__popc(valid) + 1e-8f);
     // ---- MLP 49 -> 32 -> 32 -> 1, LeakyReLU(0.01) ----
@@ -344,7 +388,7 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_tc_kernel(FsCostVo
 #pragma unroll
     for (int c = 0; c < kCvC; c++) cur[c] = __ldg(cb + (size_t)c * HW);
   }
-  const float* src_b = a.src_feats + (size_t)b * K * kCvC * HW;
+  const float4* src_b = reinterpret_cast<const float4*>(a.src_packed) + (size_t)b * K * (kCvC / 4) * HW;
   const unsigned all = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
   const int d0 = blockIdx.y * planes_per_block, d1 = min(a.D, d0 + planes_per_block);
   const uint32_t my_off = (uint32_t)((tid >> 3) * 256 + (tid & 7) * 16);   // row part of op_off
@@ -356,9 +400,9 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_tc_kernel(FsCostVo
       float x[kCvC];
       float dsum;
       unsigned geo, zero;
-      gather_sources(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, all, x, dsum, geo, zero);
+      gather_sources_packed(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, all, x, dsum, geo, zero);
       const unsigned valid = geo & ~zero;
-      if (zero) { float ds2; unsigned g2, z2; gather_sources(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, valid, x, ds2, g2, z2); }
+      if (zero) { float ds2; unsigned g2, z2; gather_sources_packed(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, valid, x, ds2, g2, z2); }
       const float rn = 1.0f / ((float)__popc(valid) + 1e-8f);
       // ---- A operand of layer 1: row tid, k = 0..55 (x*rn, dot*rn, zero padding), hi/lo tf32 ----
 #pragma unroll
@@ -430,9 +474,17 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_tc_kernel(FsCostVo
 
 }  // namespace tc
 
+static int launch_pack(const FsCostVolumeArgs& a, cudaStream_t s) {
+  const size_t HW = (size_t)a.H * a.W;
+  const size_t total = (size_t)a.B * a.K * (kCvC / 4) * HW;
+  cv_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a.src_feats, reinterpret_cast<float4*>(a.src_packed), HW, total);
+  return check_cuda(cudaGetLastError(), "cv_pack_kernel");
+}
+
 int launch_cost_volume_fwd(const FsCostVolumeArgs& a, cudaStream_t s) {
   const size_t HW = (size_t)a.H * a.W;
   const int ppb = 8;
+  if (int rc = launch_pack(a, s)) return rc;
   dim3 grid((unsigned)((HW + kCvThreads - 1) / kCvThreads), (unsigned)((a.D + ppb - 1) / ppb), (unsigned)a.B);
   if (a.mlp_mode == 1) {   // fp32 CUDA-core MLP: validation path for the tensor-core kernel
     cost_volume_fwd_kernel<<<grid, kCvThreads, 0, s>>>(a, ppb);
@@ -462,11 +514,9 @@ namespace fs {
 constexpr int kRowStride = 196;                  // floats per parked row (16-byte aligned segments)
 constexpr int kOffDz1 = 0, kOffX = 32, kOffDz2 = 84, kOffA1 = 116, kOffGa2 = 148, kOffG = 180;
 
-struct CvBwdSmem {
+struct CvBwdSmem {                                // ~10.5 KB: with the 100 KB row buffer two CTAs fit per SM
   float W0t[kCvIn][kCvHid];
   float W1t[kCvHid][kCvHid];
-  float W0[kCvHid][kCvIn + 3];                   // row-major copy for dx = W0^T dz1 (padded to 52)
-  float W1[kCvHid][kCvHid];
   float W2[kCvHid];
   float b0[kCvHid];
   float b1[kCvHid];
@@ -486,12 +536,11 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
   const size_t HW = (size_t)H * W;
   {
     const float* w = a.mlp;
-    for (int k = tid; k < kCvHid * kCvIn; k += kCvThreads) { const int o = k / kCvIn, i = k - o * kCvIn; sm.W0t[i][o] = w[k]; sm.W0[o][i] = w[k]; }
-    for (int k = tid; k < kCvHid * 3; k += kCvThreads) sm.W0[k / 3][kCvIn + (k % 3)] = 0.f;
+    for (int k = tid; k < kCvHid * kCvIn; k += kCvThreads) { const int o = k / kCvIn, i = k - o * kCvIn; sm.W0t[i][o] = w[k]; }
     w += kCvHid * kCvIn;
     for (int k = tid; k < kCvHid; k += kCvThreads) sm.b0[k] = w[k];
     w += kCvHid;
-    for (int k = tid; k < kCvHid * kCvHid; k += kCvThreads) { const int o = k / kCvHid, i = k - o * kCvHid; sm.W1t[i][o] = w[k]; sm.W1[o][i] = w[k]; }
+    for (int k = tid; k < kCvHid * kCvHid; k += kCvThreads) { const int o = k / kCvHid, i = k - o * kCvHid; sm.W1t[i][o] = w[k]; }
     w += kCvHid * kCvHid;
     for (int k = tid; k < kCvHid; k += kCvThreads) sm.b1[k] = w[k];
     w += kCvHid;
@@ -517,7 +566,7 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
 #pragma unroll
     for (int c = 0; c < kCvC; c++) { cur[c] = __ldg(cb + (size_t)c * HW); dcur[c] = 0.f; }
   }
-  const float* src_b = a.src_feats + (size_t)b * K * kCvC * HW;
+  const float4* src_b = reinterpret_cast<const float4*>(a.src_packed) + (size_t)b * K * (kCvC / 4) * HW;
   float* dsrc_b = a.dL_dsrc + (size_t)b * K * kCvC * HW;
   const unsigned all = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
   const int d0 = blockIdx.y * planes_per_block, d1 = min(a.D, d0 + planes_per_block);
@@ -541,9 +590,9 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
       float x[kCvC];
       float dsum;
       unsigned geo, zero;
-      gather_sources(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, all, x, dsum, geo, zero);
+      gather_sources_packed(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, all, x, dsum, geo, zero);
       const unsigned valid = geo & ~zero;
-      if (zero) { float ds2; unsigned g2, z2; gather_sources(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, valid, x, ds2, g2, z2); }
+      if (zero) { float ds2; unsigned g2, z2; gather_sources_packed(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, valid, x, ds2, g2, z2); }
       const float rn = 1.0f / ((float)__popc(valid) + 1e-8f);
       float z1[kCvHid], z2v[kCvHid];
 #pragma unroll
@@ -578,24 +627,25 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
       // da1[i] = sum_o W1[o][i] dz2[o] ; dz1 = da1 * lk'(z1)
       float da1[kCvHid];
 #pragma unroll
-      for (int i = 0; i < kCvHid; i++) da1[i] = 0.f;
+      for (int i = 0; i < kCvHid; i++) {          // W1t[i][o] = W1[o][i]
+        float acc = 0.f;
 #pragma unroll
-      for (int o = 0; o < kCvHid; o++) {
-#pragma unroll
-        for (int i = 0; i < kCvHid; i++) da1[i] = fmaf(sm.W1[o][i], z2v[o], da1[i]);
+        for (int o = 0; o < kCvHid; o++) acc = fmaf(sm.W1t[i][o], z2v[o], acc);
+        da1[i] = acc;
       }
 #pragma unroll
       for (int i = 0; i < kCvHid; i++) { z1[i] = da1[i] * dleaky(z1[i]); myrow[kOffDz1 + i] = z1[i]; }
       // dx[i] = sum_o W0[o][i] dz1[o]   (x[] reused as dx[])
       float dxdot = 0.f;
 #pragma unroll
-      for (int i = 0; i < kCvC; i++) x[i] = 0.f;
+      for (int i = 0; i < kCvC; i++) {            // W0t[i][o] = W0[o][i]
+        float acc = 0.f;
 #pragma unroll
-      for (int o = 0; o < kCvHid; o++) {
-#pragma unroll
-        for (int i = 0; i < kCvC; i++) x[i] = fmaf(sm.W0[o][i], z1[o], x[i]);
-        dxdot = fmaf(sm.W0[o][kCvC], z1[o], dxdot);
+        for (int o = 0; o < kCvHid; o++) acc = fmaf(sm.W0t[i][o], z1[o], acc);
+        x[i] = acc;
       }
+#pragma unroll
+      for (int o = 0; o < kCvHid; o++) dxdot = fmaf(sm.W0t[kCvC][o], z1[o], dxdot);
       // ---- back through the masked means: dw_k[c] = [valid_k] dx[c]/n + [geo_k] cur[c] dxdot/n
       if (active && g != 0.f) {
         const float gd = dxdot * rn;
@@ -604,20 +654,28 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
           Taps t;
           make_taps(sm.proj + 12 * k, X0, X1, X2, H, W, uvx, uvy, t);
           const float fv = ((valid >> k) & 1u) ? rn : 0.f;
-          const float* __restrict__ s = src_b + (size_t)k * kCvC * HW;
+          const float4* __restrict__ s = src_b + (size_t)k * (kCvC / 4) * HW;
           float* __restrict__ ds = dsrc_b + (size_t)k * kCvC * HW;
 #pragma unroll
-          for (int c = 0; c < kCvC; c++) {
-            const float gw = fmaf(x[c], fv, cur[c] * gd);
-            float* dc = ds + (size_t)c * HW;
-            if (t.w00 != 0.f) atomicAdd(dc + t.o00, t.w00 * gw);
-            if (t.w01 != 0.f) atomicAdd(dc + t.o01, t.w01 * gw);
-            if (t.w10 != 0.f) atomicAdd(dc + t.o10, t.w10 * gw);
-            if (t.w11 != 0.f) atomicAdd(dc + t.o11, t.w11 * gw);
+          for (int g4 = 0; g4 < kCvC / 4; g4++) {
             // d dot_k / d cur[c] = w_k[c]  (re-gathered: cheaper than keeping K x 48 registers)
-            const float* __restrict__ sc = s + (size_t)c * HW;
-            const float wk = fmaf(t.w11, __ldg(sc + t.o11), fmaf(t.w10, __ldg(sc + t.o10), fmaf(t.w01, __ldg(sc + t.o01), t.w00 * __ldg(sc + t.o00))));
-            dcur[c] = fmaf(gd, wk, dcur[c]);
+            const float4* __restrict__ sg = s + (size_t)g4 * HW;
+            const float4 qa = __ldg(sg + t.o00), qb = __ldg(sg + t.o01), qc = __ldg(sg + t.o10), qd = __ldg(sg + t.o11);
+            const float wk[4] = {fmaf(t.w11, qd.x, fmaf(t.w10, qc.x, fmaf(t.w01, qb.x, t.w00 * qa.x))),
+                                 fmaf(t.w11, qd.y, fmaf(t.w10, qc.y, fmaf(t.w01, qb.y, t.w00 * qa.y))),
+                                 fmaf(t.w11, qd.z, fmaf(t.w10, qc.z, fmaf(t.w01, qb.z, t.w00 * qa.z))),
+                                 fmaf(t.w11, qd.w, fmaf(t.w10, qc.w, fmaf(t.w01, qb.w, t.w00 * qa.w)))};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int c = 4 * g4 + e;
+              const float gw = fmaf(x[c], fv, cur[c] * gd);
+              float* dc = ds + (size_t)c * HW;
+              if (t.w00 != 0.f) atomicAdd(dc + t.o00, t.w00 * gw);
+              if (t.w01 != 0.f) atomicAdd(dc + t.o01, t.w01 * gw);
+              if (t.w10 != 0.f) atomicAdd(dc + t.o10, t.w10 * gw);
+              if (t.w11 != 0.f) atomicAdd(dc + t.o11, t.w11 * gw);
+              dcur[c] = fmaf(gd, wk[e], dcur[c]);
+            }
           }
         }
       }
@@ -698,6 +756,7 @@ int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s) {
   int rc;
   const size_t n_src = (size_t)a.B * a.K * kCvC * HW, n_cur = (size_t)a.B * kCvC * HW;
   const size_t n_mlp = kCvHid * kCvIn + kCvHid + kCvHid * kCvHid + kCvHid + kCvHid + 1;
+  if ((rc = launch_pack(a, s))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(a.dL_dsrc, 0, n_src * sizeof(float), s), "memset dL_dsrc"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(a.dL_dcur, 0, n_cur * sizeof(float), s), "memset dL_dcur"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(a.dL_dmlp, 0, n_mlp * sizeof(float), s), "memset dL_dmlp"))) return rc;

@@ -21,6 +21,9 @@ namespace fs {
 //                               per load instruction); sh_stride is odd => conflict-free reads.
 //   float4 out[256 * 3]         records of one view, written back as contiguous 16-byte chunks.
 // Each thread projects ITS Gaussian into all V views: the 148 input bytes are read once, not V times.
+// DEG = active SH degree (compile time: the 3*(DEG+1)^2 coefficient loads become straight-line shared-memory
+// reads with immediate offsets; the generic loop cost ~300 instructions of predicates / address math per view).
+template <int DEG>
 __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy, int sh_stride) {
   extern __shared__ float4 smem4[];
   float4* s_out = smem4;                                   // [256*3]
@@ -92,13 +95,18 @@ __global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(FsRasterFwdArgs
           rgb[0] = __ldg(a.colors_precomp + 3 * (size_t)i); rgb[1] = __ldg(a.colors_precomp + 3 * (size_t)i + 1);
           rgb[2] = __ldg(a.colors_precomp + 3 * (size_t)i + 2);
         } else {
-          float sh[48];
-          const int nf = ((a.sh_degree + 1) * (a.sh_degree + 1)) * 3;   // only the active coefficients are used
+          constexpr int NC = (DEG + 1) * (DEG + 1);                      // only the active coefficients are used
+          float sh[NC * 3];                                              // sh[coef*3 + ch]
           const float* shp = s_sh + tid * sh_stride;
+          if (a.sh_layout) {       // [P,3,M] (the reference's Gaussians.harmonics): channel-major rows
+            const float* p0 = shp; const float* p1 = shp + a.M; const float* p2 = shp + 2 * a.M;
 #pragma unroll
-          for (int k = 0; k < 48; k++)   // sh[coef*3 + ch]; layout 1 = [P,3,M] (the reference's Gaussians.harmonics)
-            sh[k] = (k < nf) ? (a.sh_layout ? shp[(k % 3) * a.M + k / 3] : shp[k]) : 0.f;
-          clampmask = fsm::sh_to_rgb(a.sh_degree, mean, view + 32, sh, rgb);
+            for (int k = 0; k < NC; k++) { sh[3 * k] = p0[k]; sh[3 * k + 1] = p1[k]; sh[3 * k + 2] = p2[k]; }
+          } else {
+#pragma unroll
+            for (int k = 0; k < NC * 3; k++) sh[k] = shp[k];
+          }
+          clampmask = fsm::sh_to_rgb(DEG, mean, view + 32, sh, rgb);
         }
         float hx, hy;
         fsm::alpha_extent(pr.con_x, pr.con_y, pr.con_z, opacity, &hx, &hy);
@@ -378,11 +386,13 @@ int launch_preprocess(const FsRasterFwdArgs& a, cudaStream_t s) {
   if (a.P > 0) {
     const int sh_stride = (a.M * 3) | 1;
     const size_t smem = (size_t)kThreads * 3 * sizeof(float4) + (a.shs ? (size_t)kThreads * sh_stride * sizeof(float) : 0);
+    void (*kern)(FsRasterFwdArgs, int, int, int) =
+        a.sh_degree == 0 ? preprocess_kernel<0> : a.sh_degree == 1 ? preprocess_kernel<1> : a.sh_degree == 2 ? preprocess_kernel<2> : preprocess_kernel<3>;
     if (smem > 48 * 1024) {
-      if ((rc = check_cuda(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+      if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                            "cudaFuncSetAttribute(preprocess_kernel)"))) return rc;
     }
-    preprocess_kernel<<<(a.P + kThreads - 1) / kThreads, kThreads, smem, s>>>(a, gx, gy, sh_stride);
+    kern<<<(a.P + kThreads - 1) / kThreads, kThreads, smem, s>>>(a, gx, gy, sh_stride);
     if ((rc = check_cuda(cudaGetLastError(), "preprocess_kernel"))) return rc;
   }
   return FS_OK;

@@ -514,9 +514,11 @@ namespace fs {
 constexpr int kRowStride = 196;                  // floats per parked row (16-byte aligned segments)
 constexpr int kOffDz1 = 0, kOffX = 32, kOffDz2 = 84, kOffA1 = 116, kOffGa2 = 148, kOffG = 180;
 
-struct CvBwdSmem {                                // ~10.5 KB: with the 100 KB row buffer two CTAs fit per SM
+struct CvBwdSmem {
   float W0t[kCvIn][kCvHid];
   float W1t[kCvHid][kCvHid];
+  float W0[kCvHid][kCvIn + 3];                   // row-major copy for dx = W0^T dz1 (padded to 52)
+  float W1[kCvHid][kCvHid];
   float W2[kCvHid];
   float b0[kCvHid];
   float b1[kCvHid];
@@ -536,11 +538,12 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
   const size_t HW = (size_t)H * W;
   {
     const float* w = a.mlp;
-    for (int k = tid; k < kCvHid * kCvIn; k += kCvThreads) { const int o = k / kCvIn, i = k - o * kCvIn; sm.W0t[i][o] = w[k]; }
+    for (int k = tid; k < kCvHid * kCvIn; k += kCvThreads) { const int o = k / kCvIn, i = k - o * kCvIn; sm.W0t[i][o] = w[k]; sm.W0[o][i] = w[k]; }
+    for (int k = tid; k < kCvHid * 3; k += kCvThreads) sm.W0[k / 3][kCvIn + (k % 3)] = 0.f;
     w += kCvHid * kCvIn;
     for (int k = tid; k < kCvHid; k += kCvThreads) sm.b0[k] = w[k];
     w += kCvHid;
-    for (int k = tid; k < kCvHid * kCvHid; k += kCvThreads) { const int o = k / kCvHid, i = k - o * kCvHid; sm.W1t[i][o] = w[k]; }
+    for (int k = tid; k < kCvHid * kCvHid; k += kCvThreads) { const int o = k / kCvHid, i = k - o * kCvHid; sm.W1t[i][o] = w[k]; sm.W1[o][i] = w[k]; }
     w += kCvHid * kCvHid;
     for (int k = tid; k < kCvHid; k += kCvThreads) sm.b1[k] = w[k];
     w += kCvHid;
@@ -627,25 +630,24 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
       // da1[i] = sum_o W1[o][i] dz2[o] ; dz1 = da1 * lk'(z1)
       float da1[kCvHid];
 #pragma unroll
-      for (int i = 0; i < kCvHid; i++) {          // W1t[i][o] = W1[o][i]
-        float acc = 0.f;
+      for (int i = 0; i < kCvHid; i++) da1[i] = 0.f;
 #pragma unroll
-        for (int o = 0; o < kCvHid; o++) acc = fmaf(sm.W1t[i][o], z2v[o], acc);
-        da1[i] = acc;
+      for (int o = 0; o < kCvHid; o++) {
+#pragma unroll
+        for (int i = 0; i < kCvHid; i++) da1[i] = fmaf(sm.W1[o][i], z2v[o], da1[i]);
       }
 #pragma unroll
       for (int i = 0; i < kCvHid; i++) { z1[i] = da1[i] * dleaky(z1[i]); myrow[kOffDz1 + i] = z1[i]; }
       // dx[i] = sum_o W0[o][i] dz1[o]   (x[] reused as dx[])
       float dxdot = 0.f;
 #pragma unroll
-      for (int i = 0; i < kCvC; i++) {            // W0t[i][o] = W0[o][i]
-        float acc = 0.f;
+      for (int i = 0; i < kCvC; i++) x[i] = 0.f;
 #pragma unroll
-        for (int o = 0; o < kCvHid; o++) acc = fmaf(sm.W0t[i][o], z1[o], acc);
-        x[i] = acc;
+      for (int o = 0; o < kCvHid; o++) {
+#pragma unroll
+        for (int i = 0; i < kCvC; i++) x[i] = fmaf(sm.W0[o][i], z1[o], x[i]);
+        dxdot = fmaf(sm.W0[o][kCvC], z1[o], dxdot);
       }
-#pragma unroll
-      for (int o = 0; o < kCvHid; o++) dxdot = fmaf(sm.W0t[kCvC][o], z1[o], dxdot);
       // ---- back through the masked means: dw_k[c] = [valid_k] dx[c]/n + [geo_k] cur[c] dxdot/n
       if (active && g != 0.f) {
         const float gd = dxdot * rn;

@@ -208,8 +208,12 @@ __global__ void __launch_bounds__(kPtfThreads) ptf_compact_kernel(FsPtfArgs a) {
         a.o_coords[3 * (size_t)d_old] = a.coords[3 * (size_t)k]; a.o_coords[3 * (size_t)d_old + 1] = a.coords[3 * (size_t)k + 1];
         a.o_coords[3 * (size_t)d_old + 2] = a.coords[3 * (size_t)k + 2];
         a.o_dens[d_old] = a.dens[k]; a.o_wemb[d_old] = a.wemb[k]; a.o_depth[d_old] = a.depth[k];
-#pragma unroll
-        for (int e = 0; e < 16; e++) a.o_ext[16 * (size_t)d_old + e] = a.ext[16 * (size_t)k + e];
+        {
+          const float4* se = reinterpret_cast<const float4*>(a.ext + 16 * (size_t)k);
+          float4* de = reinterpret_cast<float4*>(a.o_ext + 16 * (size_t)d_old);
+          const float4 e0 = se[0], e1 = se[1], e2 = se[2], e3 = se[3];
+          de[0] = e0; de[1] = e1; de[2] = e2; de[3] = e3;
+        }
       } else {
         const int p = a.pix[k];
         const float w0 = a.dens[k], w1 = a.v_dens[p], ws = w0 + w1;
@@ -226,23 +230,50 @@ __global__ void __launch_bounds__(kPtfThreads) ptf_compact_kernel(FsPtfArgs a) {
       a.o_coords[3 * (size_t)d_px] = a.v_coords[3 * (size_t)k]; a.o_coords[3 * (size_t)d_px + 1] = a.v_coords[3 * (size_t)k + 1];
       a.o_coords[3 * (size_t)d_px + 2] = a.v_coords[3 * (size_t)k + 2];
       a.o_dens[d_px] = a.v_dens[k]; a.o_wemb[d_px] = a.v_wemb[k]; a.o_depth[d_px] = a.v_depth[k];
-#pragma unroll
-      for (int e = 0; e < 16; e++) a.o_ext[16 * (size_t)d_px + e] = a.v_ext[e];
+      {
+        const float4* se = reinterpret_cast<const float4*>(a.v_ext);
+        float4* de = reinterpret_cast<float4*>(a.o_ext + 16 * (size_t)d_px);
+        de[0] = se[0]; de[1] = se[1]; de[2] = se[2]; de[3] = se[3];
+      }
     }
   }
   __syncthreads();
-  // ---- feature rows (F floats): each warp copies whole rows, coalesced ----
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int t = warp; t < kPtfItems; t += 8) {
-    const int k = base + t;
-    const int d_old = s_dst_old[t], d_px = s_dst_px[t], pr = s_pair[t];
-    if (d_old >= 0) {
-      const float* src = pr >= 0 ? a.gru_out + (size_t)pr * F : a.feats + (size_t)k * F;
-      for (int e = lane; e < F; e += 32) a.o_feats[(size_t)d_old * F + e] = src[e];
+  // ---- feature rows: 16-byte chunks, one (row, chunk) pair per thread and iteration (independent loads in flight) ----
+  if ((F & 3) == 0) {
+    const int cpr = F >> 2;                                   // float4 chunks per row
+    const float4* feats4 = reinterpret_cast<const float4*>(a.feats);
+    const float4* gru4 = reinterpret_cast<const float4*>(a.gru_out);
+    const float4* vfeats4 = reinterpret_cast<const float4*>(a.v_feats);
+    float4* out4 = reinterpret_cast<float4*>(a.o_feats);
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < kPtfItems * cpr; idx += kPtfThreads) {
+      const int t = idx / cpr, ch = idx - t * cpr;
+      const int d_old = s_dst_old[t];
+      if (d_old >= 0) {
+        const int pr = s_pair[t];
+        const float4 v = pr >= 0 ? gru4[(size_t)pr * cpr + ch] : feats4[(size_t)(base + t) * cpr + ch];
+        out4[(size_t)d_old * cpr + ch] = v;
+      }
     }
-    if (d_px >= 0) {
-      const float* src = a.v_feats + (size_t)k * F;
-      for (int e = lane; e < F; e += 32) a.o_feats[(size_t)d_px * F + e] = src[e];
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < kPtfItems * cpr; idx += kPtfThreads) {
+      const int t = idx / cpr, ch = idx - t * cpr;
+      const int d_px = s_dst_px[t];
+      if (d_px >= 0) out4[(size_t)d_px * cpr + ch] = vfeats4[(size_t)(base + t) * cpr + ch];
+    }
+  } else {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = warp; t < kPtfItems; t += 8) {
+      const int k = base + t;
+      const int d_old = s_dst_old[t], d_px = s_dst_px[t], pr = s_pair[t];
+      if (d_old >= 0) {
+        const float* src = pr >= 0 ? a.gru_out + (size_t)pr * F : a.feats + (size_t)k * F;
+        for (int e = lane; e < F; e += 32) a.o_feats[(size_t)d_old * F + e] = src[e];
+      }
+      if (d_px >= 0) {
+        const float* src = a.v_feats + (size_t)k * F;
+        for (int e = lane; e < F; e += 32) a.o_feats[(size_t)d_px * F + e] = src[e];
+      }
     }
   }
 }

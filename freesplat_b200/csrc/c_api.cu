@@ -89,6 +89,12 @@ int fs_mark_visible(int32_t P, const float* means3D, const float* view, uint8_t*
   return launch_mark_visible(P, means3D, view, visible, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int fs_camera_records(int32_t V, const float* extrinsics, const float* intrinsics, const float* near, const float* far,
+                      const float* bg, int32_t scale_invariant, float* views, void* stream) {
+  FS_REQUIRE(V >= 0 && (V == 0 || (extrinsics && intrinsics && near && far && bg && views)), "bad arguments");
+  return launch_camera_records(V, extrinsics, intrinsics, near, far, bg, scale_invariant, views, reinterpret_cast<cudaStream_t>(stream));
+}
+
 static int check_cv(const FsCostVolumeArgs* a) {
   FS_REQUIRE(a != nullptr, "args is NULL");
   FS_REQUIRE(a->B >= 1 && a->K >= 1 && a->K <= 16 && a->H >= 1 && a->W >= 1 && a->D >= 1, "bad sizes (K must be 1..16)");

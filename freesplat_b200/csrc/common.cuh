@@ -25,6 +25,8 @@ int launch_render_bwd(const FsRasterBwdArgs& a, cudaStream_t s);     // raster_r
 int launch_preprocess_bwd(const FsRasterBwdArgs& a, cudaStream_t s); // raster_pre.cu
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* vis, cudaStream_t s);
 
+int launch_camera_records(int V, const float* ext, const float* K, const float* near, const float* far, const float* bg,
+                          int scale_invariant, float* views, cudaStream_t s);   // raster_pre.cu
 int launch_cost_volume_fwd(const FsCostVolumeArgs& a, cudaStream_t s);  // cost_volume.cu
 int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s);  // cost_volume.cu
 

@@ -377,6 +377,82 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Camera records: what the reference adapter assembles with ~30 tiny torch launches per call
+// (cuda_splatting.py:64-87 + geometry/projection.py:233-247; 0.76 ms of host-driven launches, 3x the whole
+// raster pipeline) as ONE launch, one thread per view, evaluated in fp64 and rounded once to fp32.
+__device__ inline void inv3(const double* m, double* o) {
+  const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  const double det = m[0] * c00 + m[1] * c01 + m[2] * c02, id = 1.0 / det;
+  o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  o[3] = c01 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = c02 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+
+__global__ void camera_records_kernel(int V, const float* __restrict__ extrinsics, const float* __restrict__ intrinsics,
+                                      const float* __restrict__ near, const float* __restrict__ far, const float* __restrict__ bg,
+                                      int scale_invariant, float* __restrict__ views) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  double E[16], K[9];
+  for (int k = 0; k < 16; k++) E[k] = (double)extrinsics[16 * v + k];
+  for (int k = 0; k < 9; k++) K[k] = (double)intrinsics[9 * v + k];
+  double nr = (double)near[v], fr = (double)far[v];
+  const float scale_f = scale_invariant ? 1.0f / near[v] : 1.0f;     // fp32, exactly as `scale = 1 / near`
+  const double scale = (double)scale_f;
+  if (scale_invariant) {
+    // the reference scales in fp32: extrinsics[:3,3] * scale, near * scale, far * scale
+    E[3] = (double)((float)E[3] * scale_f); E[7] = (double)((float)E[7] * scale_f); E[11] = (double)((float)E[11] * scale_f);
+    nr = (double)(near[v] * scale_f); fr = (double)(far[v] * scale_f);
+  }
+  // ---- fov from the normalised intrinsics (get_fov) ----
+  double Ki[9];
+  inv3(K, Ki);
+  auto dir = [&](double x, double y, double* o) {
+    o[0] = Ki[0] * x + Ki[1] * y + Ki[2]; o[1] = Ki[3] * x + Ki[4] * y + Ki[5]; o[2] = Ki[6] * x + Ki[7] * y + Ki[8];
+    const double n = sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
+    o[0] /= n; o[1] /= n; o[2] /= n;
+  };
+  double l[3], r[3], t[3], b[3];
+  dir(0.0, 0.5, l); dir(1.0, 0.5, r); dir(0.5, 0.0, t); dir(0.5, 1.0, b);
+  const double fov_x = acos(l[0] * r[0] + l[1] * r[1] + l[2] * r[2]);
+  const double fov_y = acos(t[0] * b[0] + t[1] * b[1] + t[2] * b[2]);
+  const double tx = tan(0.5 * fov_x), ty = tan(0.5 * fov_y);
+  // ---- projection matrix (get_projection_matrix) ----
+  const double top = ty * nr, right = tx * nr;
+  double P[16] = {0};
+  P[0] = 2 * nr / (2 * right); P[5] = 2 * nr / (2 * top);
+  P[2] = 0.0; P[6] = 0.0;                       // symmetric frustum: (right+left), (top+bottom) = 0
+  P[14] = 1.0; P[10] = fr / (fr - nr); P[11] = -(fr * nr) / (fr - nr);
+  // ---- world->camera = inverse of the (rigid or general affine) camera-to-world matrix ----
+  double R[9] = {E[0], E[1], E[2], E[4], E[5], E[6], E[8], E[9], E[10]}, Ri[9];
+  inv3(R, Ri);
+  double Vw[16] = {Ri[0], Ri[1], Ri[2], -(Ri[0] * E[3] + Ri[1] * E[7] + Ri[2] * E[11]),
+                   Ri[3], Ri[4], Ri[5], -(Ri[3] * E[3] + Ri[4] * E[7] + Ri[5] * E[11]),
+                   Ri[6], Ri[7], Ri[8], -(Ri[6] * E[3] + Ri[7] * E[7] + Ri[8] * E[11]),
+                   0, 0, 0, 1};
+  float* o = views + (size_t)v * kViewFloats;
+  // records hold the TRANSPOSES (flat m[c*4+r] = M[r][c]); full projection = P * Vw
+  for (int rr = 0; rr < 4; rr++)
+    for (int c = 0; c < 4; c++) {
+      o[c * 4 + rr] = (float)Vw[rr * 4 + c];
+      double acc = 0.0;
+      for (int k = 0; k < 4; k++) acc += P[rr * 4 + k] * Vw[k * 4 + c];
+      o[16 + c * 4 + rr] = (float)acc;
+    }
+  o[32] = (float)E[3]; o[33] = (float)E[7]; o[34] = (float)E[11];
+  o[35] = bg[3 * v]; o[36] = bg[3 * v + 1]; o[37] = bg[3 * v + 2];
+  o[38] = (float)tx; o[39] = (float)ty; o[40] = scale_f;
+  for (int k = 41; k < kViewFloats; k++) o[k] = 0.f;
+}
+
+int launch_camera_records(int V, const float* ext, const float* K, const float* near, const float* far, const float* bg,
+                          int scale_invariant, float* views, cudaStream_t s) {
+  if (V <= 0) return FS_OK;
+  camera_records_kernel<<<(V + 63) / 64, 64, 0, s>>>(V, ext, K, near, far, bg, scale_invariant, views);
+  return check_cuda(cudaGetLastError(), "camera_records_kernel");
+}
+
 int launch_preprocess(const FsRasterFwdArgs& a, cudaStream_t s) {
   const int gx = tiles_x(a.W), gy = tiles_y(a.H);
   const size_t nt = (size_t)a.V * gx * gy;

@@ -82,6 +82,27 @@ def camera_records(extrinsics, intrinsics, near, far, background_color, scale_in
     return views, torch.stack((tan_fov_x, tan_fov_y), dim=-1)
 
 
+def camera_records_fused(extrinsics, intrinsics, near, far, background_color, scale_invariant=True):
+    """Same result as camera_records (to fp32 rounding: evaluated in fp64 on the device) in ONE kernel launch
+    (fs_camera_records) instead of ~30 host-driven torch launches."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    V = extrinsics.shape[0]
+    dev = extrinsics.device
+    if not extrinsics.is_cuda:
+        raise _lib.FreeSplatB200Error("camera_records_fused needs CUDA tensors")
+    f = lambda t: t.detach().float().contiguous()
+    e, k, n, fr, bg = f(extrinsics), f(intrinsics), f(near), f(far), f(background_color)
+    views = torch.empty((V, 48), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.fs_camera_records(C.c_int32(V), C.c_void_p(e.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(n.data_ptr()),
+                                       C.c_void_p(fr.data_ptr()), C.c_void_p(bg.data_ptr()), C.c_int32(int(scale_invariant)),
+                                       C.c_void_p(views.data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                   "fs_camera_records")
+    return views
+
+
 def render_views(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
                  gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant=True,
                  use_sh=True, depth_grad=False, check_overflow=None):
@@ -99,7 +120,7 @@ def render_views(extrinsics, intrinsics, near, far, image_shape, background_colo
     h, w = image_shape
     n = gaussian_sh_coefficients.shape[-1]
     degree = isqrt(n) - 1
-    views, _ = camera_records(extrinsics, intrinsics, near, far, background_color, scale_invariant)
+    views = camera_records_fused(extrinsics, intrinsics, near, far, background_color, scale_invariant)
     color, radii, depth, _ = rasterize_views(
         gaussian_means, gaussian_opacities, views, h, w,
         shs=gaussian_sh_coefficients if use_sh else None,

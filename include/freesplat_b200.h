@@ -222,6 +222,11 @@ int fs_device_sm_count(void);         /* negative FsStatus on failure           
 
 int fs_raster_forward(const FsRasterFwdArgs* args, void* stream);
 int fs_raster_backward(const FsRasterBwdArgs* args, void* stream);
+/* Builds the [V,FS_VIEW_FLOATS] camera records from camera-to-world extrinsics [V,4,4], normalised intrinsics
+ * [V,3,3], near/far [V] and background colours [V,3] -- the work of cuda_splatting.py:64-87 (scale-invariant
+ * rescale, get_fov, get_projection_matrix, inverse, transposes) in one launch.                       */
+int fs_camera_records(int32_t V, const float* extrinsics, const float* intrinsics, const float* near, const float* far,
+                      const float* bg, int32_t scale_invariant, float* views, void* stream);
 /* visible[i] = (p_view.z > 0.2) for one view (upstream mark_visible / checkFrustum) */
 int fs_mark_visible(int32_t P, const float* means3D, const float* view /*FS_VIEW_FLOATS*/,
                     uint8_t* visible, void* stream);

@@ -29,7 +29,7 @@ class FsCostVolumeArgs(C.Structure):
         ("cur_feats", C.c_void_p), ("src_feats", C.c_void_p), ("proj", C.c_void_p), ("cur_invK", C.c_void_p),
         ("planes", C.c_void_p), ("mlp", C.c_void_p), ("out", C.c_void_p),
         ("dL_dout", C.c_void_p), ("dL_dcur", C.c_void_p), ("dL_dsrc", C.c_void_p), ("dL_dmlp", C.c_void_p),
-        ("src_packed", C.c_void_p), ("mlp_mode", C.c_int32),
+        ("src_packed", C.c_void_p), ("dsrc_packed", C.c_void_p), ("mlp_mode", C.c_int32),
     ]
 
 
@@ -89,7 +89,8 @@ class _CostVolumeFn(torch.autograd.Function):
         g = g.float().contiguous()
         d_cur = torch.empty_like(cur); d_src = torch.empty_like(src); d_mlp = torch.empty_like(mlp_flat)
         a = _args(cur, src, proj, invk, planes, mlp_flat)
-        packed = torch.empty_like(src)
+        packed = torch.empty_like(src); dpacked = torch.empty_like(src)
+        a.dsrc_packed = ptr(dpacked)
         a.dL_dout = ptr(g); a.dL_dcur = ptr(d_cur); a.dL_dsrc = ptr(d_src); a.dL_dmlp = ptr(d_mlp); a.src_packed = ptr(packed)
         with torch.cuda.device(cur.device):
             check(L.fs_cost_volume_backward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)),

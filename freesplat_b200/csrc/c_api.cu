@@ -112,7 +112,7 @@ int fs_cost_volume_forward(const FsCostVolumeArgs* a, void* stream) {
 
 int fs_cost_volume_backward(const FsCostVolumeArgs* a, void* stream) {
   if (int rc = check_cv(a)) return rc;
-  FS_REQUIRE(a->dL_dout && a->dL_dcur && a->dL_dsrc && a->dL_dmlp && a->src_packed, "NULL gradient / scratch buffer");
+  FS_REQUIRE(a->dL_dout && a->dL_dcur && a->dL_dsrc && a->dL_dmlp && a->src_packed && a->dsrc_packed, "NULL gradient / scratch buffer");
   return launch_cost_volume_bwd(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 

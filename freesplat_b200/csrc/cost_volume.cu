@@ -526,6 +526,21 @@ struct CvBwdSmem {
   float proj[16 * 12];
 };
 
+// inverse of cv_pack_kernel: [maps][C/4][HW][4] -> NCHW
+__global__ void __launch_bounds__(256) cv_unpack_kernel(const float4* __restrict__ src, float* __restrict__ dst, size_t HW, size_t total) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const size_t pix = i % HW, mg = i / HW;
+  const float4 v = src[i];
+  float* d = dst + (mg * 4) * HW + pix;
+  d[0] = v.x; d[HW] = v.y; d[2 * HW] = v.z; d[3 * HW] = v.w;
+}
+
+// one 16-byte vector reduction (REDG.E.ADD.F32x4): four channels of one tap
+__device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ float dleaky(float z) { return z > 0.f ? 1.f : 0.01f; }
 
 __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolumeArgs a, int planes_per_block) {
@@ -570,7 +585,7 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
     for (int c = 0; c < kCvC; c++) { cur[c] = __ldg(cb + (size_t)c * HW); dcur[c] = 0.f; }
   }
   const float4* src_b = reinterpret_cast<const float4*>(a.src_packed) + (size_t)b * K * (kCvC / 4) * HW;
-  float* dsrc_b = a.dL_dsrc + (size_t)b * K * kCvC * HW;
+  float4* dsrc_b = reinterpret_cast<float4*>(a.dsrc_packed) + (size_t)b * K * (kCvC / 4) * HW;
   const unsigned all = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
   const int d0 = blockIdx.y * planes_per_block, d1 = min(a.D, d0 + planes_per_block);
   float* myrow = rows + (size_t)tid * kRowStride;
@@ -657,7 +672,7 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
           make_taps(sm.proj + 12 * k, X0, X1, X2, H, W, uvx, uvy, t);
           const float fv = ((valid >> k) & 1u) ? rn : 0.f;
           const float4* __restrict__ s = src_b + (size_t)k * (kCvC / 4) * HW;
-          float* __restrict__ ds = dsrc_b + (size_t)k * kCvC * HW;
+          float4* __restrict__ ds = dsrc_b + (size_t)k * (kCvC / 4) * HW;
 #pragma unroll
           for (int g4 = 0; g4 < kCvC / 4; g4++) {
             // d dot_k / d cur[c] = w_k[c]  (re-gathered: cheaper than keeping K x 48 registers)
@@ -667,17 +682,18 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
                                  fmaf(t.w11, qd.y, fmaf(t.w10, qc.y, fmaf(t.w01, qb.y, t.w00 * qa.y))),
                                  fmaf(t.w11, qd.z, fmaf(t.w10, qc.z, fmaf(t.w01, qb.z, t.w00 * qa.z))),
                                  fmaf(t.w11, qd.w, fmaf(t.w10, qc.w, fmaf(t.w01, qb.w, t.w00 * qa.w)))};
+            float gw[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
               const int c = 4 * g4 + e;
-              const float gw = fmaf(x[c], fv, cur[c] * gd);
-              float* dc = ds + (size_t)c * HW;
-              if (t.w00 != 0.f) atomicAdd(dc + t.o00, t.w00 * gw);
-              if (t.w01 != 0.f) atomicAdd(dc + t.o01, t.w01 * gw);
-              if (t.w10 != 0.f) atomicAdd(dc + t.o10, t.w10 * gw);
-              if (t.w11 != 0.f) atomicAdd(dc + t.o11, t.w11 * gw);
+              gw[e] = fmaf(x[c], fv, cur[c] * gd);
               dcur[c] = fmaf(gd, wk[e], dcur[c]);
             }
+            float4* dg = ds + (size_t)g4 * HW;     // d(warped) scattered with one 16-byte reduction per tap
+            if (t.w00 != 0.f) red_add_v4(dg + t.o00, t.w00 * gw[0], t.w00 * gw[1], t.w00 * gw[2], t.w00 * gw[3]);
+            if (t.w01 != 0.f) red_add_v4(dg + t.o01, t.w01 * gw[0], t.w01 * gw[1], t.w01 * gw[2], t.w01 * gw[3]);
+            if (t.w10 != 0.f) red_add_v4(dg + t.o10, t.w10 * gw[0], t.w10 * gw[1], t.w10 * gw[2], t.w10 * gw[3]);
+            if (t.w11 != 0.f) red_add_v4(dg + t.o11, t.w11 * gw[0], t.w11 * gw[1], t.w11 * gw[2], t.w11 * gw[3]);
           }
         }
       }
@@ -759,7 +775,7 @@ int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s) {
   const size_t n_src = (size_t)a.B * a.K * kCvC * HW, n_cur = (size_t)a.B * kCvC * HW;
   const size_t n_mlp = kCvHid * kCvIn + kCvHid + kCvHid * kCvHid + kCvHid + kCvHid + 1;
   if ((rc = launch_pack(a, s))) return rc;
-  if ((rc = check_cuda(cudaMemsetAsync(a.dL_dsrc, 0, n_src * sizeof(float), s), "memset dL_dsrc"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(a.dsrc_packed, 0, n_src * sizeof(float), s), "memset dsrc_packed"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(a.dL_dcur, 0, n_cur * sizeof(float), s), "memset dL_dcur"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(a.dL_dmlp, 0, n_mlp * sizeof(float), s), "memset dL_dmlp"))) return rc;
   const size_t smem = ((sizeof(CvBwdSmem) + 15) / 16) * 16 + (size_t)kCvThreads * kRowStride * sizeof(float);
@@ -767,7 +783,10 @@ int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s) {
                        "cudaFuncSetAttribute(cost_volume_bwd_kernel)"))) return rc;
   dim3 grid((unsigned)((HW + kCvThreads - 1) / kCvThreads), (unsigned)((a.D + ppb - 1) / ppb), (unsigned)a.B);
   cost_volume_bwd_kernel<<<grid, kCvThreads, smem, s>>>(a, ppb);
-  return check_cuda(cudaGetLastError(), "cost_volume_bwd_kernel");
+  if ((rc = check_cuda(cudaGetLastError(), "cost_volume_bwd_kernel"))) return rc;
+  const size_t total = n_src / 4;
+  cv_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(a.dsrc_packed), a.dL_dsrc, HW, total);
+  return check_cuda(cudaGetLastError(), "cv_unpack_kernel");
 }
 
 }  // namespace fs

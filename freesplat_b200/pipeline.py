@@ -8,7 +8,7 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from . import decoder
+from . import _lib, decoder, rasterizer
 
 
 class HostRenderPipeline:
@@ -28,6 +28,7 @@ class HostRenderPipeline:
         self.ev_copied = [torch.cuda.Event() for _ in range(depth)]
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]        # kernels of slot finished
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]         # host outputs of slot are valid
+        self.status = [None] * depth      # device status word of the slot's forward (overflow flag)
         self.n = 0
 
     def submit(self, host: Dict[str, torch.Tensor]) -> int:
@@ -52,6 +53,7 @@ class HostRenderPipeline:
             c, dp = decoder.render_views(d["extrinsics"], d["intrinsics"], d["near"], d["far"], (self.h, self.w), self.bg,
                                          d["means"], d["covariances"], d["harmonics"], d["opacities"],
                                          check_overflow="deferred" if self.n > self.depth else "sync")
+            self.status[slot] = rasterizer.last_deferred_status() if self.n > self.depth else None
             self.ev_done[slot].record(self.s_run)
             self.ev_in_free[slot].record(self.s_run)
         with torch.cuda.stream(self.s_d2h):
@@ -64,6 +66,10 @@ class HostRenderPipeline:
 
     def wait(self, slot: int):
         self.ev_out[slot].synchronize()
+        st = self.status[slot]
+        if st is not None and int(st.cpu()[2]):
+            raise _lib.FreeSplatB200Error("tile-instance workspace overflowed in a deferred-check step; "
+                                          "re-submit the scene (the next sync-checked call grows the workspace)")
         return self.out_c[slot], self.out_d[slot]
 
     def drain(self):

@@ -65,6 +65,15 @@ _capacity_hint: dict = {}
 _ASYNC = os.environ.get("FREESPLAT_B200_DEFERRED_CHECK", "0") == "1"
 
 
+# status word of the most recent forward issued with check_overflow="deferred"
+_deferred: dict = {"status": None}
+
+
+def last_deferred_status() -> Optional[torch.Tensor]:
+    """Device tensor [4] {R_lo, R_hi, overflow, 0} of the last deferred-check forward (None if there was none)."""
+    return _deferred["status"]
+
+
 def _initial_capacity(P: int, V: int) -> int:
     return max(8 * P * V, 1 << 18)
 
@@ -158,6 +167,7 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
                     check(L.fs_raster_forward(C.byref(a), C.c_void_p(stream)), "fs_raster_forward")
                 stage_events[3].record()
             if check_overflow != "sync":
+                _deferred["status"] = st.status          # the caller (or the next call) must look at it
                 return st
             s = st.status.cpu()
             R = int(s[0]) | (int(s[1]) << 32)

@@ -163,6 +163,8 @@ typedef struct FsCostVolumeArgs {
   float* dL_dmlp;          /* packed like `mlp` (zeroed by the call, then accumulated)       */
   float* src_packed;       /* scratch [B,K,C/4,H*W,4]: channel-packed copy of src_feats written by the call
                               (one 16-byte load per tap and 4 channels in the gather)         */
+  float* dsrc_packed;      /* backward scratch [B,K,C/4,H*W,4]: dL_dsrc accumulated with 16-byte vector reductions,
+                              unpacked to NCHW at the end of the call                           */
   int32_t mlp_mode;        /* forward: 0 = tcgen05 tensor cores (3xTF32, fp32-accurate), 1 = fp32 CUDA cores
                               (validation of mode 0)                                         */
 } FsCostVolumeArgs;

@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(kThreads) render_fwd_kernel(
   const uint32_t aT = (uint32_t)__cvta_generic_to_shared(sm.T), aA = (uint32_t)__cvta_generic_to_shared(sm.A),
                  aC = (uint32_t)__cvta_generic_to_shared(sm.C), aB = (uint32_t)__cvta_generic_to_shared(sm.B);
 
-  // T > 0: pixel still accumulating.  T < 0: finished (its final transmittance is in T_fin).
-  float T = inside ? 1.f : -1.f, T_fin = 1.f;
+  // T > 0: pixel still accumulating.  T < 0: finished, |T| is its final transmittance.
+  float T = inside ? 1.f : -1.f;
   float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
   uint32_t last = 0;
 
@@ -123,15 +123,14 @@ __global__ void __launch_bounds__(kThreads) render_fwd_kernel(
         const float w = acc ? alpha * T : 0.f;
         C0 = fmaf(c.x, w, C0); C1 = fmaf(c.y, w, C1); C2 = fmaf(c.z, w, C2);
         Dp = fmaf(c.w, w, Dp);
-        T_fin = fin ? T : T_fin;
-        T = fin ? -1.f : (acc ? test_T : T);
+        T = fin ? -T : (acc ? test_T : T);
         last = acc ? pos0 + jj : last;
       }
       if (__all_sync(kFull, T < 0.f)) break;
     }
   }
   if (inside) {
-    if (T > 0.f) T_fin = T;
+    const float T_fin = fabsf(T);
     const float* bg = views + (size_t)v * kViewFloats + 35;
     const size_t HW = (size_t)H * W, pix = (size_t)py * W + px;
     float* oc = out_color + (size_t)v * 3 * HW;

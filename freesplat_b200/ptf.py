@@ -141,7 +141,7 @@ class _PtfMerge(torch.autograd.Function):
 
 
 def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, image_shape, depth_thres=0.1,
-               E_inv=None, return_debug=False):
+               E_inv=None, return_debug=False, timings=None):
     """Flat form: feats [V,HW,F], coords [V,HW,3], dens/wemb [V,HW], depths [V,HW], extrinsics [V,4,4] (c2w),
     intrinsics [V,3,3] (normalised).  Returns (feats [N,F], coords [N,3], ext [N,4,4], depth [N]) (+ debug).
     With autograd enabled and differentiable inputs the result is differentiable w.r.t. feats, coords, dens,
@@ -193,8 +193,13 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
             vdet = tuple(t.detach() for t in view)
             out_bufs = None if need_grad else (nxt.feats, nxt.coords, nxt.dens, nxt.wemb, nxt.ext, nxt.depth)
             a = _ptf_args(h, w, F, N, depth_thres, det, cin, vdet, scratch, counts[i], out_bufs)
+            if timings is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record()
             check(L.fs_ptf_match(C.byref(a), C.c_void_p(stream)), "fs_ptf_match")
             c = counts[i].tolist()                         # the one host read of this step
+            if timings is not None:
+                ev[1].record()
             M, N_out = c[2], c[4]
             gru_out = None
             if M > 0:
@@ -205,6 +210,8 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
                 e_h = positional_encoding(torch.stack([dens[i][pp], state[3][pj]], -1), 6)
                 gru_out = gru(inp[None, :, None, :], hidden[None, :, None, :], e_in[None, :, None, :],
                               e_h[None, :, None, :])[0, :, 0, :].float().contiguous()
+            if timings is not None:
+                ev[2].record()
             if return_debug:
                 debug.append(dict(pix=pix[:N].clone(), zeta=zeta[:N].clone(), match=match[:N].clone(),
                                   append=append.clone(), zbuf=zbuf.clone(), counts=c))
@@ -217,6 +224,10 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
                 check(L.fs_ptf_merge(C.byref(a), C.c_void_p(stream)), "fs_ptf_merge")
                 cur, nxt = nxt, cur
                 state = (cur.feats, cur.coords, cur.dens, cur.wemb, cur.ext, cur.depth)
+            if timings is not None:
+                ev[3].record(); torch.cuda.synchronize()
+                timings.append(dict(step=i, N_in=c[0], matched=M, N_out=N_out, match_ms=ev[0].elapsed_time(ev[1]),
+                                    gru_ms=ev[1].elapsed_time(ev[2]), merge_ms=ev[2].elapsed_time(ev[3])))
             N = N_out
     out = (state[0][:N], state[1][:N], state[4][:N].reshape(N, 4, 4), state[5][:N])
     if return_debug:

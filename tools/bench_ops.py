@@ -57,8 +57,13 @@ for V in (3, 10):
         out = ptf.fuse_views(g, *args, hw)
         ms = timeit(lambda: ptf.fuse_views(g, *args, hw), n=3, warm=1)
     N = out[0].shape[0]
+    tm = []
+    with torch.no_grad():
+        ptf.fuse_views(g, *args, hw, timings=tm)
     res[f"ptf_V{V}_640x480"] = {"ms": ms, "N_out": N, "ratio": N / (V * h * w),
-                                "alg_bytes": 280 * h * w * V + 344 * N}
+                                "alg_bytes": 280 * h * w * V + 344 * N,
+                                "per_step_ms": {k: round(sum(t[k] for t in tm) / len(tm), 3) for k in ("match_ms", "gru_ms", "merge_ms")},
+                                "matched_mean": sum(t["matched"] for t in tm) / len(tm)}
 # ---- raster fwd + bwd (BASELINE config 3: 4 target views, MSE loss on colour) ----
 from freesplat_b200 import decoder  # noqa: E402
 sc = synth.pixel_aligned_scene(seed=0, h=480, w=640, n_context=3, n_target=4, keep=460800).to(dev)

@@ -137,4 +137,18 @@ int fs_ptf_merge(const FsPtfArgs* a, void* stream) {
   return launch_ptf_merge(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int fs_ptf_gru_inputs(int32_t M, int32_t F, const int32_t* pair_j, const int32_t* pair_p, const float* feats, const float* dens,
+                      const float* wemb, const float* v_feats, const float* v_dens, const float* v_wemb, float* A1, void* stream) {
+  FS_REQUIRE(M >= 0 && F >= 1 && (M == 0 || (pair_j && pair_p && feats && dens && wemb && v_feats && v_dens && v_wemb && A1)), "bad arguments");
+  return launch_ptf_gru_inputs(M, F, pair_j, pair_p, feats, dens, wemb, v_feats, v_dens, v_wemb, A1, reinterpret_cast<cudaStream_t>(stream));
+}
+int fs_ptf_gru_update(int32_t M, int32_t F, const float* A1, const float* r_lin, float* U, void* stream) {
+  FS_REQUIRE(M >= 0 && F >= 1 && (M == 0 || (A1 && r_lin && U)), "bad arguments");
+  return launch_ptf_gru_update(M, F, A1, r_lin, U, reinterpret_cast<cudaStream_t>(stream));
+}
+int fs_ptf_gru_output(int32_t M, int32_t F, const float* A1, const float* z_lin, const float* q_lin, float* out, void* stream) {
+  FS_REQUIRE(M >= 0 && F >= 1 && (M == 0 || (A1 && z_lin && q_lin && out)), "bad arguments");
+  return launch_ptf_gru_output(M, F, A1, z_lin, q_lin, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

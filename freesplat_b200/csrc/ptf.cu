@@ -288,6 +288,83 @@ static int ptf_fill_u32(uint32_t* p, uint32_t v, int n, cudaStream_t s) {
   return check_cuda(cudaGetLastError(), "ptf_fill_kernel");
 }
 
+// ---- GRU glue (networks.py:201-214) around the cuBLAS GEMMs: gathers, positional encodings, concatenations and
+// gates of the matched pairs in three launches instead of ~30 element-wise torch kernels per fused view ----
+__device__ __forceinline__ void pe6(float x, float* o) {   // encoder_freesplat.py:62-77: (sin, cos)(x * 2^f), f = 0..5
+  float s = x;
+#pragma unroll
+  for (int f = 0; f < 6; f++) { o[2 * f] = sinf(s); o[2 * f + 1] = cosf(s); s = s * 2.0f; }
+}
+
+// A1[m] = [hidden(F) | PE(v_dens[p], wemb[j]) (24) | input(F) | PE(dens[j], v_wemb[p]) (24)]     (concat_input of the GRU)
+__global__ void __launch_bounds__(256) ptf_gru_inputs_kernel(int M, int F, const int* __restrict__ pair_j, const int* __restrict__ pair_p,
+                                                             const float* __restrict__ feats, const float* __restrict__ dens,
+                                                             const float* __restrict__ wemb, const float* __restrict__ v_feats,
+                                                             const float* __restrict__ v_dens, const float* __restrict__ v_wemb,
+                                                             float* __restrict__ A1) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);      // one warp per pair
+  if (m >= M) return;
+  const int j = pair_j[m], p = pair_p[m];
+  const int ld = 2 * F + 48;
+  float* row = A1 + (size_t)m * ld;
+  for (int e = lane; e < F; e += 32) { row[e] = feats[(size_t)j * F + e]; row[F + 24 + e] = v_feats[(size_t)p * F + e]; }
+  if (lane < 4) {
+    // lane 0: PE(v_dens[p]) ; 1: PE(wemb[j])  -> e_h    ; 2: PE(dens[j]) ; 3: PE(v_wemb[p]) -> e_in
+    const float x = lane == 0 ? v_dens[p] : lane == 1 ? wemb[j] : lane == 2 ? dens[j] : v_wemb[p];
+    float o[12];
+    pe6(x, o);
+    float* dst = row + (lane < 2 ? F + 12 * lane : 2 * F + 24 + 12 * (lane - 2));
+#pragma unroll
+    for (int k = 0; k < 12; k++) dst[k] = o[k];
+  }
+}
+
+// U[m] = [sigmoid(r_lin[m]) * hidden | input_feat_1]  (update_feat)
+__global__ void __launch_bounds__(256) ptf_gru_update_kernel(int M, int F, const float* __restrict__ A1, const float* __restrict__ r_lin,
+                                                             float* __restrict__ U) {
+  const int ld1 = 2 * F + 48, ldu = 2 * F + 24;
+  const size_t total = (size_t)M * ldu;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const size_t m = i / ldu; const int c = (int)(i - m * ldu);
+  float v;
+  if (c < F) v = A1[m * ld1 + c] * (1.0f / (1.0f + expf(-r_lin[m * F + c])));
+  else v = A1[m * ld1 + F + 24 + (c - F)];
+  U[i] = v;
+}
+
+// out = (1 - z) * hidden + z * tanh(q_lin),  z = sigmoid(z_lin)
+__global__ void __launch_bounds__(256) ptf_gru_output_kernel(int M, int F, const float* __restrict__ A1, const float* __restrict__ z_lin,
+                                                             const float* __restrict__ q_lin, float* __restrict__ out) {
+  const size_t total = (size_t)M * F;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const size_t m = i / F; const int c = (int)(i - m * F);
+  const float z = 1.0f / (1.0f + expf(-z_lin[i]));
+  const float h = A1[m * (2 * F + 48) + c];
+  out[i] = (1.0f - z) * h + z * tanhf(q_lin[i]);
+}
+
+int launch_ptf_gru_inputs(int M, int F, const int* pj, const int* pp, const float* feats, const float* dens, const float* wemb,
+                          const float* v_feats, const float* v_dens, const float* v_wemb, float* A1, cudaStream_t s) {
+  if (M <= 0) return FS_OK;
+  ptf_gru_inputs_kernel<<<(M + 7) / 8, 256, 0, s>>>(M, F, pj, pp, feats, dens, wemb, v_feats, v_dens, v_wemb, A1);
+  return check_cuda(cudaGetLastError(), "ptf_gru_inputs_kernel");
+}
+int launch_ptf_gru_update(int M, int F, const float* A1, const float* r_lin, float* U, cudaStream_t s) {
+  if (M <= 0) return FS_OK;
+  const size_t total = (size_t)M * (2 * F + 24);
+  ptf_gru_update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(M, F, A1, r_lin, U);
+  return check_cuda(cudaGetLastError(), "ptf_gru_update_kernel");
+}
+int launch_ptf_gru_output(int M, int F, const float* A1, const float* z_lin, const float* q_lin, float* out, cudaStream_t s) {
+  if (M <= 0) return FS_OK;
+  const size_t total = (size_t)M * F;
+  ptf_gru_output_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(M, F, A1, z_lin, q_lin, out);
+  return check_cuda(cudaGetLastError(), "ptf_gru_output_kernel");
+}
+
 static inline int ptf_blocks(int n_upper, int HW) {
   const int m = n_upper > HW ? n_upper : HW;
   return (m + kPtfItems - 1) / kPtfItems;

@@ -55,6 +55,34 @@ class _State:
         self.feats, self.coords, self.dens, self.wemb, self.ext, self.depth = e(cap, F), e(cap, 3), e(cap), e(cap), e(cap, 16), e(cap)
 
 
+def _gru_has_reference_structure(gru) -> bool:
+    """networks.py:188-200: mlp_z / mlp_r / mlp_n = Sequential(Linear, ReLU, Linear)."""
+    try:
+        return all(isinstance(getattr(gru, n)[0], torch.nn.Linear) and isinstance(getattr(gru, n)[2], torch.nn.Linear)
+                   and len(getattr(gru, n)) == 3 for n in ("mlp_z", "mlp_r", "mlp_n"))
+    except Exception:
+        return False
+
+
+def _gru_fused(gru, M, F, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream):
+    """GRU.forward (networks.py:201-214) for the matched pairs, inference path: three glue kernels of ours around the
+    six nn.Linear GEMMs (cuBLAS), instead of ~30 element-wise torch launches."""
+    L = _lib.lib()
+    dev = state[0].device
+    A1 = torch.empty((M, 2 * F + 48), dtype=torch.float32, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    check(L.fs_ptf_gru_inputs(C.c_int32(M), C.c_int32(F), vp(pair_j), vp(pair_p), vp(state[0]), vp(state[2]), vp(state[3]),
+                              vp(view_feats), vp(view_dens), vp(view_wemb), vp(A1), C.c_void_p(stream)), "fs_ptf_gru_inputs")
+    r_lin = gru.mlp_r(A1).contiguous()
+    z_lin = gru.mlp_z(A1).contiguous()
+    U = torch.empty((M, 2 * F + 24), dtype=torch.float32, device=dev)
+    check(L.fs_ptf_gru_update(C.c_int32(M), C.c_int32(F), vp(A1), vp(r_lin), vp(U), C.c_void_p(stream)), "fs_ptf_gru_update")
+    q_lin = gru.mlp_n(U).contiguous()
+    out = torch.empty((M, F), dtype=torch.float32, device=dev)
+    check(L.fs_ptf_gru_output(C.c_int32(M), C.c_int32(F), vp(A1), vp(z_lin), vp(q_lin), vp(out), C.c_void_p(stream)), "fs_ptf_gru_output")
+    return out
+
+
 def _ptf_args(h, w, F, n_upper, depth_thres, state, cin, view, scratch, counts_out, out=None, gru_out=None):
     feats, coords, dens, wemb, ext, depth = state
     v_feats, v_coords, v_dens, v_wemb, v_depth, v_ext, E_inv, K_px = view
@@ -159,6 +187,8 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
     stream = torch.cuda.current_stream(dev).cuda_stream
     need_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in (feats, coords, dens, wemb, depths))
                                              or any(p.requires_grad for p in gru.parameters()))
+    fused_gru = (not need_grad) and (not torch.is_grad_enabled() or not any(p.requires_grad for p in gru.parameters())) \
+        and _gru_has_reference_structure(gru) and F == gru.mlp_z[2].out_features
     K_px = intrinsics.detach().clone()
     K_px[:, :1, :] *= w                       # encoder_freesplat.py:445-447
     K_px[:, 1:2, :] *= h
@@ -202,7 +232,9 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
                 ev[1].record()
             M, N_out = c[2], c[4]
             gru_out = None
-            if M > 0:
+            if M > 0 and fused_gru:
+                gru_out = _gru_fused(gru, M, F, pair_j, pair_p, det, feats[i], dens[i], wemb[i], stream)
+            elif M > 0:
                 pj, pp = pair_j[:M].long(), pair_p[:M].long()
                 hidden = state[0][pj]                      # global latent   (networks.py:201 `hidden_feat`)
                 inp = feats[i][pp]                         # view-i latent   (`input_feat`)

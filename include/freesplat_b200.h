@@ -217,6 +217,13 @@ typedef struct FsPtfArgs {
 
 int fs_ptf_match(const FsPtfArgs* args, void* stream);
 int fs_ptf_merge(const FsPtfArgs* args, void* stream);
+/* Element-wise glue of the GRU (networks.py:201-214) for the M matched pairs; the Linear layers in between are
+ * plain GEMMs run by the caller (cuBLAS).  A1 [M,2F+48] = [hidden | PE(v_dens,wemb) | input | PE(dens,v_wemb)],
+ * U [M,2F+24] = [sigmoid(r_lin)*hidden | input | PE(dens,v_wemb)], out [M,F] = (1-z)*hidden + z*tanh(q_lin).          */
+int fs_ptf_gru_inputs(int32_t M, int32_t F, const int32_t* pair_j, const int32_t* pair_p, const float* feats, const float* dens,
+                      const float* wemb, const float* v_feats, const float* v_dens, const float* v_wemb, float* A1, void* stream);
+int fs_ptf_gru_update(int32_t M, int32_t F, const float* A1, const float* r_lin, float* U, void* stream);
+int fs_ptf_gru_output(int32_t M, int32_t F, const float* A1, const float* z_lin, const float* q_lin, float* out, void* stream);
 
 int fs_abi_version(void);
 const char* fs_last_error(void);      /* thread-local, valid until the next call  */

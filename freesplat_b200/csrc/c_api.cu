@@ -151,4 +151,12 @@ int fs_ptf_gru_output(int32_t M, int32_t F, const float* A1, const float* z_lin,
   return launch_ptf_gru_output(M, F, A1, z_lin, q_lin, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int fs_ptf_gru(const FsPtfGruArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr && a->M >= 0, "bad arguments");
+  FS_REQUIRE(a->M == 0 || (a->pair_j && a->pair_p && a->feats && a->dens && a->wemb && a->v_feats && a->v_dens && a->v_wemb && a->W_r0 &&
+                           a->W_z0 && a->W_r2 && a->W_z2 && a->W_n0 && a->W_n2 && a->biases && a->wscratch && a->out), "NULL buffer");
+  return launch_ptf_gru_tc(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+int64_t fs_ptf_gru_wscratch_bytes(void) { return (int64_t)ptf_gru_wscratch_bytes(); }
+
 }  // extern "C"

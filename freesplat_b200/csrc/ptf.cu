@@ -394,4 +394,364 @@ int launch_ptf_merge(const FsPtfArgs& a, cudaStream_t s) {
   return check_cuda(cudaGetLastError(), "ptf_compact_kernel");
 }
 
+// ============================================================================================================
+// GRU of the matched pairs on the tensor cores (networks.py:188-214): out = (1-z) h + z tanh(n), with
+//   [r,z] = sigmoid(MLP_{r,z}([h | e_h | x | e_in])),  n = MLP_n([r*h | x | e_in]),  MLP = Linear-ReLU-Linear.
+// cuBLAS fp32 ran these skinny GEMMs (N = 64) at ~15 TFLOP/s and needed ~10 element-wise launches around them
+// (1.5 ms per fused view at 0.26 M pairs, profiles/r1_bench_ops.json).  Here one CTA owns 128 pairs:
+//   * thread = pair = TMEM lane; K is streamed in 16-column rounds, double-buffered in shared memory: the A operand
+//     round is built by the threads themselves (gather of the latents, positional encodings, ReLU / gate outputs of the
+//     previous layer read back from TMEM), the B operand round is a straight 16-byte copy of weights pre-split into
+//     tf32 hi/lo and pre-arranged in the canonical K-major core-matrix layout by ptf_gru_prep_kernel;
+//   * 3xTF32 (Ahi*Bhi + Ahi*Blo + Alo*Bhi), fp32 accumulation in TMEM: fp32-accurate (tests: <= 1e-4 vs the reference);
+//   * layer 1 computes r and z hidden layers together (N = 128); TMEM columns: D1 [0,128) -> reused by D3 [0,64), D4 [64,128);
+//     D2r [128,192), D2z [192,256).
+namespace gru {
+
+constexpr int kF = 64, kE = 24, kK1 = 2 * kF + 2 * kE /*176*/, kK3 = 2 * kF + kE /*152*/, kK3p = 160;
+constexpr int kRound = 16;                                   // K columns per round = 2 UMMA k-steps
+constexpr int kR1 = kK1 / kRound /*11*/, kR2 = kF / kRound /*4*/, kR3 = kK3p / kRound /*10*/, kR4 = kF / kRound /*4*/;
+constexpr int kATile = 2 * (128 / 8) * 256;                  // one A round (128 rows x 16 cols): 8 KB per hi / lo
+__host__ __device__ constexpr int bTile(int n) { return 2 * (n / 8) * 256; }     // one B round (n rows x 16 cols)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+__device__ __forceinline__ void mma_tf32(uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(da),
+               "l"(db), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(bar),
+               "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+// byte offset of (row, k) inside one operand round (k in 0..15)
+__host__ __device__ inline uint32_t op_off(int row, int k, int rows) {
+  return (uint32_t)((k >> 3) * ((rows / 8) * 256) + (row >> 3) * 256 + ((k >> 2) & 1) * 128 + (row & 7) * 16 + (k & 3) * 4);
+}
+
+// ---- weight preparation: every B round as [hi tile | lo tile] in the canonical layout, rounds concatenated ----
+// order: L1 (N=128: rows 0..63 = mlp_r[0], 64..127 = mlp_z[0]; 11 rounds) | L2r (N=64, 4) | L2z (4) | L3 (N=64, 10, K padded) | L4 (4)
+constexpr size_t kOffL1 = 0, kOffL2r = kOffL1 + (size_t)kR1 * 2 * bTile(128), kOffL2z = kOffL2r + (size_t)kR2 * 2 * bTile(64),
+                 kOffL3 = kOffL2z + (size_t)kR2 * 2 * bTile(64), kOffL4 = kOffL3 + (size_t)kR3 * 2 * bTile(64),
+                 kWBytes = kOffL4 + (size_t)kR4 * 2 * bTile(64);
+
+__global__ void ptf_gru_prep_kernel(const float* Wr0, const float* Wz0, const float* Wr2, const float* Wz2, const float* Wn0, const float* Wn2,
+                                    unsigned char* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  auto put = [&](size_t base, int rows, int round, int row, int kk, float v) {
+    const uint32_t hi = to_tf32(v), lo = to_tf32(v - __uint_as_float(hi));
+    unsigned char* tile = out + base + (size_t)round * 2 * bTile(rows);
+    *reinterpret_cast<uint32_t*>(tile + op_off(row, kk, rows)) = hi;
+    *reinterpret_cast<uint32_t*>(tile + bTile(rows) + op_off(row, kk, rows)) = lo;
+  };
+  if (t < 128 * kK1) { const int n = t / kK1, k = t - n * kK1; put(kOffL1, 128, k / kRound, n, k % kRound, n < 64 ? Wr0[n * kK1 + k] : Wz0[(n - 64) * kK1 + k]); }
+  if (t < 64 * kF) { const int n = t / kF, k = t - n * kF; put(kOffL2r, 64, k / kRound, n, k % kRound, Wr2[t]); put(kOffL2z, 64, k / kRound, n, k % kRound, Wz2[t]);
+                     put(kOffL4, 64, k / kRound, n, k % kRound, Wn2[t]); }
+  if (t < 64 * kK3p) { const int n = t / kK3p, k = t - n * kK3p; put(kOffL3, 64, k / kRound, n, k % kRound, k < kK3 ? Wn0[n * kK3 + k] : 0.f); }
+}
+
+struct __align__(128) Smem {
+  unsigned char A[2][2][kATile];        // [buffer][hi|lo]   (a second A tile for layer 2's z half lives in Az)
+  unsigned char Az[2][2][kATile];
+  unsigned char B[2][2 * bTile(128)];   // [buffer][hi tile | lo tile]  (layer 2: r round then z round, 64 rows each)
+  float b_r0[kF], b_z0[kF], b_r2[kF], b_z2[kF], b_n0[kF], b_n2[kF];
+  unsigned long long bar_free[2], bar_done;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void store_a4(unsigned char* hi, unsigned char* lo, int row, int k0, float v0, float v1, float v2, float v3) {
+  uint4 h, l;
+  h.x = to_tf32(v0); h.y = to_tf32(v1); h.z = to_tf32(v2); h.w = to_tf32(v3);
+  l.x = to_tf32(v0 - __uint_as_float(h.x)); l.y = to_tf32(v1 - __uint_as_float(h.y));
+  l.z = to_tf32(v2 - __uint_as_float(h.z)); l.w = to_tf32(v3 - __uint_as_float(h.w));
+  const uint32_t off = op_off(row, k0, 128);
+  *reinterpret_cast<uint4*>(hi + off) = h; *reinterpret_cast<uint4*>(lo + off) = l;
+}
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __restrict__ pair_j, const int* __restrict__ pair_p,
+                                                         const float* __restrict__ feats, const float* __restrict__ dens,
+                                                         const float* __restrict__ wemb, const float* __restrict__ v_feats,
+                                                         const float* __restrict__ v_dens, const float* __restrict__ v_wemb,
+                                                         const unsigned char* __restrict__ W, const float* __restrict__ biases /*6 x 64*/,
+                                                         float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char gru_smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(gru_smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m = blockIdx.x * 128 + tid;
+  const bool active = m < M;
+  if (tid < kF) { sm.b_r0[tid] = biases[tid]; sm.b_z0[tid] = biases[64 + tid]; sm.b_r2[tid] = biases[128 + tid]; sm.b_z2[tid] = biases[192 + tid];
+                  sm.b_n0[tid] = biases[256 + tid]; sm.b_n2[tid] = biases[320 + tid]; }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_free[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_free[1])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_done)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t bar_free[2] = {smem_u32(&sm.bar_free[0]), smem_u32(&sm.bar_free[1])};
+  const uint32_t bar_done = smem_u32(&sm.bar_done);
+  uint32_t ph_free[2] = {0u, 0u}, ph_done = 0u;
+  int uses[2] = {0, 0};                                    // rounds issued on each buffer so far
+
+  const int j = active ? pair_j[m] : 0, p = active ? pair_p[m] : 0;
+  float h[kF];
+  {
+    const float4* hp = reinterpret_cast<const float4*>(feats + (size_t)j * kF);
+#pragma unroll
+    for (int q = 0; q < kF / 4; q++) { const float4 v = __ldg(hp + q); h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w; }
+  }
+  const float4* xp = reinterpret_cast<const float4*>(v_feats + (size_t)p * kF);
+  const float pe_src[4] = {v_dens[p], wemb[j], dens[j], v_wemb[p]};     // e_h = PE(v_dens, wemb) ; e_in = PE(dens, v_wemb)
+
+  // generic "run one round": wait until buffer free, let `fill` write the A tile(s), copy the B round, issue the MMAs
+  auto begin_round = [&](int buf) {
+    if (uses[buf] > 0) { mbar_wait(bar_free[buf], ph_free[buf]); ph_free[buf] ^= 1u; }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  };
+  auto copy_b = [&](int buf, const unsigned char* src, int bytes) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(sm.B[buf]);
+    for (int k = tid; k < bytes / 16; k += 128) d4[k] = __ldg(s4 + k);
+  };
+  auto publish = [&]() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  };
+  // element c of the 24-wide positional encoding of (a, b)
+  auto pe24 = [&](float a, float b, int c) -> float {
+    const float x = (c < 12 ? a : b) * (float)(1 << (((c < 12 ? c : c - 12)) >> 1));
+    return (c & 1) ? cosf(x) : sinf(x);
+  };
+  // column c of concat_input (176) / of update_feat's tail; r_gate only used for layer 3
+  auto a1_col = [&](int c) -> float {
+    if (c < kF) return h[c];
+    if (c < kF + kE) return pe24(pe_src[0], pe_src[1], c - kF);
+    if (c < 2 * kF + kE) return __ldg(reinterpret_cast<const float*>(xp) + (c - kF - kE));
+    return pe24(pe_src[2], pe_src[3], c - 2 * kF - kE);
+  };
+
+  int round_no = 0;
+  // (all round loops are fully unrolled: column indices, buffer numbers and mbarrier phases are compile-time constants,
+  //  so h[] stays in registers)
+  // ------------------------------------------------ layer 1: [128 x 176] x [176 x 128]
+#pragma unroll
+  for (int r = 0; r < kR1; r++, round_no++) {
+    const int buf = round_no & 1;
+    begin_round(buf);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int c = r * kRound + 4 * q;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) v[e] = a1_col(c + e);
+      store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, v[0], v[1], v[2], v[3]);
+    }
+    copy_b(buf, W + kOffL1 + (size_t)r * 2 * bTile(128), 2 * bTile(128));
+    publish();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t aH = smem_u32(sm.A[buf][0]), aL = smem_u32(sm.A[buf][1]), bH = smem_u32(sm.B[buf]), bL = bH + bTile(128);
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const uint32_t ao = s * (128 / 8) * 256, bo = s * (128 / 8) * 256;
+        mma_tf32(tmem, make_desc(aL + ao), make_desc(bH + bo), idesc(128), (r > 0 || s > 0) ? 1u : 0u);
+        mma_tf32(tmem, make_desc(aH + ao), make_desc(bL + bo), idesc(128), 1u);
+        mma_tf32(tmem, make_desc(aH + ao), make_desc(bH + bo), idesc(128), 1u);
+      }
+      commit(bar_free[buf]);
+      if (r == kR1 - 1) commit(bar_done);
+    }
+    uses[buf]++;
+  }
+  mbar_wait(bar_done, ph_done); ph_done ^= 1u;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // ------------------------------------------------ layer 2: relu(D1 + b) -> r_lin (D2r), z_lin (D2z)
+#pragma unroll
+  for (int r = 0; r < kR2; r++, round_no++) {
+    const int buf = round_no & 1;
+    begin_round(buf);
+    float hr[16], hz[16];
+    tmem_ld16(t_row + (uint32_t)(r * kRound), hr);
+    tmem_ld16(t_row + (uint32_t)(64 + r * kRound), hz);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        a[e] = fmaxf(hr[4 * q + e] + sm.b_r0[r * kRound + 4 * q + e], 0.f);
+        b[e] = fmaxf(hz[4 * q + e] + sm.b_z0[r * kRound + 4 * q + e], 0.f);
+      }
+      store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, a[0], a[1], a[2], a[3]);
+      store_a4(sm.Az[buf][0], sm.Az[buf][1], tid, 4 * q, b[0], b[1], b[2], b[3]);
+    }
+    {   // B: r round (hi|lo, 64 rows) then z round
+      const uint4* s1 = reinterpret_cast<const uint4*>(W + kOffL2r + (size_t)r * 2 * bTile(64));
+      const uint4* s2 = reinterpret_cast<const uint4*>(W + kOffL2z + (size_t)r * 2 * bTile(64));
+      uint4* d4 = reinterpret_cast<uint4*>(sm.B[buf]);
+      const int n16 = 2 * bTile(64) / 16;
+      for (int k = tid; k < n16; k += 128) { d4[k] = __ldg(s1 + k); d4[n16 + k] = __ldg(s2 + k); }
+    }
+    publish();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t bR = smem_u32(sm.B[buf]), bZ = bR + 2 * bTile(64);
+      const uint32_t arH = smem_u32(sm.A[buf][0]), arL = smem_u32(sm.A[buf][1]), azH = smem_u32(sm.Az[buf][0]), azL = smem_u32(sm.Az[buf][1]);
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const uint32_t ao = s * (128 / 8) * 256, bo = s * (64 / 8) * 256;
+        const uint32_t acc = (r > 0 || s > 0) ? 1u : 0u;
+        mma_tf32(tmem + 128u, make_desc(arL + ao), make_desc(bR + bo), idesc(64), acc);
+        mma_tf32(tmem + 128u, make_desc(arH + ao), make_desc(bR + bTile(64) + bo), idesc(64), 1u);
+        mma_tf32(tmem + 128u, make_desc(arH + ao), make_desc(bR + bo), idesc(64), 1u);
+        mma_tf32(tmem + 192u, make_desc(azL + ao), make_desc(bZ + bo), idesc(64), acc);
+        mma_tf32(tmem + 192u, make_desc(azH + ao), make_desc(bZ + bTile(64) + bo), idesc(64), 1u);
+        mma_tf32(tmem + 192u, make_desc(azH + ao), make_desc(bZ + bo), idesc(64), 1u);
+      }
+      commit(bar_free[buf]);
+      if (r == kR2 - 1) commit(bar_done);
+    }
+    uses[buf]++;
+  }
+  mbar_wait(bar_done, ph_done); ph_done ^= 1u;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // ------------------------------------------------ layer 3: U = [sigmoid(r_lin + b) * h | x | e_in | 0] (160) x [160 x 64] -> D3 [0,64)
+#pragma unroll
+  for (int r = 0; r < kR3; r++, round_no++) {
+    const int buf = round_no & 1;
+    begin_round(buf);
+    float rg[16];
+    if (r < kR2) tmem_ld16(t_row + (uint32_t)(128 + r * kRound), rg);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int c = r * kRound + 4 * q + e;           // column of update_feat
+        if (r < kR2) v[e] = sigm(rg[4 * q + e] + sm.b_r2[c]) * h[c];
+        else if (c < 2 * kF) v[e] = __ldg(reinterpret_cast<const float*>(xp) + (c - kF));
+        else if (c < kK3) v[e] = pe24(pe_src[2], pe_src[3], c - 2 * kF);
+        else v[e] = 0.f;
+      }
+      store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, v[0], v[1], v[2], v[3]);
+    }
+    copy_b(buf, W + kOffL3 + (size_t)r * 2 * bTile(64), 2 * bTile(64));
+    publish();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t aH = smem_u32(sm.A[buf][0]), aL = smem_u32(sm.A[buf][1]), bH = smem_u32(sm.B[buf]), bL = bH + bTile(64);
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const uint32_t ao = s * (128 / 8) * 256, bo = s * (64 / 8) * 256;
+        mma_tf32(tmem, make_desc(aL + ao), make_desc(bH + bo), idesc(64), (r > 0 || s > 0) ? 1u : 0u);
+        mma_tf32(tmem, make_desc(aH + ao), make_desc(bL + bo), idesc(64), 1u);
+        mma_tf32(tmem, make_desc(aH + ao), make_desc(bH + bo), idesc(64), 1u);
+      }
+      commit(bar_free[buf]);
+      if (r == kR3 - 1) commit(bar_done);
+    }
+    uses[buf]++;
+  }
+  mbar_wait(bar_done, ph_done); ph_done ^= 1u;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // ------------------------------------------------ layer 4: relu(D3 + b) x [64 x 64] -> D4 [64,128)
+#pragma unroll
+  for (int r = 0; r < kR4; r++, round_no++) {
+    const int buf = round_no & 1;
+    begin_round(buf);
+    float hn[16];
+    tmem_ld16(t_row + (uint32_t)(r * kRound), hn);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, fmaxf(hn[4 * q] + sm.b_n0[r * kRound + 4 * q], 0.f),
+               fmaxf(hn[4 * q + 1] + sm.b_n0[r * kRound + 4 * q + 1], 0.f), fmaxf(hn[4 * q + 2] + sm.b_n0[r * kRound + 4 * q + 2], 0.f),
+               fmaxf(hn[4 * q + 3] + sm.b_n0[r * kRound + 4 * q + 3], 0.f));
+    copy_b(buf, W + kOffL4 + (size_t)r * 2 * bTile(64), 2 * bTile(64));
+    publish();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t aH = smem_u32(sm.A[buf][0]), aL = smem_u32(sm.A[buf][1]), bH = smem_u32(sm.B[buf]), bL = bH + bTile(64);
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const uint32_t ao = s * (128 / 8) * 256, bo = s * (64 / 8) * 256;
+        mma_tf32(tmem + 64u, make_desc(aL + ao), make_desc(bH + bo), idesc(64), (r > 0 || s > 0) ? 1u : 0u);
+        mma_tf32(tmem + 64u, make_desc(aH + ao), make_desc(bL + bo), idesc(64), 1u);
+        mma_tf32(tmem + 64u, make_desc(aH + ao), make_desc(bH + bo), idesc(64), 1u);
+      }
+      commit(bar_free[buf]);
+      if (r == kR4 - 1) commit(bar_done);
+    }
+    uses[buf]++;
+  }
+  mbar_wait(bar_done, ph_done); ph_done ^= 1u;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // ------------------------------------------------ gates
+#pragma unroll
+  for (int r = 0; r < kR2; r++) {
+    float zl[16], ql[16];
+    tmem_ld16(t_row + (uint32_t)(192 + r * kRound), zl);
+    tmem_ld16(t_row + (uint32_t)(64 + r * kRound), ql);
+    if (active) {
+      float4* op = reinterpret_cast<float4*>(out + (size_t)m * kF + r * kRound);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int c = r * kRound + 4 * q + e;
+          const float z = sigm(zl[4 * q + e] + sm.b_z2[c]);
+          o[e] = (1.0f - z) * h[c] + z * tanhf(ql[4 * q + e] + sm.b_n2[c]);
+        }
+        op[q] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+}  // namespace gru
+
+int launch_ptf_gru_tc(const FsPtfGruArgs& a, cudaStream_t s) {
+  if (a.M <= 0) return FS_OK;
+  int rc;
+  gru::ptf_gru_prep_kernel<<<(128 * gru::kK1 + 255) / 256, 256, 0, s>>>(a.W_r0, a.W_z0, a.W_r2, a.W_z2, a.W_n0, a.W_n2, a.wscratch);
+  if ((rc = check_cuda(cudaGetLastError(), "ptf_gru_prep_kernel"))) return rc;
+  const size_t smem = sizeof(gru::Smem) + 128;
+  if ((rc = check_cuda(cudaFuncSetAttribute(gru::ptf_gru_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute(ptf_gru_tc_kernel)"))) return rc;
+  gru::ptf_gru_tc_kernel<<<(a.M + 127) / 128, 128, smem, s>>>(a.M, a.pair_j, a.pair_p, a.feats, a.dens, a.wemb, a.v_feats, a.v_dens, a.v_wemb,
+                                                            a.wscratch, a.biases, a.out);
+  return check_cuda(cudaGetLastError(), "ptf_gru_tc_kernel");
+}
+
+size_t ptf_gru_wscratch_bytes() { return gru::kWBytes; }
+
 }  // namespace fs

@@ -18,6 +18,7 @@ of the step counters per view sizes the GRU batch.  CPU tensors raise: there is 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -62,6 +63,47 @@ def _gru_has_reference_structure(gru) -> bool:
                    and len(getattr(gru, n)) == 3 for n in ("mlp_z", "mlp_r", "mlp_n"))
     except Exception:
         return False
+
+
+class FsPtfGruArgs(C.Structure):
+    _fields_ = [("M", C.c_int32), ("pair_j", C.c_void_p), ("pair_p", C.c_void_p),
+                ("feats", C.c_void_p), ("dens", C.c_void_p), ("wemb", C.c_void_p),
+                ("v_feats", C.c_void_p), ("v_dens", C.c_void_p), ("v_wemb", C.c_void_p),
+                ("W_r0", C.c_void_p), ("W_z0", C.c_void_p), ("W_r2", C.c_void_p), ("W_z2", C.c_void_p), ("W_n0", C.c_void_p),
+                ("W_n2", C.c_void_p), ("biases", C.c_void_p), ("wscratch", C.c_void_p), ("out", C.c_void_p)]
+
+
+# "tc": the whole GRU on the tensor cores (fs_ptf_gru, 3xTF32) ; "cublas": glue kernels + nn.Linear GEMMs
+GRU_MODE = os.environ.get("FREESPLAT_B200_PTF_GRU", "tc")
+
+
+def _gru_tc_ok(gru, F) -> bool:
+    try:
+        return (F == 64 and tuple(gru.mlp_r[0].weight.shape) == (64, 176) and tuple(gru.mlp_z[0].weight.shape) == (64, 176)
+                and tuple(gru.mlp_n[0].weight.shape) == (64, 152) and all(tuple(getattr(gru, n)[2].weight.shape) == (64, 64)
+                                                                         for n in ("mlp_r", "mlp_z", "mlp_n")))
+    except Exception:
+        return False
+
+
+def _gru_fused_tc(gru, M, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream):
+    """GRU.forward (networks.py:201-214) for the matched pairs in ONE kernel on the tensor cores (fs_ptf_gru)."""
+    L = _lib.lib()
+    dev = state[0].device
+    w = lambda t: t.detach().float().contiguous()
+    Ws = [w(gru.mlp_r[0].weight), w(gru.mlp_z[0].weight), w(gru.mlp_r[2].weight), w(gru.mlp_z[2].weight),
+          w(gru.mlp_n[0].weight), w(gru.mlp_n[2].weight)]
+    biases = torch.cat([w(gru.mlp_r[0].bias), w(gru.mlp_z[0].bias), w(gru.mlp_r[2].bias), w(gru.mlp_z[2].bias),
+                        w(gru.mlp_n[0].bias), w(gru.mlp_n[2].bias)]).contiguous()
+    L.fs_ptf_gru_wscratch_bytes.restype = C.c_int64
+    scratch = torch.empty(int(L.fs_ptf_gru_wscratch_bytes()), dtype=torch.uint8, device=dev)
+    out = torch.empty((M, 64), dtype=torch.float32, device=dev)
+    a = FsPtfGruArgs(M=M, pair_j=ptr(pair_j), pair_p=ptr(pair_p), feats=ptr(state[0]), dens=ptr(state[2]), wemb=ptr(state[3]),
+                     v_feats=ptr(view_feats), v_dens=ptr(view_dens), v_wemb=ptr(view_wemb),
+                     W_r0=ptr(Ws[0]), W_z0=ptr(Ws[1]), W_r2=ptr(Ws[2]), W_z2=ptr(Ws[3]), W_n0=ptr(Ws[4]), W_n2=ptr(Ws[5]),
+                     biases=ptr(biases), wscratch=ptr(scratch), out=ptr(out))
+    check(L.fs_ptf_gru(C.byref(a), C.c_void_p(stream)), "fs_ptf_gru")
+    return out
 
 
 def _gru_fused(gru, M, F, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream):
@@ -232,7 +274,9 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
                 ev[1].record()
             M, N_out = c[2], c[4]
             gru_out = None
-            if M > 0 and fused_gru:
+            if M > 0 and fused_gru and GRU_MODE == "tc" and _gru_tc_ok(gru, F):
+                gru_out = _gru_fused_tc(gru, M, pair_j, pair_p, det, feats[i], dens[i], wemb[i], stream)
+            elif M > 0 and fused_gru:
                 gru_out = _gru_fused(gru, M, F, pair_j, pair_p, det, feats[i], dens[i], wemb[i], stream)
             elif M > 0:
                 pj, pp = pair_j[:M].long(), pair_p[:M].long()

@@ -225,6 +225,24 @@ int fs_ptf_gru_inputs(int32_t M, int32_t F, const int32_t* pair_j, const int32_t
 int fs_ptf_gru_update(int32_t M, int32_t F, const float* A1, const float* r_lin, float* U, void* stream);
 int fs_ptf_gru_output(int32_t M, int32_t F, const float* A1, const float* z_lin, const float* q_lin, float* out, void* stream);
 
+/* The whole GRU (networks.py:188-214, latent width 64, 24-wide weight embeddings) for the M matched pairs on the
+ * tensor cores (tcgen05, 3xTF32): gathers, positional encodings, the six Linear layers and the gates in one kernel.
+ * W_* are the nn.Linear weights ([out,in] row-major): mlp_r[0] [64,176], mlp_z[0] [64,176], mlp_r[2] / mlp_z[2] [64,64],
+ * mlp_n[0] [64,152], mlp_n[2] [64,64]; biases = [b_r0 | b_z0 | b_r2 | b_z2 | b_n0 | b_n2] (6 x 64);
+ * wscratch: fs_ptf_gru_wscratch_bytes() bytes of device scratch (tf32-split, pre-tiled weights).                */
+typedef struct FsPtfGruArgs {
+  int32_t M;
+  const int32_t* pair_j; const int32_t* pair_p;
+  const float* feats; const float* dens; const float* wemb;          /* global state  */
+  const float* v_feats; const float* v_dens; const float* v_wemb;    /* view i        */
+  const float* W_r0; const float* W_z0; const float* W_r2; const float* W_z2; const float* W_n0; const float* W_n2;
+  const float* biases;
+  unsigned char* wscratch;
+  float* out;                                                         /* [M,64]        */
+} FsPtfGruArgs;
+int fs_ptf_gru(const FsPtfGruArgs* args, void* stream);
+int64_t fs_ptf_gru_wscratch_bytes(void);
+
 int fs_abi_version(void);
 const char* fs_last_error(void);      /* thread-local, valid until the next call  */
 int fs_device_sm_count(void);         /* negative FsStatus on failure             */

@@ -135,3 +135,25 @@ def test_backward_vs_reference_golden(path):
         scale = np.abs(want).max() + 1e-12
         err = np.abs(got.cpu().numpy() - want).max() / scale
         assert err < 2e-4, (name, err)
+
+
+def test_gru_paths_agree():
+    """The three GRU evaluations -- tensor-core kernel (fs_ptf_gru), glue kernels + cuBLAS, plain module call -- on the
+    same matched pairs."""
+    from freesplat_b200 import ptf
+    inp = synth.ptf_inputs(7, 3, 64, 96)
+    feats, coords, dens, wemb, depths, ext, K, hw = flat_inputs(inp)
+    outs = {}
+    old = ptf.GRU_MODE
+    try:
+        for mode in ("tc", "cublas"):
+            ptf.GRU_MODE = mode
+            outs[mode] = _run(feats, coords, dens, wemb, depths, ext, K, hw, 7)[0].cpu().numpy()
+    finally:
+        ptf.GRU_MODE = old
+    from oracle import ptf as optf
+    want = optf.fuse(feats, coords, dens, wemb, depths, ext, K, hw, optf.torch_gru_fn(synth.gru_state(7)),
+                     E_invs=torch_inverses(ext))[0]
+    assert outs["tc"].shape == want.shape
+    np.testing.assert_allclose(outs["cublas"], want, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(outs["tc"], want, rtol=1e-4, atol=2e-5)

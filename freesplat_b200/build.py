@@ -24,6 +24,7 @@ SOURCES = [
     ("raster_render.cu", []),
     ("cost_volume.cu", []),
     ("ptf.cu", ["-fmad=false"]),
+    ("adapter.cu", []),
     ("c_api.cu", []),
 ]
 

@@ -151,6 +151,13 @@ int fs_ptf_gru_output(int32_t M, int32_t F, const float* A1, const float* z_lin,
   return launch_ptf_gru_output(M, F, A1, z_lin, q_lin, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int fs_gaussian_head(const FsAdapterArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr && a->N >= 0 && a->H >= 1 && a->W >= 1 && a->sh_degree >= 0 && a->sh_degree <= 3, "bad arguments");
+  FS_REQUIRE(a->N == 0 || (a->raw && a->depths && a->opacities && a->coords && a->ext && a->K && a->means && a->covariances &&
+                           a->harmonics && a->opacities_out && a->scales && a->rotations), "NULL buffer");
+  return launch_gaussian_head(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int fs_ptf_gru(const FsPtfGruArgs* a, void* stream) {
   FS_REQUIRE(a != nullptr && a->M >= 0, "bad arguments");
   FS_REQUIRE(a->M == 0 || (a->pair_j && a->pair_p && a->feats && a->dens && a->wemb && a->v_feats && a->v_dens && a->v_wemb && a->W_r0 &&

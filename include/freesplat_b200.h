@@ -243,6 +243,26 @@ typedef struct FsPtfGruArgs {
 int fs_ptf_gru(const FsPtfGruArgs* args, void* stream);
 int64_t fs_ptf_gru_wscratch_bytes(void);
 
+/* ------------------------------------------------------------ Gaussian head */
+/* GaussianAdapter.forward(fusion=False, coords=...) (gaussian_adapter.py:136-200) as one kernel.               */
+typedef struct FsAdapterArgs {
+  int32_t N, H, W, sh_degree;
+  float scale_min, scale_max, eps;
+  const float* raw;        /* [N, 7+3*d_sh]: scales(3) | quaternion xyzw (4) | SH (3 x d_sh)          */
+  const float* depths;     /* [N]                                                                    */
+  const float* opacities;  /* [N]                                                                    */
+  const float* coords;     /* [N,3]                                                                  */
+  const float* ext;        /* [N,16] per-Gaussian camera-to-world                                    */
+  const float* K;          /* [9] normalised intrinsics                                              */
+  float* means;            /* [N,3]  */
+  float* covariances;      /* [N,3,3]*/
+  float* harmonics;        /* [N,3,d_sh] */
+  float* opacities_out;    /* [N]    */
+  float* scales;           /* [N,3]  */
+  float* rotations;        /* [N,4]  */
+} FsAdapterArgs;
+int fs_gaussian_head(const FsAdapterArgs* args, void* stream);
+
 int fs_abi_version(void);
 const char* fs_last_error(void);      /* thread-local, valid until the next call  */
 int fs_device_sm_count(void);         /* negative FsStatus on failure             */

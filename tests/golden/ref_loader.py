@@ -84,3 +84,37 @@ def load_fuse_gaussians():
     load_cost_volume_module()
     GRU = sys.modules["refmods.networks"].GRU
     return ns["fuse_gaussians"], ns["positional_encoding"], GRU
+
+
+def load_gaussian_adapter():
+    """Returns the reference's GaussianAdapter / GaussianAdapterCfg classes
+    (src/model/encoder/common/gaussian_adapter.py), with stubs for the two imports this path never calls
+    (get_world_rays, rotate_sh: only used when `coords is None`) and for cv2."""
+    import types as _t
+    root = "refpkg"
+    def mod(name, path=None, is_pkg=False):
+        m = _t.ModuleType(name)
+        if is_pkg:
+            m.__path__ = []
+        sys.modules[name] = m
+        return m
+    for pkg in (root, f"{root}.src", f"{root}.src.geometry", f"{root}.src.misc", f"{root}.src.model", f"{root}.src.model.encoder",
+                f"{root}.src.model.encoder.common"):
+        if pkg not in sys.modules:
+            mod(pkg, is_pkg=True)
+    proj = mod(f"{root}.src.geometry.projection"); proj.get_world_rays = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("unused"))
+    shr = mod(f"{root}.src.misc.sh_rotation"); shr.rotate_sh = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("unused"))
+    if "cv2" not in sys.modules:
+        try:
+            import cv2  # noqa: F401
+        except Exception:
+            sys.modules["cv2"] = _t.ModuleType("cv2")
+    base = os.path.join(REF, "src", "model", "encoder", "common")
+    for name in ("gaussians", "gaussian_adapter"):
+        full = f"{root}.src.model.encoder.common.{name}"
+        spec = importlib.util.spec_from_file_location(full, os.path.join(base, f"{name}.py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[full] = m
+        spec.loader.exec_module(m)
+    ga = sys.modules[f"{root}.src.model.encoder.common.gaussian_adapter"]
+    return ga.GaussianAdapter, ga.GaussianAdapterCfg

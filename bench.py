@@ -45,6 +45,23 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic(kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the committed ncu export (profiles/), bytes per launch."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_fwd_step_ncu_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if kernel_substr in r[ik]:
+                return float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]]
+    except Exception:
+        return None
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
 
@@ -224,21 +241,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    # (a) the timed region proper: one fs_raster_forward per step, events around the whole step
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
-        st = step(stage_events=ev[k])
+        st = step(stage_events=list(evs[k]))
     barrier()
     clocks = sampler.stop()
     assert not st.overflowed()
-    step_ms = [e[0].elapsed_time(e[3]) for e in ev]
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = sum(step_ms)
+    # (b) the same steps again with events BETWEEN the three stages of the ABI (roofline of the render kernel)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        st = step(stage_events=ev[k])
+    barrier()
     render_ms = [e[2].elapsed_time(e[3]) for e in ev]
     pre_ms = [e[0].elapsed_time(e[1]) for e in ev]
     bin_ms = [e[1].elapsed_time(e[2]) for e in ev]
-    total_ms = sum(step_ms)
 
     # ---- end to end from pinned host memory through the public API ------------------------------
     pin = lambda t: t.contiguous().pin_memory()
@@ -296,7 +320,8 @@ def main():
             "gpu_launches": 5 * args.steps,
             "stage_ms": {"preprocess": sum(pre_ms) / len(pre_ms), "binning": sum(bin_ms) / len(bin_ms), "render": rd},
             "roofline": {"kernel": "render_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": _ncu_traffic("render_fwd_kernel"),
+                         "traffic_source": "profiles/r1_fwd_step_ncu_raw.csv (ncu --set full, same workload)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "render is FP32/SFU-issue bound at this size (SURVEY §7), reported against HBM as BASELINE asks"},
             "clocks": clocks,

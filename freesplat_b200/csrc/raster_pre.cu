@@ -24,7 +24,7 @@ namespace fs {
 // DEG = active SH degree (compile time: the 3*(DEG+1)^2 coefficient loads become straight-line shared-memory
 // reads with immediate offsets; the generic loop cost ~300 instructions of predicates / address math per view).
 template <int DEG>
-__global__ void __launch_bounds__(kThreads, 3) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy, int sh_stride) {
+__global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy, int sh_stride) {
   extern __shared__ float4 smem4[];
   float4* s_out = smem4;                                   // [256*3]
   float* s_sh = reinterpret_cast<float*>(smem4 + kThreads * 3);

@@ -159,6 +159,11 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
                 ranges=ptr(st.ranges), keybuf=ptr(st.keybuf), point_list=ptr(st.point_list), status=ptr(st.status))
             if stage_events is None:
                 check(L.fs_raster_forward(C.byref(a), C.c_void_p(stream)), "fs_raster_forward")
+            elif len(stage_events) == 2:
+                # bracket exactly the one library call (workspace allocation above is host work, not part of the path)
+                stage_events[0].record()
+                check(L.fs_raster_forward(C.byref(a), C.c_void_p(stream)), "fs_raster_forward")
+                stage_events[1].record()
             else:
                 # stage_events: list of 4 torch.cuda.Event recorded around preprocess | binning | render
                 for k, bit in enumerate((1, 2, 4)):

@@ -167,3 +167,26 @@ def test_native_layout_gradients_match_upstream_layout():
         # radius or a pixel whose threshold flips changes a few entries; everything else agrees to atomics noise
         assert torch.quantile(err.flatten()[:4_000_000], 0.999) < 2e-4, name
     assert torch.equal(grads[0][2][:, 1, 0], torch.zeros_like(grads[0][2][:, 1, 0]))   # lower triangle: no gradient
+
+
+def test_host_pipeline_matches_direct_call():
+    """HostRenderPipeline (3 streams, double-buffered, deferred overflow check) returns what render_views returns."""
+    from freesplat_b200 import decoder
+    from freesplat_b200.pipeline import HostRenderPipeline
+    dev = "cuda:0"
+    scenes = [synth.pixel_aligned_scene(seed=s, h=96, w=128, n_context=2, n_target=2, keep=None) for s in (0, 1, 2, 3, 4)]
+    pipe = HostRenderPipeline(dev, (96, 128), 2, depth=2)
+    pin = lambda t: t.contiguous().pin_memory()
+    got = []
+    for sc in scenes:
+        host = dict(extrinsics=pin(sc.extrinsics), intrinsics=pin(sc.intrinsics), near=pin(sc.near), far=pin(sc.far),
+                    means=pin(sc.means), covariances=pin(sc.covariances), harmonics=pin(sc.harmonics), opacities=pin(sc.opacities))
+        slot = pipe.submit(host)
+        c, d = pipe.wait(slot)
+        got.append((c.clone(), d.clone()))
+    for sc, (c, d) in zip(scenes, got):
+        g = sc.to(dev)
+        with torch.no_grad():
+            c2, d2 = decoder.render_views(g.extrinsics, g.intrinsics, g.near, g.far, g.image_shape, torch.zeros((2, 3), device=dev),
+                                          g.means, g.covariances, g.harmonics, g.opacities)
+        assert torch.equal(c, c2.cpu()) and torch.equal(d, d2.cpu())

@@ -47,7 +47,7 @@ class FsRasterBwdArgs(C.Structure):
 
 # every symbol include/freesplat_b200.h declares (tests/test_abi.py checks the header against this)
 EXPORTS = [
-    "fs_abi_version", "fs_last_error", "fs_device_sm_count",
+    "fs_abi_version", "fs_struct_size", "fs_last_error", "fs_device_sm_count",
     "fs_raster_forward", "fs_raster_backward", "fs_mark_visible", "fs_camera_records",
     "fs_cost_volume_forward", "fs_cost_volume_backward",
     "fs_ptf_match", "fs_ptf_merge", "fs_ptf_gru_inputs", "fs_ptf_gru_update", "fs_ptf_gru_output",

@@ -28,6 +28,17 @@ using namespace fs;
 extern "C" {
 
 int fs_abi_version(void) { return FS_ABI_VERSION; }
+int fs_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return (int)sizeof(FsRasterFwdArgs);
+    case 1: return (int)sizeof(FsRasterBwdArgs);
+    case 2: return (int)sizeof(FsCostVolumeArgs);
+    case 3: return (int)sizeof(FsPtfArgs);
+    case 4: return (int)sizeof(FsPtfGruArgs);
+    case 5: return (int)sizeof(FsAdapterArgs);
+    default: return -1;
+  }
+}
 const char* fs_last_error(void) { return g_err; }
 
 int fs_device_sm_count(void) {

@@ -264,6 +264,9 @@ typedef struct FsAdapterArgs {
 int fs_gaussian_head(const FsAdapterArgs* args, void* stream);
 
 int fs_abi_version(void);
+/* sizeof() of the argument structs as compiled (0: FsRasterFwdArgs, 1: FsRasterBwdArgs, 2: FsCostVolumeArgs, 3: FsPtfArgs,
+ * 4: FsPtfGruArgs, 5: FsAdapterArgs; -1 otherwise) so that a foreign-language binding can verify its layout.      */
+int fs_struct_size(int32_t which);
 const char* fs_last_error(void);      /* thread-local, valid until the next call  */
 int fs_device_sm_count(void);         /* negative FsStatus on failure             */
 

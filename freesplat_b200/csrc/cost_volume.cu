@@ -781,6 +781,497 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
   }
 }
 
+
+// =========================================================================== tensor-core backward
+// The fp32 kernel above keeps 1 CTA x 4 warps per SM (121 KB of parked rows, 255 registers + spills) and spends
+// its time in dependent FMA chains (ncu r1: FMA pipe 10.7 %, 6 % warps active).  Here every contraction of the
+// backward pass is a tcgen05 MMA (3xTF32, fp32-accurate):
+//
+//   Z1  = X  . W0^T          (M128 N32 K56)  X = [x*rn (48) | dot*rn | 1 | 0..]  -> the bias b0 rides in column 49
+//   Z2  = A1 . W1^T          (M128 N32 K32)  A1 = leaky(Z1)
+//   dA1 = dZ2 . W1           (M128 N32 K32)  dZ2 = g * W2 * leaky'(Z2)
+//   dX  = dZ1 . W0           (M128 N64 K32)  dZ1 = dA1 * leaky'(Z1)
+//   U1 += [X | A1]^T . dZ2   (M128 N32, K = the 128 rows)   rows 64..95 = dW1^T, row 49 (the ones column) = db1
+//   U0 += [X | A1]^T . dZ1   (M128 N32, K = the 128 rows)   rows 0..48 = dW0^T, row 49 = db0
+//
+// Row-wise products take their A operand (row = TMEM lane = reference pixel) straight from tensor memory, where the
+// threads put it with tcgen05.st; weights are K-major SWIZZLE_NONE tiles in shared memory (both orientations).
+// The two products that reduce over the ROWS need MN-major operands: for tf32 the tensor core accepts those only in
+// the SWIZZLE_128B_BASE32B layout (measured with tools/probe/umma_layout_probe.cu: every other layout type reads as
+// zeros): element (row, col) at  (col/32)*LBO + (row/4)*SBO + (row%4)*128 + ((((col%32)/8) ^ (row%4))*32 + (col%8)*4,
+// here dense (SBO = 512, LBO = 16 KB): a thread writes its 128-byte row with the 32-byte units permuted by row%4.
+// U0/U1 stay in TMEM across all planes of the CTA and are flushed once.
+// 256 threads: thread t and t+128 share reference pixel t&127 and split the 48 channels (24 each) and every
+// 32-column TMEM read (16 each) -> 8 warps per SM and no spills, instead of 4 warps that spill.
+namespace tcb {
+
+using tc::commit;
+using tc::mbar_wait;
+using tc::smem_u32;
+using tc::to_tf32;
+
+constexpr int kThreads = 256;
+constexpr int kHalfC = kCvC / 2;                 // channels per thread
+constexpr uint32_t kGroup = 128 * 128;           // one MN-major group: 128 rows x 32 columns x 4 B
+// tensor-memory columns: accumulators ...
+constexpr uint32_t kColZ1 = 0, kColZ2 = 32, kColDA1 = 64, kColDX = 96, kColU0 = 160, kColU1 = 192;
+// ... and A operands (hi / lo halves of the 3xTF32 split)
+constexpr uint32_t kColXhi = 224, kColXlo = 280, kColHhi = 336, kColHlo = 368, kTmemCols = 512;
+constexpr int kMaxK = 16;
+
+struct __align__(1024) Smem {
+  // MN-major tiles.  The M = 128 operand window is 4 groups from Xg0: [X cols 0..31][X cols 32..63][A1][whatever follows];
+  // the 4th group only feeds accumulator rows 96..127, which nobody reads.
+  unsigned char X_hi[2 * kGroup], A1_hi[kGroup];
+  unsigned char X_lo[2 * kGroup], A1_lo[kGroup];
+  unsigned char dZ_hi[kGroup], dZ_lo[kGroup];
+  // K-major SWIZZLE_NONE weight tiles, [k-step][n/8][2 chunks][8 rows][16 B]
+  unsigned char W0f_hi[7 * 1024], W0f_lo[7 * 1024];     // n = out (32), k = in (56):  Z1 = X W0^T
+  unsigned char W1f_hi[4 * 1024], W1f_lo[4 * 1024];     // n = out, k = in:            Z2 = A1 W1^T
+  unsigned char W1t_hi[4 * 1024], W1t_lo[4 * 1024];     // n = in, k = out:            dA1 = dZ2 W1
+  unsigned char W0t_hi[4 * 2048], W0t_lo[4 * 2048];     // n = in (64), k = out (32):  dX = dZ1 W0
+  float dotp[2][kMaxK][128];                     // per-half partial dot products of one plane
+  float b1[kCvHid], W2[kCvHid];
+  float proj[kMaxK * 12];
+  unsigned long long bar_chain, bar_dw;
+  uint32_t tmem_base;
+};
+
+// K-major SWIZZLE_NONE descriptor of a weight tile k-step (LBO = 128: the two 16-byte k-chunks, SBO = 256: 8-row groups)
+__device__ __forceinline__ uint64_t desc_k(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+}
+// MN-major SWIZZLE_128B_BASE32B descriptor (layout type 1): LBO = 32-column groups, SBO = 4-row groups
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(kGroup >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
+// D = f32, A = B = tf32, M = 128
+__host__ __device__ constexpr uint32_t idesc(uint32_t n, uint32_t a_mn, uint32_t b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t id, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(id), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t id, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(id), "r"(accumulate) : "memory");
+}
+// 3xTF32 product of one k-step: lo*hi + hi*lo + hi*hi
+__device__ __forceinline__ void mma3_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t id, uint32_t accumulate) {
+  mma_ts(tmem_d, a_lo, desc_k(b_hi), id, accumulate);
+  mma_ts(tmem_d, a_hi, desc_k(b_lo), id, 1u);
+  mma_ts(tmem_d, a_hi, desc_k(b_hi), id, 1u);
+}
+__device__ __forceinline__ void mma3_mn(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t id, uint32_t accumulate) {
+  mma_ss(tmem_d, desc_mn(a_lo), desc_mn(b_hi), id, accumulate);
+  mma_ss(tmem_d, desc_mn(a_hi), desc_mn(b_lo), id, 1u);
+  mma_ss(tmem_d, desc_mn(a_hi), desc_mn(b_hi), id, 1u);
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld1_issue(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]) {     // N columns (multiple of 8) of this thread's lane
+  uint32_t r[N / 8][8];
+#pragma unroll
+  for (int q = 0; q < N / 8; q++) tmem_ld8_issue(taddr + (uint32_t)(8 * q), r[q]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int q = 0; q < N / 8; q++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[8 * q + e] = __uint_as_float(r[q][e]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&w)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+// Splits 8 consecutive columns (col0 multiple of 8) of this thread's row into tf32 hi / lo and puts them (a) into the
+// TMEM A-operand columns t_hi / t_lo (already offset to col0) and (b) into the MN-major tile pair at mn_hi / mn_lo.
+__device__ __forceinline__ void put8(const float (&v)[8], uint32_t t_hi, uint32_t t_lo, bool to_tmem, unsigned char* mn_hi,
+                                     unsigned char* mn_lo, int row, int col0) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) { h[e] = to_tf32(v[e]); l[e] = to_tf32(v[e] - __uint_as_float(h[e])); }
+  if (to_tmem) { tmem_st8(t_hi, h); tmem_st8(t_lo, l); }
+  const uint32_t off = (uint32_t)((col0 >> 5) * kGroup + row * 128 + ((((col0 & 31) >> 3) ^ (row & 3)) << 5));
+  *reinterpret_cast<uint4*>(mn_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(mn_hi + off + 16) = make_uint4(h[4], h[5], h[6], h[7]);
+  *reinterpret_cast<uint4*>(mn_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  *reinterpret_cast<uint4*>(mn_lo + off + 16) = make_uint4(l[4], l[5], l[6], l[7]);
+}
+__device__ __forceinline__ void sync_for_mma() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+}
+// byte offset of element (n, k) in a K-major SWIZZLE_NONE weight tile with N rows
+__device__ __forceinline__ uint32_t wk_off(int n, int k, int N) {
+  return (uint32_t)((k >> 3) * (N / 8 * 256) + (n >> 3) * 256 + ((k >> 2) & 1) * 128 + (n & 7) * 16 + (k & 3) * 4);
+}
+__device__ __forceinline__ void put_w(unsigned char* hi, unsigned char* lo, uint32_t off, float v) {
+  const uint32_t h = to_tf32(v);
+  *reinterpret_cast<uint32_t*>(hi + off) = h;
+  *reinterpret_cast<uint32_t*>(lo + off) = to_tf32(v - __uint_as_float(h));
+}
+
+// This thread's half of the gather: channel groups [g0, g0 + 6) of the sources in use_mask.  Partial dot products go
+// to dots[k * 128] (0 for sources that are not geometrically valid).
+__device__ __forceinline__ void gather_half(const float4* __restrict__ srcp_b, const float* __restrict__ proj, int K, int H, int W,
+                                            size_t HW, float X0, float X1, float X2, float uvx, float uvy, int g0,
+                                            const float (&cur)[kHalfC], unsigned use_mask, float (&fsum)[kHalfC],
+                                            float* __restrict__ dots, unsigned& geo_mask) {
+#pragma unroll
+  for (int c = 0; c < kHalfC; c++) fsum[c] = 0.f;
+  geo_mask = 0u;
+  for (int k = 0; k < K; k++) {
+    float dot = 0.f;
+    Taps t;
+    if (((use_mask >> k) & 1u) && make_taps(proj + 12 * k, X0, X1, X2, H, W, uvx, uvy, t)) {
+      geo_mask |= 1u << k;
+      const float4* __restrict__ s = srcp_b + ((size_t)k * (kCvC / 4) + g0) * HW;
+#pragma unroll
+      for (int g = 0; g < kHalfC / 4; g++) {
+        const float4* __restrict__ sg = s + (size_t)g * HW;
+        const float4 a = __ldg(sg + t.o00), b = __ldg(sg + t.o01), c = __ldg(sg + t.o10), d = __ldg(sg + t.o11);
+        const float w0 = fmaf(t.w11, d.x, fmaf(t.w10, c.x, fmaf(t.w01, b.x, t.w00 * a.x)));
+        const float w1 = fmaf(t.w11, d.y, fmaf(t.w10, c.y, fmaf(t.w01, b.y, t.w00 * a.y)));
+        const float w2 = fmaf(t.w11, d.z, fmaf(t.w10, c.z, fmaf(t.w01, b.z, t.w00 * a.z)));
+        const float w3 = fmaf(t.w11, d.w, fmaf(t.w10, c.w, fmaf(t.w01, b.w, t.w00 * a.w)));
+        dot = fmaf(w0, cur[4 * g], dot); dot = fmaf(w1, cur[4 * g + 1], dot);
+        dot = fmaf(w2, cur[4 * g + 2], dot); dot = fmaf(w3, cur[4 * g + 3], dot);
+        fsum[4 * g] += w0; fsum[4 * g + 1] += w1; fsum[4 * g + 2] += w2; fsum[4 * g + 3] += w3;
+      }
+    }
+    if (dots) dots[k * 128] = dot;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostVolumeArgs a, int planes_per_block) {
+  extern __shared__ unsigned char tcb_smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(tcb_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid & 127, half = tid >> 7;                 // reference pixel (= tile row = TMEM lane) and channel half
+  const int b = blockIdx.z;
+  const int H = a.H, W = a.W, K = a.K;
+  const size_t HW = (size_t)H * W;
+  // ---- one-time setup ----
+  {
+    const float* w0 = a.mlp;                                // [32][49]
+    const float* pb0 = w0 + kCvHid * kCvIn;
+    const float* w1 = pb0 + kCvHid;                         // [32][32]
+    const float* pb1 = w1 + kCvHid * kCvHid;
+    const float* w2 = pb1 + kCvHid;
+    for (int e = tid; e < kCvHid * 64; e += kThreads) {     // o = e>>6, i = e&63: columns 0..48 weights, column 49 = b0, rest 0
+      const int o = e >> 6, i = e & 63;
+      const float v = i < kCvIn ? w0[o * kCvIn + i] : (i == kCvIn ? pb0[o] : 0.f);
+      if (i < 56) put_w(sm.W0f_hi, sm.W0f_lo, wk_off(o, i, 32), v);
+      put_w(sm.W0t_hi, sm.W0t_lo, wk_off(i, o, 64), i < kCvIn ? v : 0.f);     // dX needs no bias column
+    }
+    for (int e = tid; e < kCvHid * kCvHid; e += kThreads) {
+      const int o = e >> 5, i = e & 31;
+      const float v = w1[e];
+      put_w(sm.W1f_hi, sm.W1f_lo, wk_off(o, i, 32), v);
+      put_w(sm.W1t_hi, sm.W1t_lo, wk_off(i, o, 32), v);
+    }
+    for (int k = tid; k < kCvHid; k += kThreads) { sm.b1[k] = pb1[k]; sm.W2[k] = w2[k]; }
+    for (int k = tid; k < K * 12; k += kThreads) sm.proj[k] = a.proj[(size_t)b * K * 12 + k];
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_chain)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_dw)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);     // this warp's 32 TMEM lanes
+  if (half == 1) {                                          // constant columns 56..63 of the MN-major X tile (columns 52..55: see S1)
+    const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    put8(z8, 0u, 0u, false, sm.X_hi, sm.X_lo, r, 56);
+  }
+  const uint32_t bar_chain = smem_u32(&sm.bar_chain), bar_dw = smem_u32(&sm.bar_dw);
+  const uint32_t aX_hi = smem_u32(sm.X_hi), aX_lo = smem_u32(sm.X_lo), aDZ_hi = smem_u32(sm.dZ_hi), aDZ_lo = smem_u32(sm.dZ_lo);
+  const uint32_t aW0f_hi = smem_u32(sm.W0f_hi), aW0f_lo = smem_u32(sm.W0f_lo), aW1f_hi = smem_u32(sm.W1f_hi), aW1f_lo = smem_u32(sm.W1f_lo);
+  const uint32_t aW1t_hi = smem_u32(sm.W1t_hi), aW1t_lo = smem_u32(sm.W1t_lo), aW0t_hi = smem_u32(sm.W0t_hi), aW0t_lo = smem_u32(sm.W0t_lo);
+  uint32_t ph_chain = 0, ph_dw = 0;
+  constexpr uint32_t kIdK32 = idesc(32, 0, 0), kIdK64 = idesc(64, 0, 0), kIdMN32 = idesc(32, 1, 1);
+
+  int u, v;
+  const bool active = patch_pixel(blockIdx.x, r, H, W, u, v);
+  if (!active) { u = 0; v = 0; }
+  const int p = v * W + u;
+  const float uvx = 1.0f / (float)W, uvy = 1.0f / (float)H;
+  const float* ik = a.cur_invK + (size_t)b * 9;
+  const float pu = (float)u + 0.5f, pv = (float)v + 0.5f;
+  const float r0 = fmaf(ik[1], pv, ik[0] * pu) + ik[2];
+  const float r1 = fmaf(ik[4], pv, ik[3] * pu) + ik[5];
+  const float r2 = fmaf(ik[7], pv, ik[6] * pu) + ik[8];
+  const int c0 = half * kHalfC, g0 = half * (kHalfC / 4);   // first channel / channel group of this thread
+  float cur[kHalfC], dcur[kHalfC];
+  {
+    const float* cb = a.cur_feats + ((size_t)b * kCvC + c0) * HW + p;
+#pragma unroll
+    for (int c = 0; c < kHalfC; c++) { cur[c] = __ldg(cb + (size_t)c * HW); dcur[c] = 0.f; }
+  }
+  float acc_w2[16], acc_b2 = 0.f;                           // dW2[16*half + j], db2 (half 0) summed over this thread's planes
+#pragma unroll
+  for (int j = 0; j < 16; j++) acc_w2[j] = 0.f;
+  const float4* src_b = reinterpret_cast<const float4*>(a.src_packed) + (size_t)b * K * (kCvC / 4) * HW;
+  float4* dsrc_b = reinterpret_cast<float4*>(a.dsrc_packed) + (size_t)b * K * (kCvC / 4) * HW;
+  const unsigned all = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+  const int d0 = blockIdx.y * planes_per_block, d1 = min(a.D, d0 + planes_per_block);
+  float* my_dots = &sm.dotp[half][0][r];
+
+  for (int d = d0; d < d1; d++) {
+    const bool first = d == d0;
+    float g = 0.f;
+    if (active) g = __ldg(a.dL_dout + ((size_t)b * a.D + d) * HW + p);
+    const float zd = __ldg(a.planes + d);
+    const float X0 = zd * r0, X1 = zd * r1, X2 = zd * r2;
+    // ------------------------------------------------------------ S1: gather, X operand, Z1 = X W0^T (+ b0)
+    unsigned geo, valid;
+    float rn;
+    float xs[kHalfC];                                       // x * rn of this thread's channels (live until S5)
+    {
+      gather_half(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, g0, cur, all, xs, my_dots, geo);
+      __syncthreads();
+      float dsum = 0.f;
+      unsigned zero = 0u;
+      for (int k = 0; k < K; k++) {
+        const float dot = sm.dotp[0][k][r] + sm.dotp[1][k][r];
+        if (((geo >> k) & 1u) && dot == 0.f) zero |= 1u << k;
+        dsum += dot;
+      }
+      valid = geo & ~zero;
+      if (zero) { unsigned g2; gather_half(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, g0, cur, valid, xs, nullptr, g2); }
+      rn = 1.0f / ((float)__popc(valid) + 1e-8f);
+#pragma unroll
+      for (int c = 0; c < kHalfC; c++) xs[c] *= rn;
+      if (!first) { mbar_wait(bar_dw, ph_dw); ph_dw ^= 1u; }          // U0 of the previous plane has finished reading the X and dZ tiles
+#pragma unroll
+      for (int q = 0; q < kHalfC / 8; q++) {
+        const float v8[8] = {xs[8 * q], xs[8 * q + 1], xs[8 * q + 2], xs[8 * q + 3], xs[8 * q + 4], xs[8 * q + 5], xs[8 * q + 6], xs[8 * q + 7]};
+        put8(v8, t_row + kColXhi + (uint32_t)(c0 + 8 * q), t_row + kColXlo + (uint32_t)(c0 + 8 * q), true, sm.X_hi, sm.X_lo, r, c0 + 8 * q);
+      }
+      if (half == 0) {
+        const float v8[8] = {dsum * rn, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        put8(v8, t_row + kColXhi + 48u, t_row + kColXlo + 48u, true, sm.X_hi, sm.X_lo, r, 48);
+      }
+    }
+    sync_for_mma();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int s = 0; s < 7; s++)
+        mma3_ts(tmem + kColZ1, tmem + kColXhi + 8u * s, tmem + kColXlo + 8u * s, aW0f_hi + s * 1024, aW0f_lo + s * 1024, kIdK32, s > 0 ? 1u : 0u);
+      commit(bar_chain);
+    }
+    mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ------------------------------------------------------------ S2: A1 = leaky(Z1), Z2 = A1 W1^T
+    {
+      float z[16];
+      tmem_ld<16>(t_row + kColZ1 + 16u * half, z);
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const float v8[8] = {leaky(z[8 * q]), leaky(z[8 * q + 1]), leaky(z[8 * q + 2]), leaky(z[8 * q + 3]),
+                             leaky(z[8 * q + 4]), leaky(z[8 * q + 5]), leaky(z[8 * q + 6]), leaky(z[8 * q + 7])};
+        put8(v8, t_row + kColHhi + (uint32_t)(16 * half + 8 * q), t_row + kColHlo + (uint32_t)(16 * half + 8 * q), true, sm.A1_hi, sm.A1_lo, r, 16 * half + 8 * q);
+      }
+    }
+    sync_for_mma();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int s = 0; s < 4; s++)
+        mma3_ts(tmem + kColZ2, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW1f_hi + s * 1024, aW1f_lo + s * 1024, kIdK32, s > 0 ? 1u : 0u);
+      commit(bar_chain);
+    }
+    mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ------------------------------------------------------------ S3: dZ2 = g W2 leaky'(Z2); dA1 = dZ2 W1; U1 += [X|A1]^T dZ2
+    {
+      float z[16];
+      tmem_ld<16>(t_row + kColZ2 + 16u * half, z);
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const float z2 = z[j] + sm.b1[16 * half + j];
+        acc_w2[j] = fmaf(g, leaky(z2), acc_w2[j]);
+        z[j] = g * sm.W2[16 * half + j] * dleaky(z2);
+      }
+      if (half == 0) acc_b2 += g;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const float v8[8] = {z[8 * q], z[8 * q + 1], z[8 * q + 2], z[8 * q + 3], z[8 * q + 4], z[8 * q + 5], z[8 * q + 6], z[8 * q + 7]};
+        put8(v8, t_row + kColHhi + (uint32_t)(16 * half + 8 * q), t_row + kColHlo + (uint32_t)(16 * half + 8 * q), true, sm.dZ_hi, sm.dZ_lo, r, 16 * half + 8 * q);
+      }
+    }
+    sync_for_mma();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int s = 0; s < 4; s++)
+        mma3_ts(tmem + kColDA1, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW1t_hi + s * 1024, aW1t_lo + s * 1024, kIdK32, s > 0 ? 1u : 0u);
+      commit(bar_chain);
+#pragma unroll
+      for (int s = 0; s < 16; s++)     // k = 8 tile rows per step
+        mma3_mn(tmem + kColU1, aX_hi + s * 1024, aX_lo + s * 1024, aDZ_hi + s * 1024, aDZ_lo + s * 1024, kIdMN32, (first && s == 0) ? 0u : 1u);
+      commit(bar_dw);
+    }
+    mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ------------------------------------------------------------ S4: dZ1 = dA1 leaky'(Z1); dX = dZ1 W0; U0 += [X|A1]^T dZ1
+    {
+      float da[16], z[16];
+      tmem_ld<16>(t_row + kColDA1 + 16u * half, da);
+      tmem_ld<16>(t_row + kColZ1 + 16u * half, z);
+#pragma unroll
+      for (int j = 0; j < 16; j++) da[j] *= dleaky(z[j]);
+      mbar_wait(bar_dw, ph_dw); ph_dw ^= 1u;                           // U1 has finished reading dZ2
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const float v8[8] = {da[8 * q], da[8 * q + 1], da[8 * q + 2], da[8 * q + 3], da[8 * q + 4], da[8 * q + 5], da[8 * q + 6], da[8 * q + 7]};
+        put8(v8, t_row + kColHhi + (uint32_t)(16 * half + 8 * q), t_row + kColHlo + (uint32_t)(16 * half + 8 * q), true, sm.dZ_hi, sm.dZ_lo, r, 16 * half + 8 * q);
+      }
+    }
+    sync_for_mma();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int s = 0; s < 4; s++)
+        mma3_ts(tmem + kColDX, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW0t_hi + s * 2048, aW0t_lo + s * 2048, kIdK64, s > 0 ? 1u : 0u);
+      commit(bar_chain);
+#pragma unroll
+      for (int s = 0; s < 16; s++)
+        mma3_mn(tmem + kColU0, aX_hi + s * 1024, aX_lo + s * 1024, aDZ_hi + s * 1024, aDZ_lo + s * 1024, kIdMN32, (first && s == 0) ? 0u : 1u);
+      commit(bar_dw);
+    }
+    mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ------------------------------------------------------------ S5: dX -> dL_dcur (registers), dL_dsrc (vector reductions)
+    float dx[kHalfC];
+    uint32_t dd;
+    {                                // tcgen05.ld is warp-collective: issued by every lane, outside the divergent part
+      uint32_t q0[8], q1[8], q2[8];
+      tmem_ld8_issue(t_row + kColDX + (uint32_t)c0, q0);
+      tmem_ld8_issue(t_row + kColDX + (uint32_t)c0 + 8u, q1);
+      tmem_ld8_issue(t_row + kColDX + (uint32_t)c0 + 16u, q2);
+      tmem_ld1_issue(t_row + kColDX + (uint32_t)kCvC, dd);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 8; e++) { dx[e] = __uint_as_float(q0[e]); dx[8 + e] = __uint_as_float(q1[e]); dx[16 + e] = __uint_as_float(q2[e]); }
+    }
+    if (active && g != 0.f) {
+      const float dxdot = __uint_as_float(dd);
+      const float gd = dxdot * rn;
+      // d dot_k / d cur[c] = w_k[c] and gd is the same for every source: gd * sum_k w_k[c] = dxdot * (x[c] * rn)
+      if (valid == geo) {
+#pragma unroll
+        for (int c = 0; c < kHalfC; c++) dcur[c] = fmaf(dxdot, xs[c], dcur[c]);
+      } else {                       // a source whose dot product is exactly 0 still feeds dL_dcur: gather the geometric set again
+        float wsum[kHalfC]; unsigned g2;
+        gather_half(src_b, sm.proj, K, H, W, HW, X0, X1, X2, uvx, uvy, g0, cur, geo, wsum, nullptr, g2);
+#pragma unroll
+        for (int c = 0; c < kHalfC; c++) dcur[c] = fmaf(gd, wsum[c], dcur[c]);
+      }
+      // back through the masked means: d(warped_k)[c] = [valid_k] dx[c] / n + [geo_k] cur[c] dxdot / n
+      for (int k = 0; k < K; k++) {
+        if (!((geo >> k) & 1u)) continue;
+        Taps t;
+        make_taps(sm.proj + 12 * k, X0, X1, X2, H, W, uvx, uvy, t);
+        const float fv = ((valid >> k) & 1u) ? rn : 0.f;
+        float4* __restrict__ ds = dsrc_b + ((size_t)k * (kCvC / 4) + g0) * HW;
+#pragma unroll
+        for (int q = 0; q < kHalfC / 4; q++) {
+          float gw[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) gw[e] = fmaf(dx[4 * q + e], fv, cur[4 * q + e] * gd);
+          float4* dg = ds + (size_t)q * HW;
+          if (t.w00 != 0.f) red_add_v4(dg + t.o00, t.w00 * gw[0], t.w00 * gw[1], t.w00 * gw[2], t.w00 * gw[3]);
+          if (t.w01 != 0.f) red_add_v4(dg + t.o01, t.w01 * gw[0], t.w01 * gw[1], t.w01 * gw[2], t.w01 * gw[3]);
+          if (t.w10 != 0.f) red_add_v4(dg + t.o10, t.w10 * gw[0], t.w10 * gw[1], t.w10 * gw[2], t.w10 * gw[3]);
+          if (t.w11 != 0.f) red_add_v4(dg + t.o11, t.w11 * gw[0], t.w11 * gw[1], t.w11 * gw[2], t.w11 * gw[3]);
+        }
+      }
+    }
+  }
+  // ---- flush dL_dcur (the plane chunks of one pixel live in different CTAs) ----
+  if (active) {
+    float* dc = a.dL_dcur + ((size_t)b * kCvC + c0) * HW + p;
+#pragma unroll
+    for (int c = 0; c < kHalfC; c++) if (dcur[c] != 0.f) atomicAdd(dc + (size_t)c * HW, dcur[c]);
+  }
+  // ---- parameter gradients: packed layout W0[32,49] b0[32] W1[32,32] b1[32] W2[32] b2[1] ----
+  float* gW0 = a.dL_dmlp;
+  float* gb0 = gW0 + kCvHid * kCvIn;
+  float* gW1 = gb0 + kCvHid;
+  float* gb1 = gW1 + kCvHid * kCvHid;
+  float* gW2 = gb1 + kCvHid;
+  float* gb2 = gW2 + kCvHid;
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    float s = acc_w2[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) atomicAdd(gW2 + 16 * half + j, s);
+  }
+  if (half == 0) {
+    float s = acc_b2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) atomicAdd(gb2, s);
+  }
+  if (d1 > d0) {
+    mbar_wait(bar_dw, ph_dw); ph_dw ^= 1u;                  // the last U0 chain
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float w[kCvHid];
+    if (half == 0) {                                        // lane r of U0 = column r of [X | A1]: input i = r, r == 49: the ones column
+      tmem_ld<32>(t_row + kColU0, w);
+      if (r < kCvIn) {
+#pragma unroll
+        for (int o = 0; o < kCvHid; o++) atomicAdd(gW0 + o * kCvIn + r, w[o]);
+      } else if (r == kCvIn) {
+#pragma unroll
+        for (int o = 0; o < kCvHid; o++) atomicAdd(gb0 + o, w[o]);
+      }
+    } else {
+      tmem_ld<32>(t_row + kColU1, w);
+      if (r >= 64 && r < 64 + kCvHid) {
+#pragma unroll
+        for (int o = 0; o < kCvHid; o++) atomicAdd(gW1 + o * kCvHid + (r - 64), w[o]);
+      } else if (r == kCvIn) {
+#pragma unroll
+        for (int o = 0; o < kCvHid; o++) atomicAdd(gb1 + o, w[o]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+}  // namespace tcb
+
 int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s) {
   const size_t HW = (size_t)a.H * a.W;
   const int ppb = 16;
@@ -791,13 +1282,20 @@ int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s) {
   if ((rc = check_cuda(cudaMemsetAsync(a.dsrc_packed, 0, n_src * sizeof(float), s), "memset dsrc_packed"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(a.dL_dcur, 0, n_cur * sizeof(float), s), "memset dL_dcur"))) return rc;
   if ((rc = check_cuda(cudaMemsetAsync(a.dL_dmlp, 0, n_mlp * sizeof(float), s), "memset dL_dmlp"))) return rc;
-  const size_t smem = ((sizeof(CvBwdSmem) + 15) / 16) * 16 + (size_t)kCvThreads * kRowStride * sizeof(float);
-  if ((rc = check_cuda(cudaFuncSetAttribute(cost_volume_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                       "cudaFuncSetAttribute(cost_volume_bwd_kernel)"))) return rc;
-  (void)HW;
   dim3 grid(patch_blocks(a.H, a.W), (unsigned)((a.D + ppb - 1) / ppb), (unsigned)a.B);
-  cost_volume_bwd_kernel<<<grid, kCvThreads, smem, s>>>(a, ppb);
-  if ((rc = check_cuda(cudaGetLastError(), "cost_volume_bwd_kernel"))) return rc;
+  if (a.mlp_mode == 1) {   // fp32 CUDA-core kernel: validation path for the tensor-core kernel
+    const size_t smem = ((sizeof(CvBwdSmem) + 15) / 16) * 16 + (size_t)kCvThreads * kRowStride * sizeof(float);
+    if ((rc = check_cuda(cudaFuncSetAttribute(cost_volume_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                         "cudaFuncSetAttribute(cost_volume_bwd_kernel)"))) return rc;
+    cost_volume_bwd_kernel<<<grid, kCvThreads, smem, s>>>(a, ppb);
+    if ((rc = check_cuda(cudaGetLastError(), "cost_volume_bwd_kernel"))) return rc;
+  } else {
+    const size_t smem = sizeof(tcb::Smem) + 1024;
+    if ((rc = check_cuda(cudaFuncSetAttribute(tcb::cost_volume_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                         "cudaFuncSetAttribute(cost_volume_bwd_tc_kernel)"))) return rc;
+    tcb::cost_volume_bwd_tc_kernel<<<grid, tcb::kThreads, smem, s>>>(a, ppb);
+    if ((rc = check_cuda(cudaGetLastError(), "cost_volume_bwd_tc_kernel"))) return rc;
+  }
   const size_t total = n_src / 4;
   cv_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(a.dsrc_packed), a.dL_dsrc, HW, total);
   return check_cuda(cudaGetLastError(), "cv_unpack_kernel");

@@ -25,6 +25,7 @@ SOURCES = [
     ("cost_volume.cu", []),
     ("ptf.cu", ["-fmad=false"]),
     ("adapter.cu", []),
+    ("depth_head.cu", []),
     ("c_api.cu", []),
 ]
 

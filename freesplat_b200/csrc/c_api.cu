@@ -36,6 +36,7 @@ int fs_struct_size(int32_t which) {
     case 3: return (int)sizeof(FsPtfArgs);
     case 4: return (int)sizeof(FsPtfGruArgs);
     case 5: return (int)sizeof(FsAdapterArgs);
+    case 6: return (int)sizeof(FsDepthHeadArgs);
     default: return -1;
   }
 }
@@ -167,6 +168,14 @@ int fs_gaussian_head(const FsAdapterArgs* a, void* stream) {
   FS_REQUIRE(a->N == 0 || (a->raw && a->depths && a->opacities && a->coords && a->ext && a->K && a->means && a->covariances &&
                            a->harmonics && a->opacities_out && a->scales && a->rotations), "NULL buffer");
   return launch_gaussian_head(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_depth_head(const FsDepthHeadArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr && a->B >= 0 && a->D >= 1 && a->h >= 1 && a->w >= 1 && a->B <= 65535, "bad sizes");
+  FS_REQUIRE((long long)a->h * a->w < (1ll << 29), "feature map too large");
+  FS_REQUIRE(a->B == 0 || (a->logits && a->candi && a->expect && a->depth), "NULL buffer");
+  FS_REQUIRE(a->B == 0 || !a->upsample || (a->depth_up && a->weights_up), "upsample set but depth_up / weights_up is NULL");
+  return launch_depth_head(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fs_ptf_gru(const FsPtfGruArgs* a, void* stream) {

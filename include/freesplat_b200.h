@@ -263,9 +263,28 @@ typedef struct FsAdapterArgs {
 } FsAdapterArgs;
 int fs_gaussian_head(const FsAdapterArgs* args, void* stream);
 
+/* ------------------------------------------------------------ depth-regression head tail */
+/* Tail of DepthDecoder.forward (modules/networks.py:130-152) for one scale: softmax over the D planes, expectation of
+ * the plane candidates, depth = exp(E) (log_planes) or 1/E; with `upsample` also the x2 bilinear (align_corners=True)
+ * outputs of scale 0: depth_pred_s-1 and depth_weights = max_d upsampled planes.  One pass over the logits.     */
+typedef struct FsDepthHeadArgs {
+  int32_t B, D, h, w;      /* logits [B,D,h,w]                                                       */
+  int32_t log_planes;      /* 1: depth = exp(E) (ScanNet / Replica configs), 0: depth = 1/E (RE10K)  */
+  int32_t upsample;        /* 1: scale 0 (fused x2 outputs, D <= 128), 0: scales 1..3                */
+  int32_t tile_mode;       /* 0: TMA box loads of the logit tiles, 1: LDG staging (validation path)  */
+  int32_t reserved;
+  const float* logits;
+  const float* candi;      /* [D] plane candidates (DepthDecoder.depth_candi_curr)                   */
+  float* expect;           /* [B,h,w]   log_depth_pred_s{i}                                          */
+  float* depth;            /* [B,h,w]   depth_pred_s{i}                                              */
+  float* depth_up;         /* [B,2h,2w] depth_pred_s-1   (upsample only)                             */
+  float* weights_up;       /* [B,2h,2w] depth_weights    (upsample only)                             */
+} FsDepthHeadArgs;
+int fs_depth_head(const FsDepthHeadArgs* args, void* stream);
+
 int fs_abi_version(void);
 /* sizeof() of the argument structs as compiled (0: FsRasterFwdArgs, 1: FsRasterBwdArgs, 2: FsCostVolumeArgs, 3: FsPtfArgs,
- * 4: FsPtfGruArgs, 5: FsAdapterArgs; -1 otherwise) so that a foreign-language binding can verify its layout.      */
+ * 4: FsPtfGruArgs, 5: FsAdapterArgs, 6: FsDepthHeadArgs; -1 otherwise) so that a foreign-language binding can verify its layout.      */
 int fs_struct_size(int32_t which);
 const char* fs_last_error(void);      /* thread-local, valid until the next call  */
 int fs_device_sm_count(void);         /* negative FsStatus on failure             */

@@ -84,5 +84,41 @@ def raster_f():
 
 
 res["raster_cfg3_P460800_T4"] = {"fwd_ms": timeit(raster_f, n=10, warm=3), "fwd_bwd_ms": timeit(raster_fb, n=10, warm=3)}
+# ---- depth-head tail: 3 views at 640x480 (scale 0 = 240x320, D = 128) ----
+from freesplat_b200.depth_head import depth_regression  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+Vd, Dd, hd, wd = 3, 128, 240, 320
+lg = (torch.randn((Vd, Dd, hd, wd), device=dev) * 5)
+cand = (torch.log(torch.tensor(0.5)) + torch.linspace(0, 1, Dd) * torch.log(torch.tensor(30.0))).to(dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit_cold(fn, n=10, warm=3):     # L2 flushed before every timed call (the logits of 3 views fit in the 126 MB L2)
+    for _ in range(warm):
+        fn()
+    tot = 0.0
+    for _ in range(n):
+        flush.zero_(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / n
+
+
+def torch_tail():      # the reference's op sequence (networks.py:130-152) on the GPU
+    planes = F.softmax(lg, dim=1)
+    coarse = (cand.view(1, -1, 1, 1) * planes).sum(dim=1, keepdim=True)
+    fine = F.interpolate(coarse, scale_factor=2, mode="bilinear", align_corners=True)
+    return torch.exp(coarse), torch.exp(fine), F.interpolate(planes, scale_factor=2, mode="bilinear", align_corners=True).max(dim=1, keepdim=True)[0]
+
+
+with torch.no_grad():
+    t_tma = timeit_cold(lambda: depth_regression(lg, cand, True, upsample=True, tile_mode=0))
+    t_ldg = timeit_cold(lambda: depth_regression(lg, cand, True, upsample=True, tile_mode=1))
+    t_exp = timeit_cold(lambda: depth_regression(lg, cand, True, upsample=False))
+    t_ref = timeit_cold(torch_tail, n=5, warm=2)
+alg = Vd * (Dd * hd * wd * 4 + 10 * hd * wd * 4)
+res["depth_head_V3_640x480"] = {"fused_tma_ms": t_tma, "fused_ldg_ms": t_ldg, "expect_only_ms": t_exp, "torch_ops_ms": t_ref,
+                                "alg_bytes": alg, "gbs_tma": alg / (t_tma * 1e-3) / 1e9, "gbs_expect_only": Vd * (Dd + 2) * hd * wd * 4 / (t_exp * 1e-3) / 1e9}
 print(json.dumps(res, indent=1))
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_ops.json"), "w"), indent=1)

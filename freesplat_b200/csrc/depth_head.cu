@@ -112,24 +112,33 @@ __global__ void __launch_bounds__(kThreads, 2) depth_head_up_kernel(const __grid
     const int gy = ty0 + yy, gx = tx0 + xx;
     const bool mine = tid < kPlane && xx <= kCoreX && gy < h && gx < w;
     float* tp = sm.tile + tid;
-    float m = -INFINITY;
+    float m0 = -INFINITY, m1 = -INFINITY;                                // two chains: the sweeps are latency bound
     for (int c = 0; c < nchunk; c++) {
       if (kTma) mbar_wait(smem_u32(&sm.bar[c]), 0u);
       if (mine) {
         const int dend = min(D, (c + 1) * kChunkD);
-#pragma unroll 8
-        for (int d = c * kChunkD; d < dend; d++) m = fmaxf(m, tp[d * kPlane]);
+        int d = c * kChunkD;
+#pragma unroll 4
+        for (; d + 2 <= dend; d += 2) { m0 = fmaxf(m0, tp[d * kPlane]); m1 = fmaxf(m1, tp[(d + 1) * kPlane]); }
+        if (d < dend) m0 = fmaxf(m0, tp[d * kPlane]);
       }
     }
     if (mine) {
-      float s = 0.f, acc = 0.f;
-#pragma unroll 8
-      for (int d = 0; d < D; d++) {
-        const float e = __expf(tp[d * kPlane] - m);
-        s += e;
-        acc = fmaf(sm.candi[d], e, acc);
-        tp[d * kPlane] = e;
+      const float m = fmaxf(m0, m1);
+      float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
+      int d = 0;
+#pragma unroll 4
+      for (; d + 2 <= D; d += 2) {
+        const float e0 = __expf(tp[d * kPlane] - m), e1 = __expf(tp[(d + 1) * kPlane] - m);
+        s0 += e0; s1 += e1;
+        a0 = fmaf(sm.candi[d], e0, a0); a1 = fmaf(sm.candi[d + 1], e1, a1);
+        tp[d * kPlane] = e0; tp[(d + 1) * kPlane] = e1;
       }
+      if (d < D) {
+        const float e0 = __expf(tp[d * kPlane] - m);
+        s0 += e0; a0 = fmaf(sm.candi[d], e0, a0); tp[d * kPlane] = e0;
+      }
+      const float s = s0 + s1, acc = a0 + a1;
       const float rs = 1.0f / s, E = acc * rs;
       sm.rs[tid] = rs; sm.E[tid] = E;
       if (yy < kCoreY && xx < kCoreX) {

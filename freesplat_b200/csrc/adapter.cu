@@ -63,6 +63,102 @@ __global__ void __launch_bounds__(256) gaussian_head_kernel(FsAdapterArgs a) {
   a.opacities_out[i] = a.opacities[i];
 }
 
+// Depth back-projection of the context views: GaussianAdapter.forward(fusion=True)
+// (gaussian_adapter.py:175-189) -> Create_from_depth_map.project (:48-68): per pixel (i, j)
+//   cam = ((j - cx) / fx * z, (i - cy) / fy * z, z, 1),  world = c2w . cam
+// with the pixel-space intrinsics of view 0 (rows scaled by w and h in fp32, :179-181).  The reference loops over
+// views in Python with ~15 torch launches each; one launch here.  The world coordinates feed the index decisions of
+// PTF, so the arithmetic is the canonical order of oracle/adapter.py::backproject (round-to-nearest intrinsics, explicit
+// fma chain = torch's CPU sgemm order for [4,4] @ [4,N]): bit-identical to the reference on the golden cases.
+__global__ void __launch_bounds__(256) backproject_kernel(FsBackprojectArgs a) {
+  const int HW = a.H * a.W;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= HW) return;
+  const int v = blockIdx.y;
+  const int i = p / a.W, j = p - i * a.W;
+  const float fx = __fmul_rn(a.K[0], (float)a.W), cx = __fmul_rn(a.K[2], (float)a.W);
+  const float fy = __fmul_rn(a.K[4], (float)a.H), cy = __fmul_rn(a.K[5], (float)a.H);
+  const float z = a.depth[(size_t)v * HW + p];
+  const float x = __fmul_rn(__fdiv_rn(__fsub_rn((float)j, cx), fx), z);
+  const float y = __fmul_rn(__fdiv_rn(__fsub_rn((float)i, cy), fy), z);
+  const float* E = a.c2w + 16 * (size_t)v;
+  float* o = a.means + 3 * ((size_t)v * HW + p);
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+    o[r] = __fmaf_rn(E[4 * r + 3], 1.0f, __fmaf_rn(E[4 * r + 2], z, __fmaf_rn(E[4 * r + 1], y, __fmul_rn(E[4 * r], x))));
+}
+
+int launch_backproject(const FsBackprojectArgs& a, cudaStream_t s) {
+  if (a.V <= 0) return FS_OK;
+  dim3 grid((unsigned)((a.H * a.W + 255) / 256), (unsigned)a.V);
+  backproject_kernel<<<grid, 256, 0, s>>>(a);
+  return check_cuda(cudaGetLastError(), "backproject_kernel");
+}
+
+// Vertex table of the .ply export (src/model/ply_export.py:26-92): per Gaussian
+//   xyz = R ((mean - median) / scale_factor), normals 0, DC band of the harmonics, opacity, log(scale / scale_factor),
+//   rotation = quaternion of  R . matrix(q)  in (w, x, y, z) order -- scipy's from_quat / from_matrix rules in fp64, as the
+// reference evaluates them (oracle/ply.py).  Rows leave through shared memory as contiguous float runs (17 floats per row).
+__global__ void __launch_bounds__(256) ply_vertices_kernel(FsPlyArgs a) {
+  __shared__ float rows[256 * 17];
+  const int base = blockIdx.x * 256, n = base + threadIdx.x;
+  if (n < a.N) {
+    float* o = rows + threadIdx.x * 17;
+    const float sf = a.scale_factor;
+    float m[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) m[k] = (a.means[3 * (size_t)n + k] - a.shift[k]) / sf;
+#pragma unroll
+    for (int r = 0; r < 3; r++) o[r] = a.R[3 * r] * m[0] + a.R[3 * r + 1] * m[1] + a.R[3 * r + 2] * m[2];
+    o[3] = 0.f; o[4] = 0.f; o[5] = 0.f;
+    const float* sh = a.harmonics + (size_t)n * 3 * a.d_sh;
+    o[6] = sh[0]; o[7] = sh[a.d_sh]; o[8] = sh[2 * a.d_sh];
+    o[9] = a.opacities[n];
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[10 + k] = logf(a.scales[3 * (size_t)n + k] / sf);
+    // quaternion (x, y, z, w) -> matrix -> rotate -> quaternion, fp64
+    double q[4] = {(double)a.rotations[4 * (size_t)n], (double)a.rotations[4 * (size_t)n + 1], (double)a.rotations[4 * (size_t)n + 2],
+                   (double)a.rotations[4 * (size_t)n + 3]};
+    const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const double x = q[0] / qn, y = q[1] / qn, z = q[2] / qn, w = q[3] / qn;
+    const double Mq[9] = {x * x - y * y - z * z + w * w, 2 * (x * y - z * w), 2 * (x * z + y * w),
+                          2 * (x * y + z * w), -x * x + y * y - z * z + w * w, 2 * (y * z - x * w),
+                          2 * (x * z - y * w), 2 * (y * z + x * w), -x * x - y * y + z * z + w * w};
+    double A[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+        A[3 * r + c] = (double)a.R[3 * r] * Mq[c] + (double)a.R[3 * r + 1] * Mq[3 + c] + (double)a.R[3 * r + 2] * Mq[6 + c];
+    const double tr = A[0] + A[4] + A[8];
+    int c = 0;
+    double best = A[0];
+    if (A[4] > best) { best = A[4]; c = 1; }
+    if (A[8] > best) { best = A[8]; c = 2; }
+    if (tr > best) c = 3;
+    double qo[4];
+    if (c != 3) {
+      const int i = c, j = (c + 1) % 3, k = (c + 2) % 3;
+      qo[i] = 1 - tr + 2 * A[3 * i + i]; qo[j] = A[3 * j + i] + A[3 * i + j]; qo[k] = A[3 * k + i] + A[3 * i + k];
+      qo[3] = A[3 * k + j] - A[3 * j + k];
+    } else {
+      qo[0] = A[7] - A[5]; qo[1] = A[2] - A[6]; qo[2] = A[3] - A[1]; qo[3] = 1 + tr;
+    }
+    const double on = sqrt(qo[0] * qo[0] + qo[1] * qo[1] + qo[2] * qo[2] + qo[3] * qo[3]);
+    o[13] = (float)(qo[3] / on); o[14] = (float)(qo[0] / on); o[15] = (float)(qo[1] / on); o[16] = (float)(qo[2] / on);
+  }
+  __syncthreads();
+  const int cnt = min(256, a.N - base) * 17;
+  float* dst = a.table + (size_t)base * 17;
+  for (int k = threadIdx.x; k < cnt; k += 256) dst[k] = rows[k];
+}
+
+int launch_ply_vertices(const FsPlyArgs& a, cudaStream_t s) {
+  if (a.N <= 0) return FS_OK;
+  ply_vertices_kernel<<<(a.N + 255) / 256, 256, 0, s>>>(a);
+  return check_cuda(cudaGetLastError(), "ply_vertices_kernel");
+}
+
 int launch_gaussian_head(const FsAdapterArgs& a, cudaStream_t s) {
   if (a.N <= 0) return FS_OK;
   gaussian_head_kernel<<<(a.N + 255) / 256, 256, 0, s>>>(a);

@@ -37,6 +37,8 @@ int fs_struct_size(int32_t which) {
     case 4: return (int)sizeof(FsPtfGruArgs);
     case 5: return (int)sizeof(FsAdapterArgs);
     case 6: return (int)sizeof(FsDepthHeadArgs);
+    case 7: return (int)sizeof(FsBackprojectArgs);
+    case 8: return (int)sizeof(FsPlyArgs);
     default: return -1;
   }
 }
@@ -168,6 +170,19 @@ int fs_gaussian_head(const FsAdapterArgs* a, void* stream) {
   FS_REQUIRE(a->N == 0 || (a->raw && a->depths && a->opacities && a->coords && a->ext && a->K && a->means && a->covariances &&
                            a->harmonics && a->opacities_out && a->scales && a->rotations), "NULL buffer");
   return launch_gaussian_head(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_ply_vertices(const FsPlyArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr && a->N >= 0 && a->d_sh >= 1, "bad sizes");
+  FS_REQUIRE(a->N == 0 || (a->means && a->scales && a->rotations && a->harmonics && a->opacities && a->table), "NULL buffer");
+  FS_REQUIRE(a->scale_factor > 0.f, "scale_factor must be positive");
+  return launch_ply_vertices(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_backproject(const FsBackprojectArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr && a->V >= 0 && a->V <= 65535 && a->H >= 1 && a->W >= 1 && (long long)a->H * a->W < (1ll << 30), "bad sizes");
+  FS_REQUIRE(a->V == 0 || (a->depth && a->K && a->c2w && a->means), "NULL buffer");
+  return launch_backproject(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fs_depth_head(const FsDepthHeadArgs* a, void* stream) {

@@ -33,6 +33,8 @@ int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s);  // cost_
 int launch_ptf_match(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
 int launch_ptf_merge(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
 int launch_gaussian_head(const FsAdapterArgs& a, cudaStream_t s);   // adapter.cu
+int launch_backproject(const FsBackprojectArgs& a, cudaStream_t s);   // adapter.cu
+int launch_ply_vertices(const FsPlyArgs& a, cudaStream_t s);          // adapter.cu
 int launch_depth_head(const FsDepthHeadArgs& a, cudaStream_t s);    // depth_head.cu
 int launch_ptf_gru_tc(const FsPtfGruArgs& a, cudaStream_t s);
 size_t ptf_gru_wscratch_bytes();

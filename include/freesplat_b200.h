@@ -263,6 +263,35 @@ typedef struct FsAdapterArgs {
 } FsAdapterArgs;
 int fs_gaussian_head(const FsAdapterArgs* args, void* stream);
 
+/* ------------------------------------------------------------ .ply vertex table */
+/* The per-Gaussian part of export_ply (src/model/ply_export.py:26-92): [N,17] float rows
+ * (x y z nx ny nz f_dc_0..2 opacity scale_0..2 rot_0..3) ready to be written after a binary_little_endian header.   */
+typedef struct FsPlyArgs {
+  int32_t N, d_sh;
+  float scale_factor;      /* means.abs().quantile(0.95, dim=0).max() of the median-shifted means     */
+  float shift[3];          /* means.median(dim=0).values                                              */
+  float R[9];              /* viewer rotation @ inverse camera rotation, row-major (ply_export.py:43-63) */
+  const float* means;      /* [N,3]  */
+  const float* scales;     /* [N,3]  */
+  const float* rotations;  /* [N,4] xyzw */
+  const float* harmonics;  /* [N,3,d_sh] */
+  const float* opacities;  /* [N]    */
+  float* table;            /* [N,17] */
+} FsPlyArgs;
+int fs_ply_vertices(const FsPlyArgs* args, void* stream);
+
+/* ------------------------------------------------------------ depth back-projection */
+/* GaussianAdapter.forward(fusion=True) (gaussian_adapter.py:175-189 -> Create_from_depth_map.project :48-68): world
+ * coordinates of every pixel of the V context views from their depth maps, one launch.                          */
+typedef struct FsBackprojectArgs {
+  int32_t V, H, W, reserved;
+  const float* depth;      /* [V,H,W]                                                                 */
+  const float* K;          /* [9] NORMALISED intrinsics of view 0 (the reference uses intrinsics[i,0]) */
+  const float* c2w;        /* [V,16] camera-to-world                                                  */
+  float* means;            /* [V,H*W,3]                                                               */
+} FsBackprojectArgs;
+int fs_backproject(const FsBackprojectArgs* args, void* stream);
+
 /* ------------------------------------------------------------ depth-regression head tail */
 /* Tail of DepthDecoder.forward (modules/networks.py:130-152) for one scale: softmax over the D planes, expectation of
  * the plane candidates, depth = exp(E) (log_planes) or 1/E; with `upsample` also the x2 bilinear (align_corners=True)
@@ -284,7 +313,7 @@ int fs_depth_head(const FsDepthHeadArgs* args, void* stream);
 
 int fs_abi_version(void);
 /* sizeof() of the argument structs as compiled (0: FsRasterFwdArgs, 1: FsRasterBwdArgs, 2: FsCostVolumeArgs, 3: FsPtfArgs,
- * 4: FsPtfGruArgs, 5: FsAdapterArgs, 6: FsDepthHeadArgs; -1 otherwise) so that a foreign-language binding can verify its layout.      */
+ * 4: FsPtfGruArgs, 5: FsAdapterArgs, 6: FsDepthHeadArgs, 7: FsBackprojectArgs, 8: FsPlyArgs; -1 otherwise) so that a foreign-language binding can verify its layout.      */
 int fs_struct_size(int32_t which);
 const char* fs_last_error(void);      /* thread-local, valid until the next call  */
 int fs_device_sm_count(void);         /* negative FsStatus on failure             */

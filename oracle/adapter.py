@@ -42,3 +42,28 @@ def forward(raw, depths, opacities, coords, ext, K, image_shape, scale_min=0.5, 
     cov = (C @ cov @ np.swapaxes(C, 1, 2)).astype(F32)
     return dict(means=np.asarray(coords, F32), covariances=cov, harmonics=sh, opacities=np.asarray(opacities, F32), scales=scales,
                 rotations=rot)
+
+
+def _fma(a, b, c):
+    """fp32 fused multiply-add (one rounding): the product of two floats is exact in fp64."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(F32)
+
+
+def backproject(depths, K_norm, c2w, image_shape):
+    """GaussianAdapter.forward(fusion=True) (gaussian_adapter.py:175-189) -> Create_from_depth_map.project (:48-68):
+    depths [V,H,W], K_norm [3,3] (view 0), c2w [V,4,4] -> world coordinates [V,H*W,3].  Canonical order: intrinsics rows
+    scaled by w / h in fp32, (j - cx) / fx * z, then the fma chain of torch's CPU sgemm for [4,4] @ [4,N]."""
+    h, w = image_shape
+    depths = np.asarray(depths, F32).reshape(-1, h, w); K = np.asarray(K_norm, F32); c2w = np.asarray(c2w, F32)
+    fx, cx = F32(K[0, 0] * F32(w)), F32(K[0, 2] * F32(w))
+    fy, cy = F32(K[1, 1] * F32(h)), F32(K[1, 2] * F32(h))
+    jj, ii = np.meshgrid(np.arange(w, dtype=F32), np.arange(h, dtype=F32))
+    px = ((jj - cx) / fx).astype(F32); py = ((ii - cy) / fy).astype(F32)
+    out = np.empty((depths.shape[0], h * w, 3), F32)
+    for v in range(depths.shape[0]):
+        z = depths[v]; x = (px * z).astype(F32); y = (py * z).astype(F32); E = c2w[v]
+        for r in range(3):
+            t = (E[r, 0] * x).astype(F32)
+            t = _fma(E[r, 1], y, t); t = _fma(E[r, 2], z, t); t = _fma(E[r, 3], F32(1.0), t)
+            out[v, :, r] = t.reshape(-1)
+    return out

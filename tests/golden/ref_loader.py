@@ -118,3 +118,37 @@ def load_gaussian_adapter():
         spec.loader.exec_module(m)
     ga = sys.modules[f"{root}.src.model.encoder.common.gaussian_adapter"]
     return ga.GaussianAdapter, ga.GaussianAdapterCfg
+
+
+def load_export_ply():
+    """Returns (export_ply, captured): the reference's src/model/ply_export.py::export_ply with stub `plyfile` /
+    `jaxtyping` modules (both absent here); the structured vertex array it hands to plyfile lands in captured["elements"]."""
+    captured = {}
+    if "jaxtyping" not in sys.modules:
+        jt = types.ModuleType("jaxtyping")
+
+        class _Ann:
+            def __class_getitem__(cls, item):
+                return cls
+        jt.Float = _Ann
+        sys.modules["jaxtyping"] = jt
+    pf = types.ModuleType("plyfile")
+
+    class PlyElement:
+        @staticmethod
+        def describe(el, name):
+            captured["elements"] = el.copy(); captured["name"] = name
+            return (name, el)
+
+    class PlyData:
+        def __init__(self, els):
+            self.els = els
+
+        def write(self, path):
+            captured["path"] = path
+    pf.PlyData, pf.PlyElement = PlyData, PlyElement
+    sys.modules["plyfile"] = pf
+    spec = importlib.util.spec_from_file_location("ref_ply_export", os.path.join(REF, "src", "model", "ply_export.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.export_ply, captured

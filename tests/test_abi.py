@@ -41,12 +41,13 @@ def test_abi_version_and_error_string(lib):
 
 
 def test_struct_sizes_match_ctypes(lib):
-    from freesplat_b200.adapter import FsAdapterArgs
+    from freesplat_b200.adapter import FsAdapterArgs, FsBackprojectArgs
     from freesplat_b200.cost_volume import FsCostVolumeArgs
     from freesplat_b200.depth_head import FsDepthHeadArgs
+    from freesplat_b200.ply_export import FsPlyArgs
     from freesplat_b200.ptf import FsPtfArgs, FsPtfGruArgs
     for which, st in enumerate([_lib.FsRasterFwdArgs, _lib.FsRasterBwdArgs, FsCostVolumeArgs, FsPtfArgs, FsPtfGruArgs, FsAdapterArgs,
-                               FsDepthHeadArgs]):
+                               FsDepthHeadArgs, FsBackprojectArgs, FsPlyArgs]):
         assert lib.fs_struct_size(which) == C.sizeof(st), (which, st.__name__, lib.fs_struct_size(which), C.sizeof(st))
     assert lib.fs_struct_size(99) == -1
 

@@ -8,6 +8,12 @@
     candidates of all ranks (the "cross-view PTF gather" of BASELINE.json) in global view order and every
     rank runs the identical deterministic fusion.
 
+  * training: every rank back-propagates the loss of ITS target views into the replicated Gaussian set, so the
+    gradients w.r.t. means / covariances / harmonics / opacities are partial sums: `sync_gaussian_grads` is the
+    identity in forward and ONE all-reduce(SUM) of the packed [G, 3+9+d+1] gradient buffer in backward (the only
+    data-path collective of the training step; NCCL rings over NVLink / NVSwitch), placed between the rasterizer
+    backward and the PTF / encoder backward.  `render_views_sharded` bundles sharding, rendering and that collective.
+
 Works with the NCCL backend on GPUs and with gloo on the CPU (tests/test_parallel_gloo.py).
 """
 from __future__ import annotations
@@ -54,3 +60,63 @@ def max_over_ranks(values: Sequence[float], device, group=None) -> List[float]:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return [float(x) for x in t]
+
+
+class _SyncGaussianGrads(torch.autograd.Function):
+    """Identity on the replicated Gaussian tensors; backward sums their gradients over the ranks with ONE all-reduce
+    of a packed buffer (a bucket sized for launch latency: 40 floats per Gaussian at SH degree 2, 120 MB at G = 750 k)."""
+
+    @staticmethod
+    def forward(ctx, group, *tensors):
+        ctx.group = group
+        ctx.shapes = [t.shape for t in tensors]
+        return tuple(t.view_as(t) for t in tensors)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        n0 = ctx.shapes[0][0]
+        cols = [int(torch.Size(s).numel() // max(n0, 1)) for s in ctx.shapes]
+        ref = next(g for g in grads if g is not None)
+        packed = ref.new_zeros((n0, sum(cols)))
+        o = 0
+        for g, c in zip(grads, cols):
+            if g is not None:
+                packed[:, o:o + c] = g.reshape(n0, c)
+            o += c
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=ctx.group)
+        out, o = [], 0
+        for s, c in zip(ctx.shapes, cols):
+            out.append(packed[:, o:o + c].reshape(s))
+            o += c
+        return (None, *out)
+
+
+def sync_gaussian_grads(*tensors, group=None):
+    """tensors: per-Gaussian tensors that are replicated on every rank ([G, ...] each).  Returns them unchanged; their
+    gradients are summed over the ranks in backward."""
+    return _SyncGaussianGrads.apply(group, *tensors)
+
+
+def render_views_sharded(extrinsics, intrinsics, near, far, image_shape, background_color, means, covariances, harmonics,
+                         opacities, group=None, render_fn=None, **kw):
+    """View-sharded rendering of one scene: all arguments are the FULL [V, ...] camera tensors and the
+    replicated Gaussian set; this rank renders views `shard_views(V, rank, world)` and returns (color, depth, view_ids)
+    for them.  Under autograd the Gaussian gradients of all ranks are summed (sync_gaussian_grads)."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    ids = shard_views(extrinsics.shape[0], rank, world)
+    if render_fn is None:
+        from .decoder import render_views as render_fn
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (means, covariances, harmonics, opacities)):
+        means, covariances, harmonics, opacities = sync_gaussian_grads(means, covariances, harmonics, opacities, group=group)
+    sel = torch.tensor(ids, dtype=torch.long, device=extrinsics.device)
+    if not ids:
+        # no view for this rank: empty outputs that still hang off the synced tensors, so that this rank's backward
+        # reaches the all-reduce (a rank that skipped the collective would dead-lock the others)
+        h, w = image_shape
+        z = (means.sum() + covariances.sum() + harmonics.sum() + opacities.sum()) * 0.0
+        return z.reshape(1, 1, 1, 1).expand(0, 3, h, w), z.reshape(1, 1, 1).expand(0, h, w), ids
+    color, depth = render_fn(extrinsics[sel], intrinsics[sel], near[sel], far[sel], image_shape, background_color[sel], means,
+                             covariances, harmonics, opacities, **kw)
+    return color, depth, ids

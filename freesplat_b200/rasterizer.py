@@ -236,20 +236,25 @@ class _RasterizeViews(torch.autograd.Function):
                                 scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp, sh_degree=sh_degree,
                                 scale_modifier=scale_modifier, prefiltered=prefiltered,
                                 check_overflow=check_overflow, sh_layout=sh_layout, cov_stride=cov_stride)
+        color, depth = st.color, st.depth
+        # the OUTPUT tensors must not stay reachable from ctx: output -> grad_fn -> ctx -> st -> output is a reference
+        # cycle that only Python's cyclic GC breaks, i.e. every step's workspace (hundreds of MB) would outlive the step
+        # and the caching allocator would cudaMalloc afresh each iteration
+        st.color = None; st.depth = None
+        st.keybuf = None  # sorted keys are only needed by the parity tests (raster_forward_raw)
         ctx.st = st
         ctx.depth_grad = depth_grad
         ctx.save_for_backward(means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp)
         ctx.mark_non_differentiable(st.radii)
         alpha = 1.0 - st.final_T
-        st.keybuf = None  # sorted keys are only needed by the parity tests (raster_forward_raw)
-        return st.color, st.radii, st.depth, alpha
+        return color, st.radii, depth, alpha
 
     @staticmethod
     def backward(ctx, g_color, g_radii, g_depth, g_alpha):
         means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp = ctx.saved_tensors
         st = ctx.st
         if g_color is None:
-            g_color = torch.zeros_like(st.color)
+            g_color = torch.zeros((st.V, 3, st.H, st.W), dtype=torch.float32, device=means3D.device)
         dd = g_depth if (ctx.depth_grad and g_depth is not None) else None
         g = raster_backward_raw(st, means3D, opacities, g_color, shs=shs, colors_precomp=colors_precomp, scales=scales,
                                 rotations=rotations, cov3D_precomp=cov3D_precomp, dL_ddepth=dd)

@@ -60,3 +60,64 @@ def test_gather_world2_uneven_and_even():
         assert [r[1] for r in res] == [parallel.shard_views(n, 0, 2), parallel.shard_views(n, 1, 2)]
         assert all(r[2] for r in res)
         assert all(r[3] == [2.0, 5.0] for r in res)
+
+
+def _fake_render(ext, intr, near, far, image_shape, bg, means, cov, sh, op):
+    """Differentiable stand-in for the rasterizer on the CPU: every view mixes all Gaussians with view-dependent weights."""
+    h, w = image_shape
+    wv = ext[:, 0, 3].reshape(-1, 1)                                         # [v,1]
+    val = (means.sum(1) + cov.sum((1, 2)) * 0.5 + sh.sum((1, 2)) * 0.25 + op)[None] * wv      # [v,G]
+    col = val.sum(1).reshape(-1, 1, 1, 1).expand(-1, 3, h, w) * torch.arange(1.0, 4.0).reshape(1, 3, 1, 1)
+    return col, col[:, 0]
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        G, V = 7, 5
+        leaf = [torch.randn(s, generator=g).requires_grad_(True) for s in ((G, 3), (G, 3, 3), (G, 3, 9), (G,))]
+        ext = torch.eye(4).repeat(V, 1, 1); ext[:, 0, 3] = torch.arange(1.0, V + 1)
+        z = torch.zeros(V)
+        col, dep, ids = parallel.render_views_sharded(ext, torch.eye(3).repeat(V, 1, 1), z, z, (2, 3), torch.zeros(V, 3), *leaf,
+                                                      render_fn=_fake_render)
+        (col.sum() + dep.sum()).backward()                                   # loss of the LOCAL views only
+        # one view, two ranks: rank 1 renders nothing but must still take part in the gradient all-reduce
+        leaf1 = [t.detach().clone().requires_grad_(True) for t in leaf]
+        c1, d1, ids1 = parallel.render_views_sharded(ext[:1], torch.eye(3).repeat(1, 1, 1), z[:1], z[:1], (2, 3), torch.zeros(1, 3),
+                                                     *leaf1, render_fn=_fake_render)
+        (c1.sum() + d1.sum()).backward()
+        assert len(ids1) == (1 if rank == 0 else 0) and c1.shape[0] == len(ids1)
+        ref1 = [t.detach().clone().requires_grad_(True) for t in leaf]
+        cr, dr = _fake_render(ext[:1], None, None, None, (2, 3), None, *ref1)
+        (cr.sum() + dr.sum()).backward()
+        for a_, b_ in zip(leaf1, ref1):
+            torch.testing.assert_close(a_.grad, b_.grad, rtol=1e-6, atol=1e-6)
+        q.put((rank, ids, [t.grad.clone() for t in leaf]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_render_sums_gaussian_gradients_over_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda r: r[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3]
+    # single-process reference: all views on one rank
+    g = torch.Generator().manual_seed(0)
+    G, V = 7, 5
+    leaf = [torch.randn(s, generator=g).requires_grad_(True) for s in ((G, 3), (G, 3, 3), (G, 3, 9), (G,))]
+    ext = torch.eye(4).repeat(V, 1, 1); ext[:, 0, 3] = torch.arange(1.0, V + 1)
+    col, dep = _fake_render(ext, None, None, None, (2, 3), None, *leaf)
+    (col.sum() + dep.sum()).backward()
+    for r in res:
+        for got, want in zip(r[2], leaf):
+            torch.testing.assert_close(got, want.grad, rtol=1e-6, atol=1e-6)

@@ -190,3 +190,27 @@ def test_host_pipeline_matches_direct_call():
             c2, d2 = decoder.render_views(g.extrinsics, g.intrinsics, g.near, g.far, g.image_shape, torch.zeros((2, 3), device=dev),
                                           g.means, g.covariances, g.harmonics, g.opacities)
         assert torch.equal(c, c2.cpu()) and torch.equal(d, d2.cpu())
+
+
+def test_training_loop_reuses_its_workspace():
+    """Steady-state training steps must not allocate device memory: the autograd node may not keep its own outputs alive
+    (a reference cycle would park every step's workspace until Python's cyclic GC runs)."""
+    import gc
+    from freesplat_b200 import decoder
+    dev = "cuda:0"
+    sc = synth.pixel_aligned_scene(seed=0, h=120, w=160, n_context=2, n_target=3, keep=None).to(dev)
+    params = [x.detach().clone().requires_grad_(True) for x in (sc.means, sc.covariances, sc.harmonics, sc.opacities)]
+    bg = torch.zeros((3, 3), device=dev)
+    gc.collect(); gc.disable()
+    try:
+        allocs = []
+        for it in range(8):
+            for p in params:
+                p.grad = None
+            col, dep = decoder.render_views(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (120, 160), bg, *params)
+            (col ** 2).mean().backward()
+            torch.cuda.synchronize()
+            allocs.append(torch.cuda.memory_stats()["num_device_alloc"])
+    finally:
+        gc.enable()
+    assert allocs[-1] == allocs[3], allocs

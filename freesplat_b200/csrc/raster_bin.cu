@@ -8,8 +8,12 @@
 //                              identifyTileRanges) and the total R, kept on the device;
 //   3. scatter_kernel        : every (Gaussian, tile) instance is appended to its tile's range
 //                              as key = depth_bits<<32 | gaussian_index (arbitrary order);
-//   4. tile_sort_kernel      : one CTA per tile sorts its range in SHARED MEMORY (bitonic
-//                              network, 64-bit keys; ranges above kSortSmemKeys sort in global).
+//   4. the render kernel     : the CTA that blends a tile first sorts that tile's range in SHARED MEMORY
+//                              (raster_sort.cuh: bitonic network, 64-bit keys; ranges above kSortSmemKeys sort in
+//                              global) and writes `point_list`: no separate sort launch, and the barrier-bound sort
+//                              of one tile overlaps the issue-bound blending of the other tiles resident on the SM.
+//   The scan kernel also emits a heaviest-first tile order (32 population buckets): long tiles start first,
+//   which trims the tail of the render launch.
 // Sorting by (depth_bits, gaussian_index) reproduces exactly the order of upstream's stable
 // radix sort on (tile<<32 | depth_bits) with values emitted in Gaussian order, so
 // `point_list` and `ranges` are bit-identical to the reference's (tests/test_raster_gpu.py).
@@ -20,17 +24,27 @@
 namespace fs {
 
 // ---- 2. scan over tile counters -------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ count, uint32_t* __restrict__ ranges,
+// `count` is consumed by the scan and then OVERWRITTEN with the tile processing order (heaviest bucket first).
+__device__ __forceinline__ int order_bucket(uint32_t c) { return 31 - (int)min(31u, c >> 6); }
+
+__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ count, uint32_t* __restrict__ ranges,
                                                          uint32_t* __restrict__ status, int n, long long capacity) {
   __shared__ unsigned long long warp_sums[32];
   __shared__ unsigned long long carry_s;
+  __shared__ uint32_t hist[32], bbase[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry_s = 0ull;
+  if (tid < 32) hist[tid] = 0u;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int k = base + tid;
-    const unsigned long long c = (k < n) ? (unsigned long long)count[k] : 0ull;
-    unsigned long long incl = c;
+  const unsigned long long cap = (unsigned long long)capacity;
+  // four consecutive counters per thread: 640x480 x 3 views (3600 tiles) is ONE pass of the block
+  for (int base = 0; base < n; base += 4096) {
+    const int k0 = base + 4 * tid;
+    uint32_t c[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) c[e] = (k0 + e < n) ? count[k0 + e] : 0u;
+    const unsigned long long s4 = (unsigned long long)c[0] + c[1] + c[2] + c[3];
+    unsigned long long incl = s4;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -50,24 +64,46 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
     __syncthreads();
     const unsigned long long carry = carry_s;
     const unsigned long long warp_excl = warp ? warp_sums[warp - 1] : 0ull;
-    const unsigned long long end = carry + warp_excl + incl;
-    if (k < n) {
-      // clamp so that a too-small workspace can never be overrun (the call reports overflow)
-      const unsigned long long cap = (unsigned long long)capacity;
-      const unsigned long long st = end - c;
-      ranges[2 * k] = (uint32_t)(st < cap ? st : cap);
-      ranges[2 * k + 1] = (uint32_t)(end < cap ? end : cap);
+    unsigned long long st = carry + warp_excl + incl - s4;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const unsigned long long end = st + c[e];
+      if (k0 + e < n) {
+        // clamp so that a too-small workspace can never be overrun (the call reports overflow)
+        ranges[2 * (k0 + e)] = (uint32_t)(st < cap ? st : cap);
+        ranges[2 * (k0 + e) + 1] = (uint32_t)(end < cap ? end : cap);
+        atomicAdd(&hist[order_bucket((uint32_t)((end < cap ? end : cap) - (st < cap ? st : cap)))], 1u);
+      }
+      st = end;
     }
     __syncthreads();
-    if (tid == 1023) carry_s = end;
+    if (tid == 1023) carry_s = st;
     __syncthreads();
   }
   if (tid == 0) {
     const unsigned long long R = carry_s;
     status[0] = (uint32_t)(R & 0xffffffffull);
     status[1] = (uint32_t)(R >> 32);
-    status[2] = (R > (unsigned long long)capacity || R > 0xffffffffull) ? 1u : 0u;
+    status[2] = (R > cap || R > 0xffffffffull) ? 1u : 0u;
     status[3] = 0u;
+  }
+  // ---- tile order: counting sort of the tiles by population bucket, heaviest first (order inside a bucket is
+  //      arbitrary: it only decides which CTA starts earlier).  `count` is dead by now and receives the order. ----
+  if (warp == 0) {
+    const uint32_t h = hist[lane];
+    uint32_t incl = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    bbase[lane] = incl - h;
+    hist[lane] = 0u;
+  }
+  __syncthreads();
+  for (int k = tid; k < n; k += 1024) {
+    const int b = order_bucket(ranges[2 * k + 1] - ranges[2 * k]);
+    count[bbase[b] + atomicAdd(&hist[b], 1u)] = (uint32_t)k;
   }
 }
 
@@ -112,119 +148,6 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(FsRasterFwdArgs a, in
   }
 }
 
-// ---- 4. per-tile sort -------------------------------------------------------------------------
-// Bitonic network with ascending comparators only (first step of every merge is the mirrored
-// "flip" step), so virtual +inf padding above n needs no storage.  Compare-exchange c of a stage
-// touches only the aligned 64-element region [64*(c/32), +64) whenever the stage's block size is
-// <= 64, and warp w always owns CEs {32w..32w+31} (+256m): such stages only need __syncwarp().
-// For N = 512 that leaves 9 block-wide barriers out of 45 stages.  All index math is shifts/masks.
-__device__ __forceinline__ void stage_sync(bool block_wide) {
-  if (block_wide) __syncthreads(); else __syncwarp();
-}
-
-template <typename KeyPtr>
-__device__ __forceinline__ void bitonic_sort_block(KeyPtr keys, int n, int tid) {
-  int logN = 0;
-  while ((1 << logN) < n) logN++;
-  const int halfN = (1 << logN) >> 1;
-  int prevB = 1 << 30;                                   // "previous stage" before the first one: block-wide
-  for (int lk = 1; lk <= logN; lk++) {
-    const int k = 1 << lk, half = k >> 1;
-    stage_sync(k > 64 || prevB > 64);
-    for (int c = tid; c < halfN; c += kThreads) {        // flip step
-      const int b = c >> (lk - 1), off = c & (half - 1);
-      const int i = (b << lk) + off, l = (b << lk) + (k - 1 - off);
-      if (l < n) {
-        const unsigned long long ki = keys[i], kl = keys[l];
-        if (ki > kl) { keys[i] = kl; keys[l] = ki; }
-      }
-    }
-    prevB = k;
-    for (int lj = lk - 2; lj >= 0; lj--) {
-      const int j = 1 << lj, B = j << 1;
-      stage_sync(B > 64 || prevB > 64);
-      for (int c = tid; c < halfN; c += kThreads) {
-        const int b = c >> lj, off = c & (j - 1);
-        const int i = (b << (lj + 1)) + off, l = i + j;
-        if (l < n) {
-          const unsigned long long ki = keys[i], kl = keys[l];
-          if (ki > kl) { keys[i] = kl; keys[l] = ki; }
-        }
-      }
-      prevB = B;
-    }
-  }
-  __syncthreads();
-}
-
-// Fully unrolled network for N = 2^LOGN <= 512 keys: one compare-exchange per thread and stage, all
-// shifts/masks compile-time constants (the generic loop spent ~64 instructions per stage, ncu r1b).
-template <int LOGN>
-__device__ __forceinline__ void bitonic_sort_fixed(unsigned long long* keys, int n, int tid) {
-  constexpr int HALF = (1 << LOGN) >> 1;
-  static_assert(HALF <= kThreads, "one compare-exchange per thread");
-  const bool has_ce = tid < HALF;
-  int prevB = 1 << 30;
-#pragma unroll
-  for (int lk = 1; lk <= LOGN; lk++) {
-    const int k = 1 << lk, half = k >> 1;
-    stage_sync(k > 64 || prevB > 64);
-    if (has_ce) {
-      const int b = tid >> (lk - 1), off = tid & (half - 1);
-      const int i = (b << lk) + off, l = (b << lk) + (k - 1 - off);
-      if (l < n) {
-        const unsigned long long ki = keys[i], kl = keys[l];
-        if (ki > kl) { keys[i] = kl; keys[l] = ki; }
-      }
-    }
-    prevB = k;
-#pragma unroll
-    for (int lj = lk - 2; lj >= 0; lj--) {
-      const int j = 1 << lj, B = j << 1;
-      stage_sync(B > 64 || prevB > 64);
-      if (has_ce) {
-        const int b = tid >> lj, off = tid & (j - 1);
-        const int i = (b << (lj + 1)) + off, l = i + j;
-        if (l < n) {
-          const unsigned long long ki = keys[i], kl = keys[l];
-          if (ki > kl) { keys[i] = kl; keys[l] = ki; }
-        }
-      }
-      prevB = B;
-    }
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(kThreads) tile_sort_kernel(const uint32_t* __restrict__ ranges, unsigned long long* __restrict__ keybuf,
-                                                             uint32_t* __restrict__ point_list, const uint32_t* __restrict__ status) {
-  if (status[2]) return;
-  extern __shared__ unsigned long long skeys[];
-  const int t = blockIdx.x;
-  const uint32_t start = ranges[2 * t], end = ranges[2 * t + 1];
-  const int n = (int)(end - start);
-  if (n <= 0) return;
-  const int tid = threadIdx.x;
-  unsigned long long* g = keybuf + start;
-  if (n <= kSortSmemKeys) {
-    for (int k = tid; k < n; k += kThreads) skeys[k] = g[k];
-    if (n <= 32) bitonic_sort_fixed<5>(skeys, n, tid);
-    else if (n <= 64) bitonic_sort_fixed<6>(skeys, n, tid);
-    else if (n <= 128) bitonic_sort_fixed<7>(skeys, n, tid);
-    else if (n <= 256) bitonic_sort_fixed<8>(skeys, n, tid);
-    else if (n <= 512) bitonic_sort_fixed<9>(skeys, n, tid);
-    else bitonic_sort_block(skeys, n, tid);
-    for (int k = tid; k < n; k += kThreads) {
-      const unsigned long long key = skeys[k];
-      g[k] = key;
-      point_list[start + k] = (uint32_t)(key & 0xffffffffull);
-    }
-  } else {
-    bitonic_sort_block(g, n, tid);             // rare: very crowded tile, sort in L2/HBM
-    for (int k = tid; k < n; k += kThreads) point_list[start + k] = (uint32_t)(g[k] & 0xffffffffull);
-  }
-}
-
 int launch_binning(const FsRasterFwdArgs& a, cudaStream_t s) {
   const int gx = tiles_x(a.W), gy = tiles_y(a.H);
   const int nt = a.V * gx * gy;
@@ -235,9 +158,6 @@ int launch_binning(const FsRasterFwdArgs& a, cudaStream_t s) {
     dim3 grid((a.P + kThreads - 1) / kThreads, a.V);
     scatter_kernel<<<grid, kThreads, 0, s>>>(a, gx, gy);
     if ((rc = check_cuda(cudaGetLastError(), "scatter_kernel"))) return rc;
-    tile_sort_kernel<<<nt, kThreads, kSortSmemKeys * 8, s>>>(a.ranges, reinterpret_cast<unsigned long long*>(a.keybuf),
-                                                              a.point_list, a.status);
-    if ((rc = check_cuda(cudaGetLastError(), "tile_sort_kernel"))) return rc;
   }
   return FS_OK;
 }

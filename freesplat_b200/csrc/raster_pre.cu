@@ -38,15 +38,19 @@ __global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs
     const int total = nblk * M3;
     // (g, c) = divmod(k, M3) maintained incrementally: a runtime integer division per element
     // was the single largest cost of this kernel (ncu r1a: IABS/IMAD/ISETP chains).
+    // The copies are asynchronous (cp.async, 4 bytes each: rows are 4*M3 bytes apart in HBM, sh_stride words apart in
+    // shared memory): they complete while the threads load and project their Gaussians; the wait sits right before
+    // the first colour evaluation (ncu r1g: the load->store dependency of the synchronous version was 15 % of all stalls).
     const int qstep = kThreads / M3, rstep = kThreads - qstep * M3;
     int g = tid / M3, c = tid - g * M3;
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_sh);
     for (int k = tid; k < total; k += kThreads) {
-      s_sh[g * sh_stride + c] = __ldg(src + k);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_base + (uint32_t)(g * sh_stride + c) * 4u), "l"(src + k) : "memory");
       g += qstep; c += rstep;
       if (c >= M3) { c -= M3; g++; }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  __syncthreads();
   const bool active = i < a.P;
   float m0 = 0.f, m1 = 0.f, m2 = 0.f, opacity = 0.f;
   float c6in[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -69,6 +73,8 @@ __global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs
       fsm::cov3d_from_scale_rot(sc, a.scale_modifier, q, c6in);
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();                                            // every thread's SH copies have landed
   for (int v = 0; v < a.V; v++) {
     const size_t vi = (size_t)v * a.P + i;
     const float* __restrict__ view = a.views + (size_t)v * kViewFloats;

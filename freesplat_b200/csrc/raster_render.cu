@@ -15,6 +15,7 @@
 //   t = fma(cb, dy, ca*dx) ; power = fma(cc*dy, dy, t*dx) ; alpha = min(.99, o*exp(power)).
 // exp() is MUFU.EX2 (ex2.approx.ftz) of power*log2(e): |rel err| < 1e-6.
 #include "common.cuh"
+#include "raster_sort.cuh"
 
 namespace fs {
 
@@ -56,14 +57,22 @@ struct __align__(16) RenderSmem {
   float2 B[kThreads];   // cc, opacity          (hot loop)
 };
 
+// The kernel first SORTS its tile: the tile's unsorted (depth_bits << 32 | gaussian) keys are pulled into
+// shared memory, sorted with the block-wide bitonic network and written back together with `point_list` (the backward
+// pass and the parity tests read both); the same shared memory is then reused for the blending batches.  Tiles are taken
+// in the heaviest-first order the scan kernel left in `order`.
+static_assert(sizeof(RenderSmem) <= (size_t)kSortSmemKeys * 8, "blend staging must fit in the sort buffer");
+
 __global__ void __launch_bounds__(kThreads) render_fwd_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
-    const float* __restrict__ views, const uint32_t* __restrict__ status, int P, int H, int W, int gx, int ntiles,
-    float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, unsigned long long* keybuf, uint32_t* point_list,
+    const float4* __restrict__ rec, const float* __restrict__ views, const uint32_t* __restrict__ status, int P, int H, int W,
+    int gx, int ntiles, float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
     uint32_t* __restrict__ n_contrib) {
   if (status[2]) return;
-  __shared__ RenderSmem sm;
-  const int tile = blockIdx.x, v = blockIdx.y;
+  extern __shared__ unsigned long long skeys[];
+  RenderSmem& sm = *reinterpret_cast<RenderSmem*>(skeys);
+  const int t_flat = (int)order[blockIdx.x];
+  const int v = t_flat / ntiles, tile = t_flat - v * ntiles;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = tile % gx, tile_y = tile / gx;
   const int x0 = tile_x * 16 + (warp & 1) * 8, y0 = tile_y * 16 + (warp >> 1) * 4;
@@ -71,8 +80,33 @@ __global__ void __launch_bounds__(kThreads) render_fwd_kernel(
   const bool inside = px < W && py < H;
   const float pxf = (float)px, pyf = (float)py;
   const float fx0 = (float)x0, fx1 = (float)(x0 + 7), fy0 = (float)y0, fy1 = (float)(y0 + 3);
-  const uint2 range = ranges[(size_t)v * ntiles + tile];
+  const uint2 range = ranges[t_flat];
   const float4* __restrict__ rec_v = rec + (size_t)v * P * 3;
+  // ---- sort this tile's keys by (depth bits, Gaussian index) ----
+  {
+    const int n = (int)(range.y - range.x);
+    if (n > 0) {
+      unsigned long long* g = keybuf + range.x;
+      if (n <= kSortSmemKeys) {
+        for (int k = tid; k < n; k += kThreads) skeys[k] = g[k];
+        if (n <= 32) bitonic_sort_fixed<5>(skeys, n, tid);
+        else if (n <= 64) bitonic_sort_fixed<6>(skeys, n, tid);
+        else if (n <= 128) bitonic_sort_fixed<7>(skeys, n, tid);
+        else if (n <= 256) bitonic_sort_fixed<8>(skeys, n, tid);
+        else if (n <= 512) bitonic_sort_fixed<9>(skeys, n, tid);
+        else bitonic_sort_block(skeys, n, tid);
+        for (int k = tid; k < n; k += kThreads) {
+          const unsigned long long key = skeys[k];
+          g[k] = key;
+          point_list[range.x + k] = (uint32_t)(key & 0xffffffffull);
+        }
+      } else {
+        bitonic_sort_block(g, n, tid);             // rare: very crowded tile, sort in L2/HBM
+        for (int k = tid; k < n; k += kThreads) point_list[range.x + k] = (uint32_t)(g[k] & 0xffffffffull);
+      }
+    }
+    __syncthreads();                               // point_list visible to the whole CTA; shared memory free for reuse
+  }
   const uint32_t aT = (uint32_t)__cvta_generic_to_shared(sm.T), aA = (uint32_t)__cvta_generic_to_shared(sm.A),
                  aC = (uint32_t)__cvta_generic_to_shared(sm.C), aB = (uint32_t)__cvta_generic_to_shared(sm.B);
 
@@ -318,10 +352,10 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
 
 int launch_render_fwd(const FsRasterFwdArgs& a, cudaStream_t s) {
   const int gx = tiles_x(a.W), gy = tiles_y(a.H);
-  dim3 grid(gx * gy, a.V);
-  render_fwd_kernel<<<grid, kThreads, 0, s>>>(reinterpret_cast<const uint2*>(a.ranges), a.point_list,
-                                               reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P, a.H, a.W, gx,
-                                               gx * gy, a.out_color, a.out_depth, a.final_T, a.n_contrib);
+  render_fwd_kernel<<<gx * gy * a.V, kThreads, kSortSmemKeys * 8, s>>>(
+      reinterpret_cast<const uint2*>(a.ranges), a.tile_count /* holds the tile order after binning */,
+      reinterpret_cast<unsigned long long*>(a.keybuf), a.point_list, reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P,
+      a.H, a.W, gx, gx * gy, a.out_color, a.out_depth, a.final_T, a.n_contrib);
   return check_cuda(cudaGetLastError(), "render_fwd_kernel");
 }
 

@@ -98,7 +98,7 @@ typedef struct FsRasterFwdArgs {
                             (backward recomputes it; only the parity tests ask for it) */
   uint32_t* tiles_touched; /* [V,P] or NULL (parity tests only)                  */
   uint8_t* clamped;      /* [V,P] bit c set <=> SH colour channel c clamped at 0 */
-  uint32_t* tile_count;  /* [V*tiles]   scratch (zeroed by the call)             */
+  uint32_t* tile_count;  /* [V*tiles]   scratch (zeroed by the call; after binning: the heaviest-first tile order) */
   uint32_t* tile_cursor; /* [V*tiles]   scratch (zeroed by the call)             */
   uint32_t* ranges;      /* [V*tiles,2] absolute [start,end) into point_list     */
   uint64_t* keybuf;      /* [capacity]  (depth_bits<<32 | gaussian) per instance,
@@ -108,8 +108,8 @@ typedef struct FsRasterFwdArgs {
 } FsRasterFwdArgs;
 
 #define FS_STAGE_PREPROCESS 1  /* per-Gaussian projection + tile counting            */
-#define FS_STAGE_BINNING 2     /* tile scan, scatter, per-tile sort                  */
-#define FS_STAGE_RENDER 4      /* per-tile alpha blend                               */
+#define FS_STAGE_BINNING 2     /* tile scan (+ tile order), scatter                  */
+#define FS_STAGE_RENDER 4      /* per-tile depth sort + alpha blend (one kernel)     */
 
 typedef struct FsRasterBwdArgs {
   int32_t P, V, H, W, sh_degree, M;

@@ -340,12 +340,16 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
     if (tid < n) {
       const float* accp = sAcc + tid * kAccStride;
       float* dst = dL_dscreen + ((size_t)v * P + sId[tid]) * 12;
-      // layout: mean2D.x, mean2D.y, conic.x, conic.y | conic.w, opacity, r, g | b, depth
-#pragma unroll
-      for (int k = 0; k < (kDepthGrad ? 10 : 9); k++) {
-        const float val = accp[k];
-        if (val != 0.f) atomicAdd(dst + k, val);
-      }
+      // layout: mean2D.x, mean2D.y, conic.x, conic.y | conic.w, opacity, r, g | b, depth -- three 16-byte groups, flushed
+      // with VECTOR reductions (red.global.add.v4/.v2.f32): 3 L2 atomic operations per (tile, instance) instead of 9-10
+      const float a0 = accp[0], a1 = accp[1], a2 = accp[2], a3 = accp[3], a4 = accp[4], a5 = accp[5], a6 = accp[6], a7 = accp[7];
+      const float a8 = accp[8], a9 = kDepthGrad ? accp[9] : 0.f;
+      if (a0 != 0.f || a1 != 0.f || a2 != 0.f || a3 != 0.f)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+      if (a4 != 0.f || a5 != 0.f || a6 != 0.f || a7 != 0.f)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(a4), "f"(a5), "f"(a6), "f"(a7) : "memory");
+      if (a8 != 0.f || a9 != 0.f)
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 8), "f"(a8), "f"(a9) : "memory");
     }
   }
 }

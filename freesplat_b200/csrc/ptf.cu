@@ -534,12 +534,15 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
     if (uses[buf] > 0) { mbar_wait(bar_free[buf], ph_free[buf]); ph_free[buf] ^= 1u; }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
+  // B rounds travel global -> shared with cp.async (16 bytes, L2 only): the copy is issued BEFORE the threads build the A
+  // round and completes underneath it (ncu r1f: the synchronous LDG -> STS copy was the long-scoreboard stall of this kernel)
   auto copy_b = [&](int buf, const unsigned char* src, int bytes) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(src);
-    uint4* d4 = reinterpret_cast<uint4*>(sm.B[buf]);
-    for (int k = tid; k < bytes / 16; k += 128) d4[k] = __ldg(s4 + k);
+    const uint32_t d0 = smem_u32(sm.B[buf]);
+    for (int k = tid; k < bytes / 16; k += 128)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)k * 16u), "l"(src + (size_t)k * 16) : "memory");
   };
   auto publish = [&]() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -565,6 +568,7 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
   for (int r = 0; r < kR1; r++, round_no++) {
     const int buf = round_no & 1;
     begin_round(buf);
+    copy_b(buf, W + kOffL1 + (size_t)r * 2 * bTile(128), 2 * bTile(128));
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const int c = r * kRound + 4 * q;
@@ -573,7 +577,6 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
       for (int e = 0; e < 4; e++) v[e] = a1_col(c + e);
       store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, v[0], v[1], v[2], v[3]);
     }
-    copy_b(buf, W + kOffL1 + (size_t)r * 2 * bTile(128), 2 * bTile(128));
     publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -597,6 +600,16 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
   for (int r = 0; r < kR2; r++, round_no++) {
     const int buf = round_no & 1;
     begin_round(buf);
+    {   // B: r round (hi|lo, 64 rows) then z round
+      const unsigned char* s1 = W + kOffL2r + (size_t)r * 2 * bTile(64);
+      const unsigned char* s2 = W + kOffL2z + (size_t)r * 2 * bTile(64);
+      const uint32_t d0 = smem_u32(sm.B[buf]);
+      const int n16 = 2 * bTile(64) / 16;
+      for (int k = tid; k < n16; k += 128) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)k * 16u), "l"(s1 + (size_t)k * 16) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)(n16 + k) * 16u), "l"(s2 + (size_t)k * 16) : "memory");
+      }
+    }
     float hr[16], hz[16];
     tmem_ld16(t_row + (uint32_t)(r * kRound), hr);
     tmem_ld16(t_row + (uint32_t)(64 + r * kRound), hz);
@@ -610,13 +623,6 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
       }
       store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, a[0], a[1], a[2], a[3]);
       store_a4(sm.Az[buf][0], sm.Az[buf][1], tid, 4 * q, b[0], b[1], b[2], b[3]);
-    }
-    {   // B: r round (hi|lo, 64 rows) then z round
-      const uint4* s1 = reinterpret_cast<const uint4*>(W + kOffL2r + (size_t)r * 2 * bTile(64));
-      const uint4* s2 = reinterpret_cast<const uint4*>(W + kOffL2z + (size_t)r * 2 * bTile(64));
-      uint4* d4 = reinterpret_cast<uint4*>(sm.B[buf]);
-      const int n16 = 2 * bTile(64) / 16;
-      for (int k = tid; k < n16; k += 128) { d4[k] = __ldg(s1 + k); d4[n16 + k] = __ldg(s2 + k); }
     }
     publish();
     if (tid == 0) {
@@ -646,6 +652,7 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
   for (int r = 0; r < kR3; r++, round_no++) {
     const int buf = round_no & 1;
     begin_round(buf);
+    copy_b(buf, W + kOffL3 + (size_t)r * 2 * bTile(64), 2 * bTile(64));
     float rg[16];
     if (r < kR2) tmem_ld16(t_row + (uint32_t)(128 + r * kRound), rg);
 #pragma unroll
@@ -661,7 +668,6 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
       }
       store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, v[0], v[1], v[2], v[3]);
     }
-    copy_b(buf, W + kOffL3 + (size_t)r * 2 * bTile(64), 2 * bTile(64));
     publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -685,6 +691,7 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
   for (int r = 0; r < kR4; r++, round_no++) {
     const int buf = round_no & 1;
     begin_round(buf);
+    copy_b(buf, W + kOffL4 + (size_t)r * 2 * bTile(64), 2 * bTile(64));
     float hn[16];
     tmem_ld16(t_row + (uint32_t)(r * kRound), hn);
 #pragma unroll
@@ -692,7 +699,6 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
       store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, fmaxf(hn[4 * q] + sm.b_n0[r * kRound + 4 * q], 0.f),
                fmaxf(hn[4 * q + 1] + sm.b_n0[r * kRound + 4 * q + 1], 0.f), fmaxf(hn[4 * q + 2] + sm.b_n0[r * kRound + 4 * q + 2], 0.f),
                fmaxf(hn[4 * q + 3] + sm.b_n0[r * kRound + 4 * q + 3], 0.f));
-    copy_b(buf, W + kOffL4 + (size_t)r * 2 * bTile(64), 2 * bTile(64));
     publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

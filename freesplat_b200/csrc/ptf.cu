@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(kPtfThreads) ptf_compact_kernel(FsPtfArgs a) {
   const int N = a.counts_in[0], HW = a.H * a.W, F = a.F;
   const int n_keep = a.counts_out[1], n_match = a.counts_out[2];
   const int base = blockIdx.x * kPtfItems;
+  if (base >= max(N, HW)) return;            // the grid is sized by an upper bound of N (no host read of the counters)
   const int off_keep = a.block_counts[3 * (size_t)blockIdx.x + 0];
   const int off_mat = a.block_counts[3 * (size_t)blockIdx.x + 1];
   const int off_app = a.block_counts[3 * (size_t)blockIdx.x + 2];
@@ -486,7 +487,7 @@ __device__ __forceinline__ void store_a4(unsigned char* hi, unsigned char* lo, i
 }
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __restrict__ pair_j, const int* __restrict__ pair_p,
+__global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* __restrict__ M_dev, const int* __restrict__ pair_j, const int* __restrict__ pair_p,
                                                          const float* __restrict__ feats, const float* __restrict__ dens,
                                                          const float* __restrict__ wemb, const float* __restrict__ v_feats,
                                                          const float* __restrict__ v_dens, const float* __restrict__ v_wemb,
@@ -495,6 +496,8 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
   extern __shared__ __align__(128) unsigned char gru_smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(gru_smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int M = M_dev ? min(*M_dev, M_host) : M_host;        // M_host is only the grid's upper bound when M_dev is given
+  if ((int)blockIdx.x * 128 >= M) return;                  // CTA-uniform, before any barrier / TMEM allocation
   const int m = blockIdx.x * 128 + tid;
   const bool active = m < M;
   if (tid < kF) { sm.b_r0[tid] = biases[tid]; sm.b_z0[tid] = biases[64 + tid]; sm.b_r2[tid] = biases[128 + tid]; sm.b_z2[tid] = biases[192 + tid];
@@ -748,12 +751,14 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M, const int* __res
 int launch_ptf_gru_tc(const FsPtfGruArgs& a, cudaStream_t s) {
   if (a.M <= 0) return FS_OK;
   int rc;
-  gru::ptf_gru_prep_kernel<<<(128 * gru::kK1 + 255) / 256, 256, 0, s>>>(a.W_r0, a.W_z0, a.W_r2, a.W_z2, a.W_n0, a.W_n2, a.wscratch);
-  if ((rc = check_cuda(cudaGetLastError(), "ptf_gru_prep_kernel"))) return rc;
+  if (!(a.flags & 1)) {
+    gru::ptf_gru_prep_kernel<<<(128 * gru::kK1 + 255) / 256, 256, 0, s>>>(a.W_r0, a.W_z0, a.W_r2, a.W_z2, a.W_n0, a.W_n2, a.wscratch);
+    if ((rc = check_cuda(cudaGetLastError(), "ptf_gru_prep_kernel"))) return rc;
+  }
   const size_t smem = sizeof(gru::Smem) + 128;
   if ((rc = check_cuda(cudaFuncSetAttribute(gru::ptf_gru_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "cudaFuncSetAttribute(ptf_gru_tc_kernel)"))) return rc;
-  gru::ptf_gru_tc_kernel<<<(a.M + 127) / 128, 128, smem, s>>>(a.M, a.pair_j, a.pair_p, a.feats, a.dens, a.wemb, a.v_feats, a.v_dens, a.v_wemb,
+  gru::ptf_gru_tc_kernel<<<(a.M + 127) / 128, 128, smem, s>>>(a.M, a.M_dev, a.pair_j, a.pair_p, a.feats, a.dens, a.wemb, a.v_feats, a.v_dens, a.v_wemb,
                                                             a.wscratch, a.biases, a.out);
   return check_cuda(cudaGetLastError(), "ptf_gru_tc_kernel");
 }

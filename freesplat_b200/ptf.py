@@ -66,15 +66,17 @@ def _gru_has_reference_structure(gru) -> bool:
 
 
 class FsPtfGruArgs(C.Structure):
-    _fields_ = [("M", C.c_int32), ("pair_j", C.c_void_p), ("pair_p", C.c_void_p),
+    _fields_ = [("M", C.c_int32), ("flags", C.c_int32), ("pair_j", C.c_void_p), ("pair_p", C.c_void_p),
                 ("feats", C.c_void_p), ("dens", C.c_void_p), ("wemb", C.c_void_p),
                 ("v_feats", C.c_void_p), ("v_dens", C.c_void_p), ("v_wemb", C.c_void_p),
                 ("W_r0", C.c_void_p), ("W_z0", C.c_void_p), ("W_r2", C.c_void_p), ("W_z2", C.c_void_p), ("W_n0", C.c_void_p),
-                ("W_n2", C.c_void_p), ("biases", C.c_void_p), ("wscratch", C.c_void_p), ("out", C.c_void_p)]
+                ("W_n2", C.c_void_p), ("biases", C.c_void_p), ("wscratch", C.c_void_p), ("out", C.c_void_p), ("M_dev", C.c_void_p)]
 
 
 # "tc": the whole GRU on the tensor cores (fs_ptf_gru, 3xTF32) ; "cublas": glue kernels + nn.Linear GEMMs
 GRU_MODE = os.environ.get("FREESPLAT_B200_PTF_GRU", "tc")
+# 1: the inference fold never reads a counter back until the end (grids sized by upper bounds); 0: one host read per step
+SYNC_FREE = os.environ.get("FREESPLAT_B200_PTF_SYNC_FREE", "1") == "1"
 
 
 def _gru_tc_ok(gru, F) -> bool:
@@ -86,24 +88,39 @@ def _gru_tc_ok(gru, F) -> bool:
         return False
 
 
+class _GruTc:
+    """GRU.forward (networks.py:201-214) for the matched pairs in ONE kernel on the tensor cores (fs_ptf_gru).  The weights
+    are split / tiled into `wscratch` by the first call and reused by the following fold steps; with `M_dev` the pair count
+    stays on the device (M is then only the upper bound that sizes the grid)."""
+
+    def __init__(self, gru, dev):
+        L = _lib.lib()
+        w = lambda t: t.detach().float().contiguous()
+        self.Ws = [w(gru.mlp_r[0].weight), w(gru.mlp_z[0].weight), w(gru.mlp_r[2].weight), w(gru.mlp_z[2].weight),
+                   w(gru.mlp_n[0].weight), w(gru.mlp_n[2].weight)]
+        self.biases = torch.cat([w(gru.mlp_r[0].bias), w(gru.mlp_z[0].bias), w(gru.mlp_r[2].bias), w(gru.mlp_z[2].bias),
+                                 w(gru.mlp_n[0].bias), w(gru.mlp_n[2].bias)]).contiguous()
+        L.fs_ptf_gru_wscratch_bytes.restype = C.c_int64
+        self.scratch = torch.empty(int(L.fs_ptf_gru_wscratch_bytes()), dtype=torch.uint8, device=dev)
+        self.prepared = False
+        self.dev = dev
+
+    def __call__(self, M, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream, out=None, M_dev=None):
+        L = _lib.lib()
+        Ws = self.Ws
+        if out is None:
+            out = torch.empty((M, 64), dtype=torch.float32, device=self.dev)
+        a = FsPtfGruArgs(M=M, flags=int(self.prepared), pair_j=ptr(pair_j), pair_p=ptr(pair_p), feats=ptr(state[0]), dens=ptr(state[2]),
+                         wemb=ptr(state[3]), v_feats=ptr(view_feats), v_dens=ptr(view_dens), v_wemb=ptr(view_wemb),
+                         W_r0=ptr(Ws[0]), W_z0=ptr(Ws[1]), W_r2=ptr(Ws[2]), W_z2=ptr(Ws[3]), W_n0=ptr(Ws[4]), W_n2=ptr(Ws[5]),
+                         biases=ptr(self.biases), wscratch=ptr(self.scratch), out=ptr(out), M_dev=ptr(M_dev))
+        check(L.fs_ptf_gru(C.byref(a), C.c_void_p(stream)), "fs_ptf_gru")
+        self.prepared = True
+        return out
+
+
 def _gru_fused_tc(gru, M, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream):
-    """GRU.forward (networks.py:201-214) for the matched pairs in ONE kernel on the tensor cores (fs_ptf_gru)."""
-    L = _lib.lib()
-    dev = state[0].device
-    w = lambda t: t.detach().float().contiguous()
-    Ws = [w(gru.mlp_r[0].weight), w(gru.mlp_z[0].weight), w(gru.mlp_r[2].weight), w(gru.mlp_z[2].weight),
-          w(gru.mlp_n[0].weight), w(gru.mlp_n[2].weight)]
-    biases = torch.cat([w(gru.mlp_r[0].bias), w(gru.mlp_z[0].bias), w(gru.mlp_r[2].bias), w(gru.mlp_z[2].bias),
-                        w(gru.mlp_n[0].bias), w(gru.mlp_n[2].bias)]).contiguous()
-    L.fs_ptf_gru_wscratch_bytes.restype = C.c_int64
-    scratch = torch.empty(int(L.fs_ptf_gru_wscratch_bytes()), dtype=torch.uint8, device=dev)
-    out = torch.empty((M, 64), dtype=torch.float32, device=dev)
-    a = FsPtfGruArgs(M=M, pair_j=ptr(pair_j), pair_p=ptr(pair_p), feats=ptr(state[0]), dens=ptr(state[2]), wemb=ptr(state[3]),
-                     v_feats=ptr(view_feats), v_dens=ptr(view_dens), v_wemb=ptr(view_wemb),
-                     W_r0=ptr(Ws[0]), W_z0=ptr(Ws[1]), W_r2=ptr(Ws[2]), W_z2=ptr(Ws[3]), W_n0=ptr(Ws[4]), W_n2=ptr(Ws[5]),
-                     biases=ptr(biases), wscratch=ptr(scratch), out=ptr(out))
-    check(L.fs_ptf_gru(C.byref(a), C.c_void_p(stream)), "fs_ptf_gru")
-    return out
+    return _GruTc(gru, state[0].device)(M, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream)
 
 
 def _gru_fused(gru, M, F, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream):
@@ -257,6 +274,27 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
         state = (cur.feats, cur.coords, cur.dens, cur.wemb, cur.ext, cur.depth)
     N = HW
     debug = []
+    use_tc = fused_gru and GRU_MODE == "tc" and _gru_tc_ok(gru, F)
+    gru_tc = _GruTc(gru, dev) if use_tc else None
+    # inference with the tensor-core GRU: the whole fold is enqueued without reading a counter back (grids are sized by
+    # upper bounds, the kernels take N / M from the device counters); ONE host read at the end returns the final size
+    sync_free = use_tc and (not need_grad) and timings is None and not return_debug and SYNC_FREE
+    if sync_free:
+        gru_buf = torch.empty((HW, F), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            for i in range(1, V):
+                cin = counts[i - 1, 4:5]
+                view = (feats[i], coords[i], dens[i], wemb[i], depths[i], ext16[i], E_inv[i], K_px[i])
+                out_bufs = (nxt.feats, nxt.coords, nxt.dens, nxt.wemb, nxt.ext, nxt.depth)
+                a = _ptf_args(h, w, F, min(cap, i * HW), depth_thres, state, cin, view, scratch, counts[i], out_bufs)
+                check(L.fs_ptf_match(C.byref(a), C.c_void_p(stream)), "fs_ptf_match")
+                gru_tc(HW, pair_j, pair_p, state, feats[i], dens[i], wemb[i], stream, out=gru_buf, M_dev=counts[i, 2:3])
+                a.gru_out = ptr(gru_buf)
+                check(L.fs_ptf_merge(C.byref(a), C.c_void_p(stream)), "fs_ptf_merge")
+                cur, nxt = nxt, cur
+                state = (cur.feats, cur.coords, cur.dens, cur.wemb, cur.ext, cur.depth)
+        N = int(counts[V - 1, 4]) if V > 1 else HW
+        return (state[0][:N], state[1][:N], state[4][:N].reshape(N, 4, 4), state[5][:N])
     with torch.cuda.device(dev):
         for i in range(1, V):
             cin = counts[i - 1, 4:5]                      # N of the current state, on the device
@@ -274,8 +312,8 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
                 ev[1].record()
             M, N_out = c[2], c[4]
             gru_out = None
-            if M > 0 and fused_gru and GRU_MODE == "tc" and _gru_tc_ok(gru, F):
-                gru_out = _gru_fused_tc(gru, M, pair_j, pair_p, det, feats[i], dens[i], wemb[i], stream)
+            if M > 0 and use_tc:
+                gru_out = gru_tc(M, pair_j, pair_p, det, feats[i], dens[i], wemb[i], stream)
             elif M > 0 and fused_gru:
                 gru_out = _gru_fused(gru, M, F, pair_j, pair_p, det, feats[i], dens[i], wemb[i], stream)
             elif M > 0:

@@ -231,7 +231,8 @@ int fs_ptf_gru_output(int32_t M, int32_t F, const float* A1, const float* z_lin,
  * mlp_n[0] [64,152], mlp_n[2] [64,64]; biases = [b_r0 | b_z0 | b_r2 | b_z2 | b_n0 | b_n2] (6 x 64);
  * wscratch: fs_ptf_gru_wscratch_bytes() bytes of device scratch (tf32-split, pre-tiled weights).                */
 typedef struct FsPtfGruArgs {
-  int32_t M;
+  int32_t M;                      /* number of pairs, or an UPPER BOUND of it when M_dev is given (sizes the grid)            */
+  int32_t flags;                  /* bit 0: wscratch already holds the prepared weights (skip the preparation kernel)       */
   const int32_t* pair_j; const int32_t* pair_p;
   const float* feats; const float* dens; const float* wemb;          /* global state  */
   const float* v_feats; const float* v_dens; const float* v_wemb;    /* view i        */
@@ -239,6 +240,7 @@ typedef struct FsPtfGruArgs {
   const float* biases;
   unsigned char* wscratch;
   float* out;                                                         /* [M,64]        */
+  const int32_t* M_dev;           /* optional: the pair count on the DEVICE (fs_ptf_match's counts_out[2]): no host read   */
 } FsPtfGruArgs;
 int fs_ptf_gru(const FsPtfGruArgs* args, void* stream);
 int64_t fs_ptf_gru_wscratch_bytes(void);

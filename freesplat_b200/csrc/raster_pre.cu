@@ -19,15 +19,13 @@ namespace fs {
 //   float sh[256 * sh_stride]   SH rows of the block's 256 Gaussians, staged with coalesced loads
 //                               (a per-thread walk over a 108-byte-strided row costs 27 L1 wavefronts
 //                               per load instruction); sh_stride is odd => conflict-free reads.
-//   float4 out[256 * 3]         records of one view, written back as contiguous 16-byte chunks.
 // Each thread projects ITS Gaussian into all V views: the 148 input bytes are read once, not V times.
 // DEG = active SH degree (compile time: the 3*(DEG+1)^2 coefficient loads become straight-line shared-memory
 // reads with immediate offsets; the generic loop cost ~300 instructions of predicates / address math per view).
 template <int DEG>
 __global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy, int sh_stride) {
   extern __shared__ float4 smem4[];
-  float4* s_out = smem4;                                   // [256*3]
-  float* s_sh = reinterpret_cast<float*>(smem4 + kThreads * 3);
+  float* s_sh = reinterpret_cast<float*>(smem4);
   const int tid = threadIdx.x;
   const int block_base = blockIdx.x * kThreads;
   const int i = block_base + tid;
@@ -143,12 +141,13 @@ __global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs
         if (++tx == rx0 + rw) { tx = rx0; ty++; }
       }
     }
-    // records: through shared memory so that the block writes contiguous 16-byte chunks
-    s_out[tid * 3 + 0] = r0; s_out[tid * 3 + 1] = r1; s_out[tid * 3 + 2] = r2;
-    __syncthreads();
-    float4* __restrict__ dst = reinterpret_cast<float4*>(a.rec) + 3 * ((size_t)v * a.P + block_base);
-    for (int k = tid; k < nblk * 3; k += kThreads) dst[k] = s_out[k];
-    __syncthreads();
+    // records: three 16-byte stores per thread (48-byte stride across the warp; the L2 merges the partial sectors).
+    // Staging them through shared memory for fully coalesced stores cost two block barriers per view and was slower
+    // (51.0 -> 46.4 us, measured).
+    if (active) {
+      float4* __restrict__ dst = reinterpret_cast<float4*>(a.rec) + 3 * vi;
+      dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    }
   }
 }
 
@@ -497,11 +496,15 @@ int launch_preprocess(const FsRasterFwdArgs& a, cudaStream_t s) {
   const int gx = tiles_x(a.W), gy = tiles_y(a.H);
   const size_t nt = (size_t)a.V * gx * gy;
   int rc;
-  if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, nt * 4, s), "memset tile_count"))) return rc;
-  if ((rc = check_cuda(cudaMemsetAsync(a.tile_cursor, 0, nt * 4, s), "memset tile_cursor"))) return rc;
+  if (a.tile_cursor == a.tile_count + nt) {          // adjacent scratch (the Python wrapper allocates it that way): one memset
+    if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, 2 * nt * 4, s), "memset tile counters"))) return rc;
+  } else {
+    if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, nt * 4, s), "memset tile_count"))) return rc;
+    if ((rc = check_cuda(cudaMemsetAsync(a.tile_cursor, 0, nt * 4, s), "memset tile_cursor"))) return rc;
+  }
   if (a.P > 0) {
     const int sh_stride = (a.M * 3) | 1;
-    const size_t smem = (size_t)kThreads * 3 * sizeof(float4) + (a.shs ? (size_t)kThreads * sh_stride * sizeof(float) : 0);
+    const size_t smem = a.shs ? (size_t)kThreads * sh_stride * sizeof(float) : 0;
     void (*kern)(FsRasterFwdArgs, int, int, int) =
         a.sh_degree == 0 ? preprocess_kernel<0> : a.sh_degree == 1 ? preprocess_kernel<1> : a.sh_degree == 2 ? preprocess_kernel<2> : preprocess_kernel<3>;
     if (smem > 48 * 1024) {

@@ -143,7 +143,8 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
             # only the parity tests ask for these (the hot path neither writes nor reads them)
             st.cov3D = e(V, P, 6) if debug_buffers else None
             st.tiles_touched = e(V, P, dtype=torch.int32) if debug_buffers else None
-            tile_count = e(nt, dtype=torch.int32); tile_cursor = e(nt, dtype=torch.int32)
+            tile_buf = e(2 * nt, dtype=torch.int32)          # [counters | cursors]: adjacent, zeroed by ONE memset in the call
+            tile_count, tile_cursor = tile_buf[:nt], tile_buf[nt:]
             st.ranges = e(nt, 2, dtype=torch.int32)
             st.keybuf = e(max(capacity, 1), dtype=torch.int64)
             st.point_list = e(max(capacity, 1), dtype=torch.int32)

@@ -11,7 +11,8 @@
 //   * depth_head_up_kernel: CTA = 32x4 coarse pixels (+1 halo row / column).  The [D][5][36] logit tile is staged
 //     in shared memory by TMA box loads (cp.async.bulk.tensor.3d, one mbarrier per 32-plane chunk; out-of-image
 //     elements are zero-filled by the hardware), normalised in place (two sweeps per pixel), and every coarse cell
-//     then produces its ~2x2 output pixels straight from the tile: 4 shared loads + 16 FMA + 4 max per plane.
+//     then produces its ~2x2 output pixels straight from the tile: per PAIR of planes 8 shared loads, 16 packed
+//     FFMA2 / FMUL2 (fma.rn.f32x2) and 4 three-input maxima (FMNMX3).
 //     256 threads = 128 cells x 2 halves of the plane range; 2 CTAs per SM (93 KB each) overlap load and math.
 //   * depth_head_expect_kernel: scales 1..3 (no upsampling): thread per pixel, online softmax, coalesced.
 // Algorithmic HBM bytes: 4*D*h*w read + (2 + 8) * 4*h*w written per view.
@@ -55,6 +56,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra DH_WAIT;\n\t"
       "DH_DONE:\n\t"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// Blackwell packed fp32 pairs (FFMA2 / FMUL2) and the 3-input maximum (FMNMX3): phase 2 evaluates two planes per instruction
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, unsigned long long v) {
+  float lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(lo), "f"(hi));
+  return r;
 }
 
 // source index / interpolation weight of output index o (aten rule, align_corners=True)
@@ -117,26 +141,33 @@ __global__ void __launch_bounds__(kThreads, 2) depth_head_up_kernel(const __grid
       if (kTma) mbar_wait(smem_u32(&sm.bar[c]), 0u);
       if (mine) {
         const int dend = min(D, (c + 1) * kChunkD);
+        const float* q = tp + c * kChunkD * kPlane;
         int d = c * kChunkD;
 #pragma unroll 4
-        for (; d + 2 <= dend; d += 2) { m0 = fmaxf(m0, tp[d * kPlane]); m1 = fmaxf(m1, tp[(d + 1) * kPlane]); }
-        if (d < dend) m0 = fmaxf(m0, tp[d * kPlane]);
+        for (; d + 2 <= dend; d += 2, q += 2 * kPlane) { m0 = fmaxf(m0, q[0]); m1 = fmaxf(m1, q[kPlane]); }
+        if (d < dend) m0 = fmaxf(m0, q[0]);
       }
     }
     if (mine) {
-      const float m = fmaxf(m0, m1);
+      // e = exp(l - m) as ex2(l*log2e - m*log2e): one FFMA + one MUFU.EX2 per plane (|rel err| < 1e-6, inside the 1e-4 budget)
+      constexpr float kLog2e = 1.4426950408889634f;
+      const float m = fmaxf(m0, m1), mb = -m * kLog2e;
       float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
+      float* q = tp;
       int d = 0;
 #pragma unroll 4
-      for (; d + 2 <= D; d += 2) {
-        const float e0 = __expf(tp[d * kPlane] - m), e1 = __expf(tp[(d + 1) * kPlane] - m);
+      for (; d + 2 <= D; d += 2, q += 2 * kPlane) {
+        float e0, e1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(q[0], kLog2e, mb)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(q[kPlane], kLog2e, mb)));
         s0 += e0; s1 += e1;
         a0 = fmaf(sm.candi[d], e0, a0); a1 = fmaf(sm.candi[d + 1], e1, a1);
-        tp[d * kPlane] = e0; tp[(d + 1) * kPlane] = e1;
+        q[0] = e0; q[kPlane] = e1;
       }
       if (d < D) {
-        const float e0 = __expf(tp[d * kPlane] - m);
-        s0 += e0; a0 = fmaf(sm.candi[d], e0, a0); tp[d * kPlane] = e0;
+        float e0;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(q[0], kLog2e, mb)));
+        s0 += e0; a0 = fmaf(sm.candi[d], e0, a0); q[0] = e0;
       }
       const float s = s0 + s1, acc = a0 + a1;
       const float rs = 1.0f / s, E = acc * rs;
@@ -185,8 +216,23 @@ __global__ void __launch_bounds__(kThreads, 2) depth_head_up_kernel(const __grid
         wgt[p][0] = wy0 * wx0 * r00; wgt[p][1] = wy0 * wx1 * r01; wgt[p][2] = wy1 * wx0 * r10; wgt[p][3] = wy1 * wx1 * r11;
       }
       const float* tp = sm.tile;
-#pragma unroll 4
-      for (int d = dbeg; d < dend; d++) {
+      unsigned long long wq[4][4];                        // tap weights duplicated into both halves of a pair
+#pragma unroll
+      for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int t = 0; t < 4; t++) wq[p][t] = pack2(wgt[p][t], wgt[p][t]);
+      int d = dbeg;
+#pragma unroll 2
+      for (; d + 2 <= dend; d += 2) {                     // planes d and d+1 per packed instruction
+        const unsigned long long e00 = pack2(tp[d * kPlane + i00], tp[(d + 1) * kPlane + i00]);
+        const unsigned long long e01 = pack2(tp[d * kPlane + i01], tp[(d + 1) * kPlane + i01]);
+        const unsigned long long e10 = pack2(tp[d * kPlane + i10], tp[(d + 1) * kPlane + i10]);
+        const unsigned long long e11 = pack2(tp[d * kPlane + i11], tp[(d + 1) * kPlane + i11]);
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+          mx[p] = max3(mx[p], fma2(wq[p][3], e11, fma2(wq[p][2], e10, fma2(wq[p][1], e01, mul2(wq[p][0], e00)))));
+      }
+      for (; d < dend; d++) {
         const float e00 = tp[d * kPlane + i00], e01 = tp[d * kPlane + i01], e10 = tp[d * kPlane + i10], e11 = tp[d * kPlane + i11];
 #pragma unroll
         for (int p = 0; p < 4; p++)

@@ -35,23 +35,36 @@ def owner_of(view: int, world: int) -> int:
 
 def all_gather_views(local: torch.Tensor, num_views: int, group=None) -> torch.Tensor:
     """local: [n_local, ...] holding this rank's views (in increasing global view index).
-    Returns [num_views, ...] in global view order on every rank.  Ranks may own different counts."""
+    Returns [num_views, ...] in global view order on every rank.  Ranks may own different counts.
+    ONE collective into one flat buffer (all_gather_into_tensor: NCCL's native all-gather, no per-rank staging copies)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     counts = [len(shard_views(num_views, r, world)) for r in range(world)]
     assert local.shape[0] == counts[rank], (local.shape, counts, rank)
     mx = max(counts)
-    pad = local
+    pad = local.contiguous()
     if local.shape[0] < mx:
-        pad = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))], 0)
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad.contiguous(), group=group)
-    out = local.new_empty((num_views,) + tuple(local.shape[1:]))
-    for r in range(world):
-        idx = shard_views(num_views, r, world)
-        if idx:
-            out[torch.tensor(idx, device=out.device)] = bufs[r][: len(idx)]
-    return out
+        pad = torch.cat([pad, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))], 0)
+    flat = local.new_empty((world * mx,) + tuple(local.shape[1:]))
+    try:
+        dist.all_gather_into_tensor(flat, pad, group=group)
+    except (RuntimeError, NotImplementedError):          # backends without the flat variant
+        bufs = list(flat.view((world, mx) + tuple(local.shape[1:])).unbind(0))
+        dist.all_gather(bufs, pad, group=group)
+    # rank r's slot k holds global view r + k*world  ->  global view v sits at flat[(v % world) * mx + v // world]
+    src = torch.tensor([(v % world) * mx + v // world for v in range(num_views)], dtype=torch.long, device=flat.device)
+    return flat.index_select(0, src)
+
+
+def all_gather_candidates(feats, coords, dens, wemb, depths, num_views: int, group=None):
+    """The cross-view PTF gather: the per-view candidates of this rank -- feats [n,HW,F], coords [n,HW,3],
+    dens / wemb / depths [n,HW] -- packed into ONE [n, HW, F+6] buffer (70 floats per candidate at F = 64) and gathered
+    with one collective; returns the five tensors for all `num_views` views in global view order."""
+    n, HW, F = feats.shape
+    packed = torch.cat([feats, coords, dens.reshape(n, HW, 1), wemb.reshape(n, HW, 1), depths.reshape(n, HW, 1)], dim=-1)
+    full = all_gather_views(packed, num_views, group)
+    return (full[..., :F].contiguous(), full[..., F:F + 3].contiguous(), full[..., F + 3].contiguous(),
+            full[..., F + 4].contiguous(), full[..., F + 5].contiguous())
 
 
 def max_over_ranks(values: Sequence[float], device, group=None) -> List[float]:

@@ -24,6 +24,16 @@ def _worker(rank, world, port, num_views, q):
         full = parallel.all_gather_views(local, num_views)
         want = torch.stack([torch.full((4, 3), float(v)) + torch.arange(3.0) for v in range(num_views)])
         ok = torch.equal(full, want)
+        # packed candidate gather: five tensors, one collective
+        n = len(mine); HW, F = 6, 4
+        mk = lambda v, c: torch.full((HW, c), float(v)) + torch.arange(float(c))
+        loc = (torch.stack([mk(v, F) for v in mine]) if n else torch.zeros((0, HW, F)),
+               torch.stack([mk(v, 3) * 2 for v in mine]) if n else torch.zeros((0, HW, 3)),
+               *[torch.stack([mk(v, 1)[:, 0] * k for v in mine]) if n else torch.zeros((0, HW)) for k in (3, 5, 7)])
+        gf, gc, gd, gw, gz = parallel.all_gather_candidates(*loc, num_views)
+        ok = ok and torch.equal(gf, torch.stack([mk(v, F) for v in range(num_views)]))
+        ok = ok and torch.equal(gc, torch.stack([mk(v, 3) * 2 for v in range(num_views)]))
+        ok = ok and all(torch.equal(g_, torch.stack([mk(v, 1)[:, 0] * k for v in range(num_views)])) for g_, k in ((gd, 3), (gw, 5), (gz, 7)))
         t = parallel.max_over_ranks([1.0 + rank, 5.0 - rank], "cpu")
         q.put((rank, mine, ok, t))
     finally:

@@ -34,7 +34,7 @@ gru = GRU(); gru.load_state_dict(synth.gru_state(0)); gru = gru.to(dev)
 def step():
     e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     e[0].record()
-    full = [parallel.all_gather_views(x, V) if world > 1 else x for x in local_c]     # 70 fp32 per candidate
+    full = list(parallel.all_gather_candidates(*local_c, V)) if world > 1 else local_c     # 70 fp32 per candidate, ONE collective
     e[1].record()
     with torch.no_grad():
         F_, X_, E_, Z_ = ptf.fuse_views(gru, full[0], full[1], full[2], full[3], full[4], t(ext), t(K), hw)

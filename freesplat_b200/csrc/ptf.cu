@@ -550,17 +550,30 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
   };
-  // element c of the 24-wide positional encoding of (a, b)
-  auto pe24 = [&](float a, float b, int c) -> float {
-    const float x = (c < 12 ? a : b) * (float)(1 << (((c < 12 ? c : c - 12)) >> 1));
-    return (c & 1) ? cosf(x) : sinf(x);
+  // 24-wide positional encoding of (a, b): [sin(2^k a), cos(2^k a)]_{k<6} ++ the same for b (encoder_freesplat.py:62-77).
+  // One sincosf per value, the five octaves by angle doubling (sin 2t = 2 sin t cos t, cos 2t = 1 - 2 sin^2 t): the 48
+  // separate sinf / cosf calls with their range-reduction branches were ~20 % of this kernel's instructions (ncu r1f);
+  // the doubling error grows to ~2^5 ulp(1) = 4e-6 absolute at the top octave, far inside the 1e-4 budget of the latents
+  // (the encodings only feed the GRU, never an index decision).
+  auto pe24_all = [&](float a, float b, float (&o)[kE]) {
+    float sa, ca, sb, cb;
+    sincosf(a, &sa, &ca); sincosf(b, &sb, &cb);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      o[2 * k] = sa; o[2 * k + 1] = ca; o[12 + 2 * k] = sb; o[12 + 2 * k + 1] = cb;
+      const float sa2 = 2.0f * sa * ca, ca2 = fmaf(-2.0f * sa, sa, 1.0f), sb2 = 2.0f * sb * cb, cb2 = fmaf(-2.0f * sb, sb, 1.0f);
+      sa = sa2; ca = ca2; sb = sb2; cb = cb2;
+    }
   };
+  float e_h[kE], e_in[kE];
+  pe24_all(pe_src[0], pe_src[1], e_h);
+  pe24_all(pe_src[2], pe_src[3], e_in);
   // column c of concat_input (176) / of update_feat's tail; r_gate only used for layer 3
   auto a1_col = [&](int c) -> float {
     if (c < kF) return h[c];
-    if (c < kF + kE) return pe24(pe_src[0], pe_src[1], c - kF);
+    if (c < kF + kE) return e_h[c - kF];
     if (c < 2 * kF + kE) return __ldg(reinterpret_cast<const float*>(xp) + (c - kF - kE));
-    return pe24(pe_src[2], pe_src[3], c - 2 * kF - kE);
+    return e_in[c - 2 * kF - kE];
   };
 
   int round_no = 0;
@@ -666,7 +679,7 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
         const int c = r * kRound + 4 * q + e;           // column of update_feat
         if (r < kR2) v[e] = sigm(rg[4 * q + e] + sm.b_r2[c]) * h[c];
         else if (c < 2 * kF) v[e] = __ldg(reinterpret_cast<const float*>(xp) + (c - kF));
-        else if (c < kK3) v[e] = pe24(pe_src[2], pe_src[3], c - 2 * kF);
+        else if (c < kK3) v[e] = e_in[c - 2 * kF];
         else v[e] = 0.f;
       }
       store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, v[0], v[1], v[2], v[3]);

@@ -485,7 +485,15 @@ __device__ __forceinline__ void store_a4(unsigned char* hi, unsigned char* lo, i
   const uint32_t off = op_off(row, k0, 128);
   *reinterpret_cast<uint4*>(hi + off) = h; *reinterpret_cast<uint4*>(lo + off) = l;
 }
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+// gates through MUFU.EX2 / MUFU.RCP (|rel err| ~ 1e-6 each, far inside the 1e-4 budget of the latents; the library expf +
+// IEEE division + tanhf versions were ~35 % of the kernel's instructions)
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigm(float x) { return rcpa(1.0f + ex2a(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = ex2a(-2.8853900817779268f * fminf(fmaxf(x, -20.f), 20.f));      // exp(-2x)
+  return (1.0f - e) * rcpa(1.0f + e);
+}
 
 __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* __restrict__ M_dev, const int* __restrict__ pair_j, const int* __restrict__ pair_p,
                                                          const float* __restrict__ feats, const float* __restrict__ dens,
@@ -748,7 +756,7 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
         for (int e = 0; e < 4; e++) {
           const int c = r * kRound + 4 * q + e;
           const float z = sigm(zl[4 * q + e] + sm.b_z2[c]);
-          o[e] = (1.0f - z) * h[c] + z * tanhf(ql[4 * q + e] + sm.b_n2[c]);
+          o[e] = (1.0f - z) * h[c] + z * tanh_fast(ql[4 * q + e] + sm.b_n2[c]);
         }
         op[q] = make_float4(o[0], o[1], o[2], o[3]);
       }

@@ -253,6 +253,14 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+// activation-side tf32 split by TRUNCATION: hi = top 19 bits of x, lo = top 19 bits of (x - hi) (the subtraction is exact).
+// cvt.rna.tf32.f32 is three instructions on sm_100a (FSETP + IADD + LOP3): the rounded split cost 7 instructions per element
+// and ~15 % of the cost-volume / GRU kernels; the truncated one costs 3.  x = hi + lo holds to 2^-20 |x| (2^-22 rounded):
+// the dropped lo*lo term and the split error stay ~1e-6 relative, inside the 1e-4 budget.  Weights keep the rounded split.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -324,9 +332,7 @@ __device__ __forceinline__ uint32_t op_off(int row, int k, int bytes_per_step) {
 
 __device__ __forceinline__ void split_store4(unsigned char* hi, unsigned char* lo, uint32_t off, float v0, float v1, float v2, float v3) {
   uint4 h, l;
-  h.x = to_tf32(v0); h.y = to_tf32(v1); h.z = to_tf32(v2); h.w = to_tf32(v3);
-  l.x = to_tf32(v0 - __uint_as_float(h.x)); l.y = to_tf32(v1 - __uint_as_float(h.y));
-  l.z = to_tf32(v2 - __uint_as_float(h.z)); l.w = to_tf32(v3 - __uint_as_float(h.w));
+  split_tf32(v0, h.x, l.x); split_tf32(v1, h.y, l.y); split_tf32(v2, h.z, l.z); split_tf32(v3, h.w, l.w);
   *reinterpret_cast<uint4*>(hi + off) = h;
   *reinterpret_cast<uint4*>(lo + off) = l;
 }
@@ -905,7 +911,7 @@ __device__ __forceinline__ void put8(const float (&v)[8], uint32_t t_hi, uint32_
                                      unsigned char* mn_lo, int row, int col0) {
   uint32_t h[8], l[8];
 #pragma unroll
-  for (int e = 0; e < 8; e++) { h[e] = to_tf32(v[e]); l[e] = to_tf32(v[e] - __uint_as_float(h[e])); }
+  for (int e = 0; e < 8; e++) tc::split_tf32(v[e], h[e], l[e]);
   if (to_tmem) { tmem_st8(t_hi, h); tmem_st8(t_lo, l); }
   const uint32_t off = (uint32_t)((col0 >> 5) * kGroup + row * 128 + ((((col0 & 31) >> 3) ^ (row & 3)) << 5));
   *reinterpret_cast<uint4*>(mn_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);

@@ -417,6 +417,14 @@ __host__ __device__ constexpr int bTile(int n) { return 2 * (n / 8) * 256; }    
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+// activation-side tf32 split by TRUNCATION: hi = top 19 bits of x, lo = top 19 bits of (x - hi) (the subtraction is exact).
+// cvt.rna.tf32.f32 is three instructions on sm_100a (FSETP + IADD + LOP3): the rounded split cost 7 instructions per element
+// and ~15 % of the cost-volume / GRU kernels; the truncated one costs 3.  x = hi + lo holds to 2^-20 |x| (2^-22 rounded):
+// the dropped lo*lo term and the split error stay ~1e-6 relative, inside the 1e-4 budget.  Weights keep the rounded split.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
 }
@@ -479,9 +487,7 @@ struct __align__(128) Smem {
 
 __device__ __forceinline__ void store_a4(unsigned char* hi, unsigned char* lo, int row, int k0, float v0, float v1, float v2, float v3) {
   uint4 h, l;
-  h.x = to_tf32(v0); h.y = to_tf32(v1); h.z = to_tf32(v2); h.w = to_tf32(v3);
-  l.x = to_tf32(v0 - __uint_as_float(h.x)); l.y = to_tf32(v1 - __uint_as_float(h.y));
-  l.z = to_tf32(v2 - __uint_as_float(h.z)); l.w = to_tf32(v3 - __uint_as_float(h.w));
+  split_tf32(v0, h.x, l.x); split_tf32(v1, h.y, l.y); split_tf32(v2, h.z, l.z); split_tf32(v3, h.w, l.w);
   const uint32_t off = op_off(row, k0, 128);
   *reinterpret_cast<uint4*>(hi + off) = h; *reinterpret_cast<uint4*>(lo + off) = l;
 }

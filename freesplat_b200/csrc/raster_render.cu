@@ -211,9 +211,6 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// smem accumulators per staged instance: 10 floats (mean2D.xy, conic.xyw, opacity, rgb, depth),
-// padded to 11 to spread banks.
-constexpr int kAccStride = 11;
 
 template <bool kDepthGrad>
 __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
@@ -224,7 +221,6 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
   if (status[2]) return;
   __shared__ float4 sA[kThreads], sB[kThreads], sC[kThreads];
   __shared__ uint32_t sId[kThreads];
-  __shared__ float sAcc[kThreads * kAccStride];
   const int tile = blockIdx.x, v = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_x = tile % gx, tile_y = tile / gx;
@@ -266,8 +262,6 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
       sA[tid] = __ldg(r); sB[tid] = __ldg(r + 1); sC[tid] = __ldg(r + 2);
       sId[tid] = id;
     }
-#pragma unroll
-    for (int k = 0; k < kAccStride; k++) sAcc[tid * kAccStride + k] = 0.f;
     __syncthreads();
     const int pos_hi = total - 1 - done_cnt;          // list position of slot 0
     if (pos_hi - (n - 1) < warp_last) {               // some slot in this batch can matter to this warp
@@ -297,7 +291,8 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
               const float G = fast_exp(power);
               const float alpha = fminf(0.99f, bb.y * G);
               if (alpha >= 1.f / 255.f) {
-                T = T / (1.f - alpha);
+                const float r1ma = __frcp_rn(1.f - alpha);     // one correctly rounded reciprocal serves both divisions
+                T = T * r1ma;
                 const float w = alpha * T;
                 float dL_dalpha;
                 acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = bb.z;
@@ -312,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
                 }
                 dL_dalpha *= T;
                 last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                dL_dalpha += (-T_final * r1ma) * bg_dot;
                 const float dL_dG = bb.y * dL_dalpha;
                 const float gdx = G * dx, gdy = G * dy;
                 g_mx = dL_dG * (-gdx * a.z - gdy * a.w) * ddelx_dx;
@@ -326,30 +321,21 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
           }
           const float r8 = warp_reduce8(g_mx, g_my, g_cx, g_cy, g_cw, g_op, g_r, g_g, lane);
           const float rb = warp_sum(g_b);
-          float* accp = sAcc + jj * kAccStride;
-          if ((lane & 3) == 0) atomicAdd(accp + (lane >> 2), r8);
-          if (lane == 1) atomicAdd(accp + 8, rb);
+          // ONE reduction instruction per walked instance: lanes 0,4,..,28 carry components 0..7, lane 1 component 8 (b),
+          // lane 2 component 9 (depth) -> ten neighbouring floats of the instance's 48-byte gradient record, i.e. two
+          // sectors for the L2 atomic unit.  The first version accumulated in shared memory (two CAS loops per walked
+          // instance: fp32 shared atomics are compare-and-swap on this part) and flushed per batch behind two more block
+          // barriers: ~190 instructions per walked instance and 30 % of the stall samples on the barrier (ncu r1f).
+          float val = r8;
+          int comp = (lane & 3) == 0 ? (lane >> 2) : -1;
+          if (lane == 1) { val = rb; comp = 8; }
           if (kDepthGrad) {
             const float rd = warp_sum(g_d);
-            if (lane == 2) atomicAdd(accp + 9, rd);
+            if (lane == 2) { val = rd; comp = 9; }
           }
+          if (comp >= 0 && val != 0.f) atomicAdd(dL_dscreen + ((size_t)v * P + sId[jj]) * 12 + comp, val);
         }
       }
-    }
-    __syncthreads();
-    if (tid < n) {
-      const float* accp = sAcc + tid * kAccStride;
-      float* dst = dL_dscreen + ((size_t)v * P + sId[tid]) * 12;
-      // layout: mean2D.x, mean2D.y, conic.x, conic.y | conic.w, opacity, r, g | b, depth -- three 16-byte groups, flushed
-      // with VECTOR reductions (red.global.add.v4/.v2.f32): 3 L2 atomic operations per (tile, instance) instead of 9-10
-      const float a0 = accp[0], a1 = accp[1], a2 = accp[2], a3 = accp[3], a4 = accp[4], a5 = accp[5], a6 = accp[6], a7 = accp[7];
-      const float a8 = accp[8], a9 = kDepthGrad ? accp[9] : 0.f;
-      if (a0 != 0.f || a1 != 0.f || a2 != 0.f || a3 != 0.f)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
-      if (a4 != 0.f || a5 != 0.f || a6 != 0.f || a7 != 0.f)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(a4), "f"(a5), "f"(a6), "f"(a7) : "memory");
-      if (a8 != 0.f || a9 != 0.f)
-        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 8), "f"(a8), "f"(a9) : "memory");
     }
   }
 }

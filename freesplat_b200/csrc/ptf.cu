@@ -543,7 +543,14 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
 #pragma unroll
     for (int q = 0; q < kF / 4; q++) { const float4 v = __ldg(hp + q); h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w; }
   }
-  const float4* xp = reinterpret_cast<const float4*>(v_feats + (size_t)p * kF);
+  // the view-i latent of the pair is consumed in rounds 5-9 of layer 1 and again in layer 3: fetched once, up front, next to h
+  // (ncu r1k: the scalar loads at the point of use were the long-scoreboard stall of the A builds)
+  float x[kF];
+  {
+    const float4* xp = reinterpret_cast<const float4*>(v_feats + (size_t)p * kF);
+#pragma unroll
+    for (int q = 0; q < kF / 4; q++) { const float4 v = __ldg(xp + q); x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w; }
+  }
   const float pe_src[4] = {v_dens[p], wemb[j], dens[j], v_wemb[p]};     // e_h = PE(v_dens, wemb) ; e_in = PE(dens, v_wemb)
 
   // generic "run one round": wait until buffer free, let `fill` write the A tile(s), copy the B round, issue the MMAs
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
   auto a1_col = [&](int c) -> float {
     if (c < kF) return h[c];
     if (c < kF + kE) return e_h[c - kF];
-    if (c < 2 * kF + kE) return __ldg(reinterpret_cast<const float*>(xp) + (c - kF - kE));
+    if (c < 2 * kF + kE) return x[c - kF - kE];
     return e_in[c - 2 * kF - kE];
   };
 
@@ -692,7 +699,7 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
       for (int e = 0; e < 4; e++) {
         const int c = r * kRound + 4 * q + e;           // column of update_feat
         if (r < kR2) v[e] = sigm(rg[4 * q + e] + sm.b_r2[c]) * h[c];
-        else if (c < 2 * kF) v[e] = __ldg(reinterpret_cast<const float*>(xp) + (c - kF));
+        else if (c < 2 * kF) v[e] = x[c - kF];
         else if (c < kK3) v[e] = e_in[c - 2 * kF];
         else v[e] = 0.f;
       }

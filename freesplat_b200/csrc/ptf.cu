@@ -19,7 +19,7 @@
 namespace fs {
 
 constexpr int kPtfThreads = 256;
-constexpr int kPtfItems = 1024;   // items per block in the flag scans (4 per thread)
+constexpr int kPtfItems = 512;    // items per block in the flag scans (2 per thread; 1024 left the merge kernel below one wave)
 
 // counters (int32[8]) of one step: [0] N_in  [1] n_keep  [2] n_match  [3] n_append  [4] N_out
 __global__ void __launch_bounds__(kPtfThreads) ptf_project_kernel(FsPtfArgs a) {

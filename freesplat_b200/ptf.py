@@ -261,7 +261,7 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
     counts[0, 4] = HW
     zbuf, pix, zeta = i32(HW), i32(cap), torch.empty(cap, dtype=torch.float32, device=dev)
     match, append = torch.empty(cap, dtype=torch.uint8, device=dev), torch.empty(HW, dtype=torch.uint8, device=dev)
-    nb = (cap + 1023) // 1024 + 1
+    nb = (cap + 511) // 512 + 1              # blocks of the flag scans (csrc/ptf.cu: kPtfItems = 512)
     block_counts, pair_j, pair_p = i32(3 * nb), i32(cap), i32(cap)
     scratch = (zbuf, pix, zeta, match, append, block_counts, pair_j, pair_p)
     if need_grad:

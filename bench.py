@@ -148,6 +148,63 @@ def cpu_reference_views_per_s(sc, n_views: int, repeats: int):
     return n_views * repeats / dt, oracle.num_threads(), dt
 
 
+def ops_section(dev):
+    """Cost volume and PTF at BASELINE config-3 sizes: GPU time of the product kernels next to the CPU restatements
+    (oracle/, the cpu_baseline leg) on bounded samples, scaled to the full size (the sample is stated)."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from freesplat_b200 import ptf, synth
+    from freesplat_b200.cost_volume import AVGFeatureVolumeManager
+    from oracle import cost_volume as ocv, ptf as optf
+    from ptf_helpers import flat_inputs, torch_inverses
+    from test_ptf_gpu import GRU
+    out = {}
+    torch.set_num_threads(host_threads())
+
+    def gpu_ms(fn, n=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    # ---- cost volume: 3 reference views, K = 2, 48 x 120 x 160, D = 128 ----
+    V, K, Hf, Wf, D = 3, 2, 120, 160, 128
+    inp = synth.cost_volume_inputs(0, V, K, 48, Hf, Wf)
+    mlp = synth.cost_volume_mlp(0)
+    m = AVGFeatureVolumeManager(Hf, Wf, num_depth_bins=D, matching_dim_size=48).to(dev)
+    ginp = {k: v.to(dev) for k, v in inp.items()}
+    with torch.no_grad():
+        g_ms = gpu_ms(lambda: m(**ginp))
+    Dsub = 32                                                  # CPU sample: 1 reference view, 32 of the 128 planes
+    sub = {k: v[:1] for k, v in inp.items() if k not in ("min_depth", "max_depth")}
+    t0 = time.perf_counter()
+    ocv.forward(sub["cur_feats"], sub["src_feats"], sub["src_extrinsics"], sub["src_Ks"], sub["cur_invK"], inp["min_depth"],
+                inp["max_depth"], mlp, Dsub, plane_chunk=8)
+    c_s = time.perf_counter() - t0
+    out["cost_volume_cfg3_fwd"] = {"gpu_ms": g_ms, "cpu_port_ms": c_s * 1e3 * (D / Dsub) * V, "cores": host_threads(),
+                                   "sample": f"1 of {V} reference views, {Dsub} of {D} planes ({c_s:.1f} s), scaled"}
+    # ---- PTF: 3 views of 640 x 480 ----
+    pin = synth.ptf_inputs(0, 3, 480, 640)
+    feats, coords, dens, wemb, depths, ext, Kn, hw = flat_inputs(pin)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    gru = GRU(); gru.load_state_dict(synth.gru_state(0)); gru = gru.to(dev)
+    gargs = [t(x) for x in (feats, coords, dens, wemb, depths, ext, Kn)]
+    with torch.no_grad():
+        g_ms = gpu_ms(lambda: ptf.fuse_views(gru, *gargs, hw), n=3)
+    t0 = time.perf_counter()
+    optf.fuse(feats, coords, dens, wemb, depths, ext, Kn, hw, optf.torch_gru_fn(synth.gru_state(0)), E_invs=torch_inverses(ext))
+    c_s = time.perf_counter() - t0
+    out["ptf_3views_640x480"] = {"gpu_ms": g_ms, "cpu_port_ms": c_s * 1e3, "cores": host_threads(),
+                                 "sample": f"the full 3-view fold ({c_s:.1f} s)"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -200,6 +257,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops", action="store_true",
+                    help="also time the cost volume and PTF (BASELINE config 3 sizes) on the GPU and their CPU restatements "
+                         "on bounded samples; adds an `ops` object to the JSON line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -343,6 +403,8 @@ def main():
             v, cores, dt = cpu_reference_views_per_s(sc_cpu, n_views=T_VIEWS, repeats=reps)
             line["cpu_baseline"] = {"value": v, "unit": "views/s", "cores": cores, "kind": "port",
                                     "sample": f"{reps} x {T_VIEWS} views of the full workload ({dt:.1f} s)"}
+        if args.ops:
+            line["ops"] = ops_section(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -500,7 +500,7 @@ static int launch_pack(const FsCostVolumeArgs& a, cudaStream_t s) {
 
 int launch_cost_volume_fwd(const FsCostVolumeArgs& a, cudaStream_t s) {
   const size_t HW = (size_t)a.H * a.W;
-  const int ppb = 8;
+  const int ppb = 16;      // planes per CTA: 4 / 8 / 16 / 32 measured 1.59 / 1.44 / 1.39 / 1.40 ms (config 3)
   if (int rc = launch_pack(a, s)) return rc;
   (void)HW;
   dim3 grid(patch_blocks(a.H, a.W), (unsigned)((a.D + ppb - 1) / ppb), (unsigned)a.B);

@@ -39,6 +39,13 @@ def test_ragged_image_and_empty():
     assert torch.allclose(st.color[0, 0], torch.full_like(st.color[0, 0], 0.5))
 
 
+def test_many_views_tile_scan_chunks():
+    """18 views x 300 tiles = 5400 tile counters: more than one 4096-counter pass of the scan / tile-order kernel."""
+    sc = synth.pixel_aligned_scene(seed=2, h=240, w=320, n_context=2, n_target=18, keep=None)
+    st, _, m = _check(sc)
+    assert st.V == 18 and len(m["views"]) == 18
+
+
 def test_crowded_tile_global_sort_path():
     # > 4096 instances in a tile: exercises the global-memory sort path and multi-batch rendering
     sc = synth.random_scene(seed=4, h=64, w=64, P=30000, sigma_px=(0.5, 2.0))

@@ -830,7 +830,8 @@ struct __align__(1024) Smem {
   // the 4th group only feeds accumulator rows 96..127, which nobody reads.
   unsigned char X_hi[2 * kGroup], A1_hi[kGroup];
   unsigned char X_lo[2 * kGroup], A1_lo[kGroup];
-  unsigned char dZ_hi[kGroup], dZ_lo[kGroup];
+  unsigned char dZ_hi[kGroup], dZ_lo[kGroup];        // dZ2 (U1's B operand)
+  unsigned char dZb_hi[kGroup], dZb_lo[kGroup];      // dZ1 (U0's B operand): its own tile, so that U1 / U0 can run BEHIND the chain
   // K-major SWIZZLE_NONE weight tiles, [k-step][n/8][2 chunks][8 rows][16 B]
   unsigned char W0f_hi[7 * 1024], W0f_lo[7 * 1024];     // n = out (32), k = in (56):  Z1 = X W0^T
   unsigned char W1f_hi[4 * 1024], W1f_lo[4 * 1024];     // n = out, k = in:            Z2 = A1 W1^T
@@ -1017,6 +1018,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
   }
   const uint32_t bar_chain = smem_u32(&sm.bar_chain), bar_dw = smem_u32(&sm.bar_dw);
   const uint32_t aX_hi = smem_u32(sm.X_hi), aX_lo = smem_u32(sm.X_lo), aDZ_hi = smem_u32(sm.dZ_hi), aDZ_lo = smem_u32(sm.dZ_lo);
+  const uint32_t aDZb_hi = smem_u32(sm.dZb_hi), aDZb_lo = smem_u32(sm.dZb_lo);
   const uint32_t aW0f_hi = smem_u32(sm.W0f_hi), aW0f_lo = smem_u32(sm.W0f_lo), aW1f_hi = smem_u32(sm.W1f_hi), aW1f_lo = smem_u32(sm.W1f_lo);
   const uint32_t aW1t_hi = smem_u32(sm.W1t_hi), aW1t_lo = smem_u32(sm.W1t_lo), aW0t_hi = smem_u32(sm.W0t_hi), aW0t_lo = smem_u32(sm.W0t_lo);
   uint32_t ph_chain = 0, ph_dw = 0;
@@ -1073,7 +1075,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       rn = 1.0f / ((float)__popc(valid) + 1e-8f);
 #pragma unroll
       for (int c = 0; c < kHalfC; c++) xs[c] *= rn;
-      if (!first) { mbar_wait(bar_dw, ph_dw); ph_dw ^= 1u; }          // U0 of the previous plane has finished reading the X and dZ tiles
+      if (!first) { mbar_wait(bar_dw, ph_dw); ph_dw ^= 1u; }          // U1 / U0 of the previous plane have finished reading the X, A1 and dZ tiles
 #pragma unroll
       for (int q = 0; q < kHalfC / 8; q++) {
         const float v8[8] = {xs[8 * q], xs[8 * q + 1], xs[8 * q + 2], xs[8 * q + 3], xs[8 * q + 4], xs[8 * q + 5], xs[8 * q + 6], xs[8 * q + 7]};
@@ -1138,11 +1140,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
 #pragma unroll
       for (int s = 0; s < 4; s++)
         mma3_ts(tmem + kColDA1, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW1t_hi + s * 1024, aW1t_lo + s * 1024, kIdK32, s > 0 ? 1u : 0u);
-      commit(bar_chain);
-#pragma unroll
-      for (int s = 0; s < 16; s++)     // k = 8 tile rows per step
-        mma3_mn(tmem + kColU1, aX_hi + s * 1024, aX_lo + s * 1024, aDZ_hi + s * 1024, aDZ_lo + s * 1024, kIdMN32, (first && s == 0) ? 0u : 1u);
-      commit(bar_dw);
+      commit(bar_chain);               // (U1 is issued behind the dX product below: the dependent chain never queues behind it)
     }
     mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1153,11 +1151,10 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       tmem_ld<16>(t_row + kColZ1 + 16u * half, z);
 #pragma unroll
       for (int j = 0; j < 16; j++) da[j] *= dleaky(z[j]);
-      mbar_wait(bar_dw, ph_dw); ph_dw ^= 1u;                           // U1 has finished reading dZ2
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         const float v8[8] = {da[8 * q], da[8 * q + 1], da[8 * q + 2], da[8 * q + 3], da[8 * q + 4], da[8 * q + 5], da[8 * q + 6], da[8 * q + 7]};
-        put8(v8, t_row + kColHhi + (uint32_t)(16 * half + 8 * q), t_row + kColHlo + (uint32_t)(16 * half + 8 * q), true, sm.dZ_hi, sm.dZ_lo, r, 16 * half + 8 * q);
+        put8(v8, t_row + kColHhi + (uint32_t)(16 * half + 8 * q), t_row + kColHlo + (uint32_t)(16 * half + 8 * q), true, sm.dZb_hi, sm.dZb_lo, r, 16 * half + 8 * q);
       }
     }
     sync_for_mma();
@@ -1167,9 +1164,14 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       for (int s = 0; s < 4; s++)
         mma3_ts(tmem + kColDX, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW0t_hi + s * 2048, aW0t_lo + s * 2048, kIdK64, s > 0 ? 1u : 0u);
       commit(bar_chain);
+      // the two weight-gradient products (2 x 48 MMAs) run behind the chain, underneath the scatter of this plane and the gather
+      // of the next one; bar_dw guards the X / A1 / dZ tiles they read (waited in S1 of the next plane)
+#pragma unroll
+      for (int s = 0; s < 16; s++)     // k = 8 tile rows per step
+        mma3_mn(tmem + kColU1, aX_hi + s * 1024, aX_lo + s * 1024, aDZ_hi + s * 1024, aDZ_lo + s * 1024, kIdMN32, (first && s == 0) ? 0u : 1u);
 #pragma unroll
       for (int s = 0; s < 16; s++)
-        mma3_mn(tmem + kColU0, aX_hi + s * 1024, aX_lo + s * 1024, aDZ_hi + s * 1024, aDZ_lo + s * 1024, kIdMN32, (first && s == 0) ? 0u : 1u);
+        mma3_mn(tmem + kColU0, aX_hi + s * 1024, aX_lo + s * 1024, aDZb_hi + s * 1024, aDZb_lo + s * 1024, kIdMN32, (first && s == 0) ? 0u : 1u);
       commit(bar_dw);
     }
     mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u;

@@ -275,6 +275,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NUMA placement of the pinned staging buffers (host-to-host path): stay on the CPUs next to this rank's GPU
+    from freesplat_b200.pipeline import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -388,7 +391,8 @@ def main():
             "e2e": {"value": world * V * args.steps / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "api": "freesplat_b200.pipeline.HostRenderPipeline (3 streams, depth 2)",
-                    "protocol": "median of 3 timings of K steps", "ms_per_step_all": [x / args.steps for x in e2e_all]},
+                    "protocol": "median of 3 timings of K steps", "ms_per_step_all": [x / args.steps for x in e2e_all],
+                    "h2d_gbs": h2d / (e2e_ms / args.steps * 1e-3) / 1e9, "numa": numa},
             "gpu_launches": 4 * args.steps,      # preprocess, tile scan, scatter, sort+render
             "stage_ms": {"preprocess": sum(pre_ms) / len(pre_ms), "binning": sum(bin_ms) / len(bin_ms), "render": rd},
             "roofline": {"kernel": "render_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -11,6 +11,39 @@ import torch
 from . import _lib, decoder, rasterizer
 
 
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Pins the calling process to the CPUs that are local to the GPU's PCIe root (NVML's ideal CPU affinity, intersected
+    with the CPUs this process may use), so that the pinned staging buffers allocated AFTERWARDS are first-touched on the
+    GPU-local NUMA node: on a two-socket host a remote node costs a third of the host-to-device bandwidth (34 instead of
+    50 GB/s measured), and the host-to-host path is PCIe-bound.  Returns what was done; never raises."""
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        phys = device_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        allowed = set(os.sched_getaffinity(0))
+        both = sorted(local & allowed)
+        info.update(gpu_local_cpus=len(local), allowed_cpus=len(allowed))
+        if both and len(both) < len(allowed):
+            os.sched_setaffinity(0, both)
+            info.update(bound=True, cpus=len(both))
+        elif both:
+            info.update(bound=False, note="already local")
+    except Exception as exc:       # NVML missing, no permission, exotic topology: run unbound
+        info["note"] = f"{type(exc).__name__}: {exc}"[:120]
+    return info
+
+
 class HostRenderPipeline:
     KEYS = ("extrinsics", "intrinsics", "near", "far", "means", "covariances", "harmonics", "opacities")
 

@@ -14,13 +14,19 @@ sys.path.insert(0, ROOT)
 from freesplat_b200 import synth  # noqa: E402
 from tests.golden import ref_loader  # noqa: E402
 
-CASES = {"ptf_v3": (0, 3, 16, 24), "ptf_v4": (1, 4, 12, 20), "ptf_v2_far": (2, 2, 16, 16)}
+CASES = {"ptf_v3": (0, 3, 16, 24), "ptf_v4": (1, 4, 12, 20), "ptf_v2_far": (2, 2, 16, 16), "ptf_v3_ties": (3, 3, 12, 16)}
 
 
 def main():
     fuse, pe, GRU = ref_loader.load_fuse_gaussians()
     for name, (seed, V, h, w) in CASES.items():
         inp = synth.ptf_inputs(seed, V, h, w, spacing=0.9 if "far" in name else 0.2)
+        if "ties" in name:
+            # exact z-buffer ties: every 5th pixel of view 0 takes the coordinates of its left neighbour, so both project to the
+            # same pixel of the later views with IDENTICAL depth -> several winners per pixel (encoder_freesplat.py:470-482)
+            c = inp["coords"][0]
+            idx = torch.arange(1, h * w, 5)
+            c[0, 0, idx] = c[0, 0, idx - 1]
         gru = GRU()
         gru.load_state_dict(synth.gru_state(seed))
         self = SimpleNamespace(gru=gru)

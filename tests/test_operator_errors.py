@@ -64,3 +64,15 @@ def test_cpu_tensors_raise_everywhere():
         cv(cur_feats=torch.zeros(1, 48, 4, 4), src_feats=torch.zeros(1, 1, 48, 4, 4), src_extrinsics=torch.eye(4)[None, None],
            src_poses=torch.eye(4)[None, None], src_Ks=torch.eye(4)[None, None], cur_invK=torch.eye(4)[None],
            min_depth=torch.tensor(0.5), max_depth=torch.tensor(15.0))
+
+
+def test_numa_binding_helper_never_raises():
+    """No NVML in the build container: the helper reports why it did nothing and leaves the affinity alone."""
+    import os
+    from freesplat_b200.pipeline import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu_numa(0)
+    assert isinstance(info, dict) and "bound" in info
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)

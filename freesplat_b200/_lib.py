@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfreesplat_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 vp = C.c_void_p
 
@@ -39,7 +39,7 @@ class FsRasterBwdArgs(C.Structure):
         ("scales", vp), ("rotations", vp), ("cov3D_precomp", vp), ("views", vp),
         ("rec", vp), ("radii", vp), ("clamped", vp), ("ranges", vp),
         ("point_list", vp), ("final_T", vp), ("n_contrib", vp), ("status", vp),
-        ("dL_dcolor", vp), ("dL_ddepth", vp), ("dL_dscreen", vp),
+        ("dL_dcolor", vp), ("dL_ddepth", vp), ("dL_dalpha", vp), ("dL_dscreen", vp),
         ("dL_dmeans2D", vp), ("dL_dmeans3D", vp), ("dL_dcov3D", vp), ("dL_dshs", vp),
         ("dL_dcolors", vp), ("dL_dopacities", vp), ("dL_dscales", vp), ("dL_drotations", vp),
     ]
@@ -51,6 +51,7 @@ EXPORTS = [
     "fs_raster_forward", "fs_raster_backward", "fs_mark_visible", "fs_camera_records",
     "fs_cost_volume_forward", "fs_cost_volume_backward",
     "fs_ptf_match", "fs_ptf_merge", "fs_ptf_gru_inputs", "fs_ptf_gru_update", "fs_ptf_gru_output",
+    "fs_ptf_view_setup", "fs_graph_capture_begin", "fs_graph_capture_end", "fs_graph_launch", "fs_graph_destroy",
     "fs_ptf_gru", "fs_ptf_gru_wscratch_bytes", "fs_gaussian_head", "fs_depth_head", "fs_backproject", "fs_ply_vertices",
 ]
 

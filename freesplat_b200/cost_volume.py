@@ -167,9 +167,18 @@ class AVGFeatureVolumeManager(nn.Module):
         if return_mask:
             raise _lib.FreeSplatB200Error("return_mask=True is not on FreeSplat's path (encoder_freesplat.py:280-288)")
         B = src_feats.shape[0]
+        numel = lambda x: x.numel() if torch.is_tensor(x) else 1
+        # FreeSplat's own call passes scalar near / far (encoder_freesplat.py:280-288): the planes are then fronto-parallel and
+        # shared by the batch by construction.  Caller-supplied planes or per-sample depth ranges are honoured by the reference
+        # per batch element and per pixel; the fused kernel takes ONE [D] plane vector, so anything else is refused (one host
+        # read, off FreeSplat's path) instead of silently producing a different volume.
+        static_planes = depth_planes_bdhw is None and numel(min_depth) == 1 and numel(max_depth) == 1
         if depth_planes_bdhw is None:
             depth_planes_bdhw = self.generate_depth_planes(B, min_depth, max_depth)
-        planes = depth_planes_bdhw[0, :, 0, 0]          # the reference's planes are fronto-parallel and shared by the batch
+        if not static_planes and not bool((depth_planes_bdhw == depth_planes_bdhw[:1, :, :1, :1]).all()):
+            raise _lib.FreeSplatB200Error("depth planes must be constant over the batch and over the pixels (one [D] plane "
+                                          "vector): per-sample / per-pixel planes are not implemented by the fused kernel")
+        planes = depth_planes_bdhw[0, :, 0, 0]
         net = self.mlp.net
         vol = cost_volume(cur_feats, src_feats, src_extrinsics, src_Ks, cur_invK, planes,
                           (net[0].weight, net[0].bias, net[2].weight, net[2].bias, net[4].weight, net[4].bias))

@@ -139,6 +139,12 @@ static int check_ptf(const FsPtfArgs* a) {
   return FS_OK;
 }
 
+int fs_ptf_view_setup(int32_t V, int32_t H, int32_t W, const float* extrinsics, const float* intrinsics, float* E_inv, float* K_px,
+                      void* stream) {
+  FS_REQUIRE(V >= 0 && H >= 1 && W >= 1 && (V == 0 || (extrinsics && intrinsics && E_inv && K_px)), "bad arguments");
+  return launch_ptf_view_setup(V, H, W, extrinsics, intrinsics, E_inv, K_px, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int fs_ptf_match(const FsPtfArgs* a, void* stream) {
   if (int rc = check_ptf(a)) return rc;
   return launch_ptf_match(*a, reinterpret_cast<cudaStream_t>(stream));
@@ -200,5 +206,43 @@ int fs_ptf_gru(const FsPtfGruArgs* a, void* stream) {
   return launch_ptf_gru_tc(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 int64_t fs_ptf_gru_wscratch_bytes(void) { return (int64_t)ptf_gru_wscratch_bytes(); }
+
+// ---- CUDA graphs: a launch sequence of fs_* calls with static arguments, replayed by ONE cudaGraphLaunch ----
+int fs_graph_capture_begin(void** stream_out) {
+  FS_REQUIRE(stream_out != nullptr, "stream_out is NULL");
+  cudaStream_t s = nullptr;
+  if (int rc = check_cuda(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreateWithFlags")) return rc;
+  // thread-local mode: allocator activity of other host threads does not invalidate the capture
+  if (int rc = check_cuda(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) {
+    cudaStreamDestroy(s);
+    return rc;
+  }
+  *stream_out = s;
+  return FS_OK;
+}
+
+int fs_graph_capture_end(void* stream, void** graph_exec_out) {
+  FS_REQUIRE(stream != nullptr && graph_exec_out != nullptr, "NULL argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t ge = nullptr;
+  int rc = check_cuda(cudaStreamEndCapture(s, &g), "cudaStreamEndCapture");
+  if (!rc) rc = check_cuda(cudaGraphInstantiate(&ge, g, 0), "cudaGraphInstantiate");
+  if (g) cudaGraphDestroy(g);
+  cudaStreamDestroy(s);
+  if (rc) return rc;
+  *graph_exec_out = ge;
+  return FS_OK;
+}
+
+int fs_graph_launch(void* graph_exec, void* stream) {
+  FS_REQUIRE(graph_exec != nullptr, "graph is NULL");
+  return check_cuda(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), reinterpret_cast<cudaStream_t>(stream)), "cudaGraphLaunch");
+}
+
+int fs_graph_destroy(void* graph_exec) {
+  if (graph_exec == nullptr) return FS_OK;
+  return check_cuda(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)), "cudaGraphExecDestroy");
+}
 
 }  // extern "C"

@@ -30,6 +30,7 @@ int launch_camera_records(int V, const float* ext, const float* K, const float* 
 int launch_cost_volume_fwd(const FsCostVolumeArgs& a, cudaStream_t s);  // cost_volume.cu
 int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s);  // cost_volume.cu
 
+int launch_ptf_view_setup(int V, int H, int W, const float* ext, const float* K, float* E_inv, float* K_px, cudaStream_t s);  // ptf.cu
 int launch_ptf_match(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
 int launch_ptf_merge(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
 int launch_gaussian_head(const FsAdapterArgs& a, cudaStream_t s);   // adapter.cu

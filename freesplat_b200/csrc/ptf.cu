@@ -371,6 +371,57 @@ static inline int ptf_blocks(int n_upper, int HW) {
   return (m + kPtfItems - 1) / kPtfItems;
 }
 
+// ---- per-view constants of the fold: E_i^-1 and the pixel-space intrinsics (encoder_freesplat.py:445-454) ----
+// The reference calls extrinsic.inverse() (LAPACK on the CPU, cuSOLVER / MAGMA on the GPU: the two differ in the last
+// bits).  The projected coordinates feed rounding and z-buffer decisions, so the inverse is part of the canonical
+// arithmetic: cofactor expansion over 2x2 sub-determinants in fp64 (no fused multiply-add: -fmad=false), one rounding
+// to fp32.  oracle/ptf.py::canonical_inverse is the same expression tree.
+__global__ void ptf_view_setup_kernel(int V, int H, int W, const float* __restrict__ ext, const float* __restrict__ K,
+                                      float* __restrict__ E_inv, float* __restrict__ K_px) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  double a[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) a[k] = (double)ext[16 * (size_t)v + k];
+  const double s0 = a[0] * a[5] - a[4] * a[1], s1 = a[0] * a[6] - a[4] * a[2], s2 = a[0] * a[7] - a[4] * a[3];
+  const double s3 = a[1] * a[6] - a[5] * a[2], s4 = a[1] * a[7] - a[5] * a[3], s5 = a[2] * a[7] - a[6] * a[3];
+  const double c5 = a[10] * a[15] - a[14] * a[11], c4 = a[9] * a[15] - a[13] * a[11], c3 = a[9] * a[14] - a[13] * a[10];
+  const double c2 = a[8] * a[15] - a[12] * a[11], c1 = a[8] * a[14] - a[12] * a[10], c0 = a[8] * a[13] - a[12] * a[9];
+  const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+  const double id = 1.0 / det;
+  double b[16];
+  b[0] = (a[5] * c5 - a[6] * c4 + a[7] * c3) * id;
+  b[1] = (-a[1] * c5 + a[2] * c4 - a[3] * c3) * id;
+  b[2] = (a[13] * s5 - a[14] * s4 + a[15] * s3) * id;
+  b[3] = (-a[9] * s5 + a[10] * s4 - a[11] * s3) * id;
+  b[4] = (-a[4] * c5 + a[6] * c2 - a[7] * c1) * id;
+  b[5] = (a[0] * c5 - a[2] * c2 + a[3] * c1) * id;
+  b[6] = (-a[12] * s5 + a[14] * s2 - a[15] * s1) * id;
+  b[7] = (a[8] * s5 - a[10] * s2 + a[11] * s1) * id;
+  b[8] = (a[4] * c4 - a[5] * c2 + a[7] * c0) * id;
+  b[9] = (-a[0] * c4 + a[1] * c2 - a[3] * c0) * id;
+  b[10] = (a[12] * s4 - a[13] * s2 + a[15] * s0) * id;
+  b[11] = (-a[8] * s4 + a[9] * s2 - a[11] * s0) * id;
+  b[12] = (-a[4] * c3 + a[5] * c1 - a[6] * c0) * id;
+  b[13] = (a[0] * c3 - a[1] * c1 + a[2] * c0) * id;
+  b[14] = (-a[12] * s3 + a[13] * s1 - a[14] * s0) * id;
+  b[15] = (a[8] * s3 - a[9] * s1 + a[10] * s0) * id;
+#pragma unroll
+  for (int k = 0; k < 16; k++) E_inv[16 * (size_t)v + k] = (float)b[k];
+  const float fw = (float)W, fh = (float)H;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const float x = K[9 * (size_t)v + k];
+    K_px[9 * (size_t)v + k] = k < 3 ? x * fw : (k < 6 ? x * fh : x);
+  }
+}
+
+int launch_ptf_view_setup(int V, int H, int W, const float* ext, const float* K, float* E_inv, float* K_px, cudaStream_t s) {
+  if (V <= 0) return FS_OK;
+  ptf_view_setup_kernel<<<(V + 63) / 64, 64, 0, s>>>(V, H, W, ext, K, E_inv, K_px);
+  return check_cuda(cudaGetLastError(), "ptf_view_setup_kernel");
+}
+
 int launch_ptf_match(const FsPtfArgs& a, cudaStream_t s) {
   const int HW = a.H * a.W;
   int rc;

@@ -19,12 +19,6 @@
 
 namespace fs {
 
-__device__ __forceinline__ float fast_exp(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
-  return y;
-}
-
 constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------- forward
@@ -217,7 +211,7 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
     const float* __restrict__ views, const uint32_t* __restrict__ status, int P, int H, int W, int gx, int ntiles,
     const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
-    const float* __restrict__ dL_ddepth, float* __restrict__ dL_dscreen) {
+    const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha_out, float* __restrict__ dL_dscreen) {
   if (status[2]) return;
   __shared__ float4 sA[kThreads], sB[kThreads], sC[kThreads];
   __shared__ uint32_t sId[kThreads];
@@ -245,7 +239,10 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
     dLp0 = g[pix]; dLp1 = g[HW + pix]; dLp2 = g[2 * HW + pix];
     if (kDepthGrad) dLd = dL_ddepth[(size_t)v * HW + pix];
   }
-  const float bg_dot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
+  // out_color = C + T_final * bg and out_alpha = 1 - T_final: both reach alpha_j only through T_final
+  // (d T_final / d alpha_j = -T_final / (1 - alpha_j)), so a gradient on the alpha output folds into the background term
+  float bg_dot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
+  if (dL_dalpha_out != nullptr && inside) bg_dot -= dL_dalpha_out[(size_t)v * HW + pix];
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f, last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;
   const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
   // highest list position (1-based) any pixel of this warp contributed to
@@ -284,11 +281,13 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
           float g_mx = 0.f, g_my = 0.f, g_cx = 0.f, g_cy = 0.f, g_cw = 0.f, g_op = 0.f, g_r = 0.f, g_g = 0.f, g_b = 0.f, g_d = 0.f;
           if (pos < last) {
             const float dx = a.x - pxf, dy = a.y - pyf;
-            const float ca = -0.5f * a.z, cb = -a.w, cc = -0.5f * bb.x;
+            // the SAME expressions as the forward pass (coefficients pre-multiplied by log2(e), MUFU.EX2): alpha and the
+            // alpha >= 1/255 decision are bit-identical to the ones that produced final_T / n_contrib
+            const float ca = (-0.5f * a.z) * kLog2e, cb = (-a.w) * kLog2e, cc = (-0.5f * bb.x) * kLog2e;
             const float t = fmaf(cb, dy, ca * dx);
             const float power = fmaf(cc * dy, dy, t * dx);
             if (power <= 0.f) {
-              const float G = fast_exp(power);
+              const float G = ex2_approx(power);
               const float alpha = fminf(0.99f, bb.y * G);
               if (alpha >= 1.f / 255.f) {
                 const float r1ma = __frcp_rn(1.f - alpha);     // one correctly rounded reciprocal serves both divisions
@@ -357,11 +356,11 @@ int launch_render_bwd(const FsRasterBwdArgs& a, cudaStream_t s) {
   if (a.has_depth_grad && a.dL_ddepth)
     render_bwd_kernel<true><<<grid, kThreads, 0, s>>>(reinterpret_cast<const uint2*>(a.ranges), a.point_list,
                                                        reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P, a.H, a.W,
-                                                       gx, gx * gy, a.final_T, a.n_contrib, a.dL_dcolor, a.dL_ddepth, a.dL_dscreen);
+                                                       gx, gx * gy, a.final_T, a.n_contrib, a.dL_dcolor, a.dL_ddepth, a.dL_dalpha, a.dL_dscreen);
   else
     render_bwd_kernel<false><<<grid, kThreads, 0, s>>>(reinterpret_cast<const uint2*>(a.ranges), a.point_list,
                                                         reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P, a.H, a.W,
-                                                        gx, gx * gy, a.final_T, a.n_contrib, a.dL_dcolor, a.dL_ddepth, a.dL_dscreen);
+                                                        gx, gx * gy, a.final_T, a.n_contrib, a.dL_dcolor, a.dL_ddepth, a.dL_dalpha, a.dL_dscreen);
   return check_cuda(cudaGetLastError(), "render_bwd_kernel");
 }
 

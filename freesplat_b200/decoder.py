@@ -1,8 +1,8 @@
 """Host-side mirror of the reference's raster adapter.
 
-  render_cuda(...)      same signature and return as
-                        /root/reference/src/model/decoder/cuda_splatting.py:47-132
-                        (per-(b v) Gaussian tensors, python loop over views) -- kept for drop-in use;
+  (`render_cuda` itself, /root/reference/src/model/decoder/cuda_splatting.py:47-132, needs no mirror: with the top-level
+  module `diff_gaussian_rasterization_depth` of this repo on PYTHONPATH the reference's own function runs unchanged --
+  tests/test_reference_adapter_gpu.py feeds the calls it makes through that module.)
   render_views(...)     what DecoderSplattingCUDA.forward (decoder_splatting_cuda.py:35-75) needs:
                         ONE Gaussian set per scene rendered into all its target views by a single
                         launch sequence; the `scale_invariant` rescale (cuda_splatting.py:64-71) is
@@ -18,7 +18,7 @@ from math import isqrt
 
 import torch
 
-from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, pack_views, rasterize_views)
+from .rasterizer import pack_views, rasterize_views
 
 
 def get_fov(intrinsics: torch.Tensor) -> torch.Tensor:
@@ -128,47 +128,6 @@ def render_views(extrinsics, intrinsics, near, far, image_shape, background_colo
         cov3D_precomp=gaussian_covariances, sh_degree=degree, depth_grad=depth_grad, sh_layout=1, cov_stride=9,
         check_overflow=check_overflow)
     return color, depth
-
-
-def render_cuda(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
-                gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant=True, use_sh=True):
-    """Drop-in for cuda_splatting.py:47-132 (batch of independent (camera, Gaussian set) pairs)."""
-    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
-    if scale_invariant:
-        scale = 1 / near
-        extrinsics = extrinsics.clone()
-        extrinsics[..., :3, 3] = extrinsics[..., :3, 3] * scale[:, None]
-        gaussian_covariances = gaussian_covariances * (scale[:, None, None, None] ** 2)
-        gaussian_means = gaussian_means * scale[:, None, None]
-        near = near * scale
-        far = far * scale
-    _, _, _, n = gaussian_sh_coefficients.shape
-    degree = isqrt(n) - 1
-    shs = gaussian_sh_coefficients.transpose(2, 3)
-    b = extrinsics.shape[0]
-    h, w = image_shape
-    fov_x, fov_y = get_fov(intrinsics).unbind(dim=-1)
-    tan_fov_x = (0.5 * fov_x).tan()
-    tan_fov_y = (0.5 * fov_y).tan()
-    projection_matrix = get_projection_matrix(near, far, fov_x, fov_y).transpose(1, 2)
-    view_matrix = extrinsics.inverse().transpose(1, 2)
-    full_projection = view_matrix @ projection_matrix
-    all_images, all_depths = [], []
-    row, col = torch.triu_indices(3, 3)
-    for i in range(b):
-        mean_gradients = torch.zeros_like(gaussian_means[i], requires_grad=True)
-        settings = GaussianRasterizationSettings(
-            image_height=h, image_width=w, tanfovx=tan_fov_x[i].item(), tanfovy=tan_fov_y[i].item(),
-            bg=background_color[i], scale_modifier=1.0, viewmatrix=view_matrix[i], projmatrix=full_projection[i],
-            sh_degree=degree, campos=extrinsics[i, :3, 3], prefiltered=False, debug=False)
-        rasterizer = GaussianRasterizer(settings)
-        image, radii, depth, _ = rasterizer(
-            means3D=gaussian_means[i], means2D=mean_gradients, shs=shs[i] if use_sh else None,
-            colors_precomp=None if use_sh else shs[i, :, 0, :], opacities=gaussian_opacities[i, ..., None],
-            cov3D_precomp=gaussian_covariances[i, :, row, col])
-        all_images.append(image)
-        all_depths.append(depth.unsqueeze(0))
-    return torch.stack(all_images), torch.stack(all_depths)
 
 
 class DecoderSplattingB200(torch.nn.Module):

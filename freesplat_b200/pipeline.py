@@ -45,24 +45,75 @@ def bind_to_gpu_numa(device_index: int) -> dict:
 
 
 class HostRenderPipeline:
+    """submit(host tensors) -> slot; wait(slot) -> (colour, depth) in pinned host memory.
+
+    Every slot owns static device input buffers, a static rasterizer workspace and ONE CUDA graph (camera records + memset +
+    preprocess + tile scan + scatter + sort/render: rasterizer.RasterPlan), so a step costs the host three async copies in,
+    one graph launch and two async copies out.  The instance count R stays on the device; the status word rides back with the
+    results and is looked at when the slot is next touched (wait() or the submit that reuses it): an overflowed step is
+    re-run on a grown workspace from the inputs still resident in the slot, transparently."""
     KEYS = ("extrinsics", "intrinsics", "near", "far", "means", "covariances", "harmonics", "opacities")
 
-    def __init__(self, device, image_shape: Tuple[int, int], n_views: int, depth: int = 2, background=(0.0, 0.0, 0.0)):
+    def __init__(self, device, image_shape: Tuple[int, int], n_views: int, depth: int = 2, background=(0.0, 0.0, 0.0),
+                 graph: bool = True):
         self.dev = torch.device(device)
         self.h, self.w = image_shape
         self.V = n_views
         self.depth = depth
+        self.graph = graph
         self.s_h2d, self.s_run, self.s_d2h = (torch.cuda.Stream(self.dev) for _ in range(3))
         self.bg = torch.tensor(background, dtype=torch.float32, device=self.dev)[None].expand(n_views, 3).contiguous()
         self.dev_in: List[Optional[Dict[str, torch.Tensor]]] = [None] * depth
+        self.plans: List[Optional[rasterizer.RasterPlan]] = [None] * depth
         self.out_c = [torch.empty((n_views, 3, self.h, self.w), dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.out_d = [torch.empty((n_views, self.h, self.w), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.out_status = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(depth)]
         self.ev_in_free = [torch.cuda.Event() for _ in range(depth)]     # device inputs of slot may be overwritten
         self.ev_copied = [torch.cuda.Event() for _ in range(depth)]
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]        # kernels of slot finished
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]         # host outputs of slot are valid
-        self.status = [None] * depth      # device status word of the slot's forward (overflow flag)
+        self.unresolved = [False] * depth  # slot holds a step whose status word has not been looked at yet
+        self.reruns = 0
         self.n = 0
+
+    def _plan(self, slot: int, host) -> "rasterizer.RasterPlan":
+        d = self.dev_in[slot]
+        n = d["harmonics"].shape[-1]
+        from math import isqrt
+        return rasterizer.RasterPlan(d["means"], d["opacities"], self.h, self.w, shs=d["harmonics"],
+                                     cov3D_precomp=d["covariances"].reshape(-1, 9),
+                                     cameras=(d["extrinsics"], d["intrinsics"], d["near"], d["far"], self.bg),
+                                     sh_degree=isqrt(n) - 1, sh_layout=1, cov_stride=9, graph=self.graph)
+
+    def _copy_out(self, slot: int):
+        plan = self.plans[slot]
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(self.ev_done[slot])
+            self.out_c[slot].copy_(plan.color, non_blocking=True)
+            self.out_d[slot].copy_(plan.depth, non_blocking=True)
+            self.out_status[slot].copy_(plan.status, non_blocking=True)
+            self.ev_out[slot].record(self.s_d2h)
+
+    def _resolve(self, slot: int):
+        """Waits for the slot's results and looks at its status word; re-runs the step if the workspace overflowed."""
+        if not self.unresolved[slot]:
+            return
+        self.ev_out[slot].synchronize()
+        self.unresolved[slot] = False
+        st = self.out_status[slot]
+        if int(st[2]):
+            R = (int(st[0]) & 0xFFFFFFFF) | ((int(st[1]) & 0xFFFFFFFF) << 32)
+            plan = self.plans[slot]
+            self.s_run.synchronize()
+            with torch.cuda.stream(self.s_run):
+                plan.grow(R)                                  # new workspace + graph; the inputs are still in the slot
+                plan.run(self.s_run)
+                self.ev_done[slot].record(self.s_run)
+            self._copy_out(slot)
+            self.ev_out[slot].synchronize()
+            self.reruns += 1
+            if int(self.out_status[slot][2]):
+                raise _lib.FreeSplatB200Error("tile-instance workspace overflowed again after growing it")
 
     def submit(self, host: Dict[str, torch.Tensor]) -> int:
         """host: pinned CPU tensors named as KEYS (one scene, V target views).  Returns the slot index;
@@ -70,41 +121,43 @@ class HostRenderPipeline:
         slot = self.n % self.depth
         first_use = self.n < self.depth
         self.n += 1
+        self._resolve(slot)        # the step that used this slot `depth` submits ago (long finished in steady state)
+        d = self.dev_in[slot]
+        if d is not None and any(d[k].shape != host[k].shape for k in self.KEYS):
+            d = None               # a scene of another size: new buffers, new plan
+            for s in (self.s_h2d, self.s_run, self.s_d2h):
+                s.synchronize()
+            first_use = True
         with torch.cuda.stream(self.s_h2d):
             if not first_use:
                 self.s_h2d.wait_event(self.ev_in_free[slot])
-            if self.dev_in[slot] is None:
-                self.dev_in[slot] = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.dev) for k in self.KEYS}
+            if d is None:
+                d = self.dev_in[slot] = {k: torch.empty(host[k].shape, dtype=torch.float32, device=self.dev) for k in self.KEYS}
+                self.plans[slot] = None
             for k in self.KEYS:
-                self.dev_in[slot][k].copy_(host[k], non_blocking=True)
+                d[k].copy_(host[k], non_blocking=True)
             self.ev_copied[slot].record(self.s_h2d)
-        with torch.cuda.stream(self.s_run), torch.no_grad():
+        if self.plans[slot] is None:
+            with torch.cuda.stream(self.s_run):
+                self.plans[slot] = self._plan(slot, host)
+        with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(self.ev_copied[slot])
             if not first_use:
                 self.s_run.wait_event(self.ev_out[slot])          # previous results of this slot were copied out
-            d = self.dev_in[slot]
-            c, dp = decoder.render_views(d["extrinsics"], d["intrinsics"], d["near"], d["far"], (self.h, self.w), self.bg,
-                                         d["means"], d["covariances"], d["harmonics"], d["opacities"],
-                                         check_overflow="deferred" if self.n > self.depth else "sync")
-            self.status[slot] = rasterizer.last_deferred_status() if self.n > self.depth else None
+            self.plans[slot].run(self.s_run)
             self.ev_done[slot].record(self.s_run)
             self.ev_in_free[slot].record(self.s_run)
-        with torch.cuda.stream(self.s_d2h):
-            self.s_d2h.wait_event(self.ev_done[slot])
-            self.out_c[slot].copy_(c, non_blocking=True)
-            self.out_d[slot].copy_(dp, non_blocking=True)
-            c.record_stream(self.s_d2h); dp.record_stream(self.s_d2h)
-            self.ev_out[slot].record(self.s_d2h)
+        self._copy_out(slot)
+        self.unresolved[slot] = True
         return slot
 
     def wait(self, slot: int):
+        self._resolve(slot)
         self.ev_out[slot].synchronize()
-        st = self.status[slot]
-        if st is not None and int(st.cpu()[2]):
-            raise _lib.FreeSplatB200Error("tile-instance workspace overflowed in a deferred-check step; "
-                                          "re-submit the scene (the next sync-checked call grows the workspace)")
         return self.out_c[slot], self.out_d[slot]
 
     def drain(self):
+        for slot in range(self.depth):
+            self._resolve(slot)
         for s in (self.s_h2d, self.s_run, self.s_d2h):
             s.synchronize()

@@ -248,13 +248,18 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
                                              or any(p.requires_grad for p in gru.parameters()))
     fused_gru = (not need_grad) and (not torch.is_grad_enabled() or not any(p.requires_grad for p in gru.parameters())) \
         and _gru_has_reference_structure(gru) and F == gru.mlp_z[2].out_features
-    K_px = intrinsics.detach().clone()
-    K_px[:, :1, :] *= w                       # encoder_freesplat.py:445-447
-    K_px[:, 1:2, :] *= h
-    if E_inv is None:
-        E_inv = torch.linalg.inv(extrinsics.detach())  # extrinsic.inverse() (:454)
-    E_inv = f32(E_inv)
     ext16 = extrinsics.detach().reshape(V, 16).contiguous()
+    # per-view constants in ONE launch: pixel-space intrinsics (encoder_freesplat.py:445-447) and extrinsic.inverse() (:454)
+    # in the canonical arithmetic of oracle/ptf.py::canonical_inverse (fp64 cofactors, one rounding): the projected
+    # coordinates feed rounding / z-buffer decisions, so the public path is bit-reproducible.  `E_inv` overrides it (the
+    # golden tests pass the inverse the reference's LAPACK build produced).
+    K_px = torch.empty((V, 3, 3), dtype=torch.float32, device=dev)
+    E_can = torch.empty((V, 4, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(L.fs_ptf_view_setup(C.c_int32(V), C.c_int32(h), C.c_int32(w), C.c_void_p(ptr(ext16)),
+                                  C.c_void_p(ptr(intrinsics.detach())), C.c_void_p(ptr(E_can)), C.c_void_p(ptr(K_px)),
+                                  C.c_void_p(stream)), "fs_ptf_view_setup")
+    E_inv = E_can if E_inv is None else f32(E_inv)
     i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
     counts = torch.zeros((V + 1, 8), dtype=torch.int32, device=dev)
     counts[0, 0] = HW
@@ -280,7 +285,9 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
     # upper bounds, the kernels take N / M from the device counters); ONE host read at the end returns the final size
     sync_free = use_tc and (not need_grad) and timings is None and not return_debug and SYNC_FREE
     if sync_free:
-        gru_buf = torch.empty((HW, F), dtype=torch.float32, device=dev)
+        # matched pairs of step i: M <= N_i <= i * HW (with exact z-buffer ties several globals match one pixel, so HW is
+        # NOT a bound); the buffer and the GRU grid take the same upper bound as the state, CTAs beyond M_dev exit at once
+        gru_buf = torch.empty((min(cap, max(V - 1, 1) * HW), F), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             for i in range(1, V):
                 cin = counts[i - 1, 4:5]
@@ -288,7 +295,7 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
                 out_bufs = (nxt.feats, nxt.coords, nxt.dens, nxt.wemb, nxt.ext, nxt.depth)
                 a = _ptf_args(h, w, F, min(cap, i * HW), depth_thres, state, cin, view, scratch, counts[i], out_bufs)
                 check(L.fs_ptf_match(C.byref(a), C.c_void_p(stream)), "fs_ptf_match")
-                gru_tc(HW, pair_j, pair_p, state, feats[i], dens[i], wemb[i], stream, out=gru_buf, M_dev=counts[i, 2:3])
+                gru_tc(min(cap, i * HW), pair_j, pair_p, state, feats[i], dens[i], wemb[i], stream, out=gru_buf, M_dev=counts[i, 2:3])
                 a.gru_out = ptr(gru_buf)
                 check(L.fs_ptf_merge(C.byref(a), C.c_void_p(stream)), "fs_ptf_merge")
                 cur, nxt = nxt, cur

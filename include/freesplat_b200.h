@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FS_ABI_VERSION 1
+#define FS_ABI_VERSION 2
 #define FS_TILE 16            /* BLOCK_X == BLOCK_Y == 16 (upstream config.h) */
 #define FS_VIEW_FLOATS 48     /* floats per FsView record                     */
 #define FS_REC_FLOATS 12      /* floats per projected-Gaussian record         */
@@ -128,6 +128,7 @@ typedef struct FsRasterBwdArgs {
   /* upstream gradients */
   const float* dL_dcolor;      /* [V,3,H,W]                                      */
   const float* dL_ddepth;      /* [V,H,W] or NULL                                */
+  const float* dL_dalpha;      /* [V,H,W] or NULL: gradient w.r.t. the 4th return value (1 - final_T) */
   /* scratch: per-(view,Gaussian) screen-space gradients, zeroed by the call     */
   float* dL_dscreen;           /* [V,P,12]: mean2D.xy, conic.xyw, opacity, rgb, depth, pad */
   /* outputs (summed over the V views)                                           */
@@ -217,6 +218,11 @@ typedef struct FsPtfArgs {
 
 int fs_ptf_match(const FsPtfArgs* args, void* stream);
 int fs_ptf_merge(const FsPtfArgs* args, void* stream);
+/* Per-view constants of the fold for all V views in one launch: E_inv[v] = extrinsics[v]^-1 (encoder_freesplat.py:454;
+ * canonical arithmetic: fp64 cofactor expansion, one rounding to fp32) and the pixel-space intrinsics K_px[v]
+ * (rows 0 / 1 of the normalised K times W / H, :445-447).  extrinsics [V,16], intrinsics [V,9] -> E_inv [V,16], K_px [V,9]. */
+int fs_ptf_view_setup(int32_t V, int32_t H, int32_t W, const float* extrinsics, const float* intrinsics, float* E_inv,
+                      float* K_px, void* stream);
 /* Element-wise glue of the GRU (networks.py:201-214) for the M matched pairs; the Linear layers in between are
  * plain GEMMs run by the caller (cuBLAS).  A1 [M,2F+48] = [hidden | PE(v_dens,wemb) | input | PE(dens,v_wemb)],
  * U [M,2F+24] = [sigmoid(r_lin)*hidden | input | PE(dens,v_wemb)], out [M,F] = (1-z)*hidden + z*tanh(q_lin).          */
@@ -312,6 +318,17 @@ typedef struct FsDepthHeadArgs {
   float* weights_up;       /* [B,2h,2w] depth_weights    (upsample only)                             */
 } FsDepthHeadArgs;
 int fs_depth_head(const FsDepthHeadArgs* args, void* stream);
+
+/* ------------------------------------------------------------ CUDA graphs */
+/* A launch sequence whose arguments (pointers, sizes) do not change between steps -- e.g. fs_raster_forward on a static
+ * workspace -- can be recorded once and replayed with ONE cudaGraphLaunch: no host-side launch gaps between its kernels.
+ *   fs_graph_capture_begin(&s);  fs_raster_forward(&args, s); ...;  fs_graph_capture_end(s, &g);   (s is consumed)
+ *   fs_graph_launch(g, stream) per step;  fs_graph_destroy(g).
+ * (The reference has no counterpart: its op blocks on a D2H read of the instance count between its launches.)          */
+int fs_graph_capture_begin(void** stream_out);
+int fs_graph_capture_end(void* stream, void** graph_exec_out);
+int fs_graph_launch(void* graph_exec, void* stream);
+int fs_graph_destroy(void* graph_exec);
 
 int fs_abi_version(void);
 /* sizeof() of the argument structs as compiled (0: FsRasterFwdArgs, 1: FsRasterBwdArgs, 2: FsCostVolumeArgs, 3: FsPtfArgs,

@@ -34,6 +34,29 @@ def positional_encoding(x: np.ndarray, freqs: int = 6) -> np.ndarray:
     return out.reshape(pts.shape[:-1] + (pts.shape[-1] * 2,)).astype(F32)
 
 
+def canonical_inverse(E: np.ndarray) -> np.ndarray:
+    """extrinsic.inverse() (encoder_freesplat.py:454) in the canonical arithmetic of the CUDA path: cofactor expansion over
+    2x2 sub-determinants in float64 (plain multiplies / adds, no fma), one rounding to float32.  The reference's own result
+    depends on the LAPACK / cuSOLVER build it runs on (last-bit differences); tests that compare against reference golden
+    outputs pass the reference's inverse in explicitly (E_invs)."""
+    a = [np.float64(x) for x in np.asarray(E, dtype=F32).reshape(16)]
+    s0 = a[0] * a[5] - a[4] * a[1]; s1 = a[0] * a[6] - a[4] * a[2]; s2 = a[0] * a[7] - a[4] * a[3]
+    s3 = a[1] * a[6] - a[5] * a[2]; s4 = a[1] * a[7] - a[5] * a[3]; s5 = a[2] * a[7] - a[6] * a[3]
+    c5 = a[10] * a[15] - a[14] * a[11]; c4 = a[9] * a[15] - a[13] * a[11]; c3 = a[9] * a[14] - a[13] * a[10]
+    c2 = a[8] * a[15] - a[12] * a[11]; c1 = a[8] * a[14] - a[12] * a[10]; c0 = a[8] * a[13] - a[12] * a[9]
+    det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0
+    i = np.float64(1.0) / det
+    b = [(a[5] * c5 - a[6] * c4 + a[7] * c3) * i, (-a[1] * c5 + a[2] * c4 - a[3] * c3) * i,
+         (a[13] * s5 - a[14] * s4 + a[15] * s3) * i, (-a[9] * s5 + a[10] * s4 - a[11] * s3) * i,
+         (-a[4] * c5 + a[6] * c2 - a[7] * c1) * i, (a[0] * c5 - a[2] * c2 + a[3] * c1) * i,
+         (-a[12] * s5 + a[14] * s2 - a[15] * s1) * i, (a[8] * s5 - a[10] * s2 + a[11] * s1) * i,
+         (a[4] * c4 - a[5] * c2 + a[7] * c0) * i, (-a[0] * c4 + a[1] * c2 - a[3] * c0) * i,
+         (a[12] * s4 - a[13] * s2 + a[15] * s0) * i, (-a[8] * s4 + a[9] * s2 - a[11] * s0) * i,
+         (-a[4] * c3 + a[5] * c1 - a[6] * c0) * i, (a[0] * c3 - a[1] * c1 + a[2] * c0) * i,
+         (-a[12] * s3 + a[13] * s1 - a[14] * s0) * i, (a[8] * s3 - a[9] * s1 + a[10] * s0) * i]
+    return np.array(b, dtype=np.float64).astype(F32).reshape(4, 4)
+
+
 def project(coords: np.ndarray, E_inv: np.ndarray, fx, fy, cx, cy, h: int, w: int):
     """Appendix C steps 1-2.  coords [N,3] -> (pix [N] int64 (-1 if invalid), zeta [N] f32, valid [N])."""
     x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
@@ -72,7 +95,7 @@ def fuse(feats, coords, dens, wemb, depths, extrinsics, intrinsics, image_shape,
     for i in range(1, V):
         Kpx = intrinsics[i].copy()
         Kpx[0, :] *= F32(w); Kpx[1, :] *= F32(h)
-        E_inv = f32(np.linalg.inv(extrinsics[i].astype(np.float64))) if E_invs is None else f32(E_invs[i])
+        E_inv = canonical_inverse(extrinsics[i]) if E_invs is None else f32(E_invs[i])
         pix, zeta, valid = project(gX, E_inv, Kpx[0, 0], Kpx[1, 1], Kpx[0, 2], Kpx[1, 2], h, w)
         zbuf = np.full(HW, 1e4, F32)
         np.minimum.at(zbuf, pix[valid], zeta[valid])

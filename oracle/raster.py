@@ -113,7 +113,7 @@ def forward(*, H, W, tanfovx, tanfovy, bg, viewmatrix, projmatrix, campos, means
 
 def backward(st: RasterState, *, tanfovx, tanfovy, bg, viewmatrix, projmatrix, campos, means3D,
              dL_dcolor, dL_ddepth=None, shs=None, colors_precomp=None, scales=None, rotations=None,
-             sh_degree=0, scale_modifier=1.0) -> dict:
+             sh_degree=0, scale_modifier=1.0, dL_dalpha=None) -> dict:
     L = lib()
     P, H, W = st.P, st.H, st.W
     means3D = _f32(means3D); shs = _f32(shs); colors_precomp = _f32(colors_precomp)
@@ -121,7 +121,7 @@ def backward(st: RasterState, *, tanfovx, tanfovy, bg, viewmatrix, projmatrix, c
     M = 0 if shs is None else shs.shape[1]
     vm = _f32(viewmatrix).reshape(16); pm = _f32(projmatrix).reshape(16)
     cp = _f32(campos).reshape(3); bg = _f32(bg).reshape(3)
-    dL_dcolor = _f32(dL_dcolor); dL_ddepth = _f32(dL_ddepth)
+    dL_dcolor = _f32(dL_dcolor); dL_ddepth = _f32(dL_ddepth); dL_dalpha = _f32(dL_dalpha)
     g = dict(
         means2D=np.zeros((P, 3), np.float32), conic=np.zeros((P, 4), np.float32),
         opacities=np.zeros((P, 1), np.float32), colors=np.zeros((P, 3), np.float32),
@@ -137,7 +137,7 @@ def backward(st: RasterState, *, tanfovx, tanfovy, bg, viewmatrix, projmatrix, c
         _p(bg), _p(means3D), _p(shs), _p(colors_precomp), _p(scales), _p(rotations), _p(st.cov3D),
         _p(vm), _p(pm), _p(cp), _p(st.radii), _p(st.xy), _p(st.conic_opacity), _p(st.rgb), _p(st.depths),
         _p(st.clamped), _p(st.ranges), _p(pl), _p(st.final_T), _p(st.n_contrib),
-        _p(dL_dcolor), _p(dL_ddepth),
+        _p(dL_dcolor), _p(dL_ddepth), _p(dL_dalpha),
         _p(g["means2D"]), _p(g["conic"]), _p(g["opacities"]), _p(g["colors"]), _p(g["means3D"]),
         _p(g["cov3D"]), _p(g["shs"]), _p(g["scales"]), _p(g["rotations"]))
     return g

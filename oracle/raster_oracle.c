@@ -351,7 +351,7 @@ void fso_raster_backward(
     const int32_t* radii, const float* xy, const float* conic_opacity, const float* rgb,
     const float* depths, const int32_t* clamped, const uint32_t* ranges, const uint32_t* point_list,
     const float* final_T, const uint32_t* n_contrib,
-    const float* dL_dcolor /*3HW*/, const float* dL_ddepth /*HW or NULL*/,
+    const float* dL_dcolor /*3HW*/, const float* dL_ddepth /*HW or NULL*/, const float* dL_dalpha_out /*HW or NULL*/,
     /* out */ float* dL_dmean2D /*3P*/, float* dL_dconic /*4P: x,y,_,w*/, float* dL_dopacity /*P*/,
     float* dL_drgb /*3P*/, float* dL_dmean3D /*3P*/, float* dL_dcov3D /*6P*/, float* dL_dsh /*P*M*3*/,
     float* dL_dscale /*3P*/, float* dL_drot /*4P*/) {
@@ -413,6 +413,8 @@ void fso_raster_backward(
             last_alpha = alpha;
             float bg_dot = 0.f;
             for (int ch = 0; ch < 3; ch++) bg_dot += bg[ch] * dLp[ch];
+            /* extension: the op's 4th output 1 - final_T depends on alpha_j only through final_T, like the background term */
+            if (dL_dalpha_out) bg_dot -= dL_dalpha_out[pix];
             dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
             float dL_dG = co[3] * dL_dalpha;
             float gdx = G * dx, gdy = G * dy;

@@ -152,3 +152,56 @@ def load_export_ply():
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m.export_ply, captured
+
+
+def _jaxtyping_stub():
+    if "jaxtyping" in sys.modules:
+        jt = sys.modules["jaxtyping"]
+    else:
+        jt = types.ModuleType("jaxtyping")
+        sys.modules["jaxtyping"] = jt
+
+    class _Ann:
+        def __class_getitem__(cls, item):
+            return cls
+    for n in ("Float", "Bool", "Int64", "Int", "Shaped", "UInt8"):
+        if not hasattr(jt, n):
+            setattr(jt, n, _Ann)
+    return jt
+
+
+def load_decoder(rasterizer_module):
+    """Loads the reference's raster adapter and decoder UNMODIFIED from their files --
+    src/model/decoder/{cuda_splatting,decoder,decoder_splatting_cuda}.py, src/geometry/projection.py, src/model/types.py --
+    under a private package name, with `rasterizer_module` standing in for the (absent) third-party extension
+    `diff_gaussian_rasterization_depth` they import (cuda_splatting.py:5-8).  Returns (render_cuda, DecoderSplattingCUDA,
+    Gaussians)."""
+    _jaxtyping_stub()
+    sys.modules["diff_gaussian_rasterization_depth"] = rasterizer_module
+    root = "refdec"
+    def pkg(name):
+        m = types.ModuleType(name); m.__path__ = []
+        sys.modules[name] = m
+        return m
+    for name in (root, f"{root}.geometry", f"{root}.model", f"{root}.model.decoder", f"{root}.model.encoder",
+                 f"{root}.model.encoder.epipolar"):
+        pkg(name)
+    ds = types.ModuleType(f"{root}.dataset")
+    class DatasetCfg:          # src/dataset/__init__.py: only `background_color` is read on this path
+        def __init__(self, background_color):
+            self.background_color = background_color
+    ds.DatasetCfg = DatasetCfg
+    sys.modules[f"{root}.dataset"] = ds
+    def load(full, rel):
+        spec = importlib.util.spec_from_file_location(full, os.path.join(REF, "src", *rel.split("/")))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[full] = m
+        spec.loader.exec_module(m)
+        return m
+    load(f"{root}.geometry.projection", "geometry/projection.py")
+    load(f"{root}.model.encoder.epipolar.conversions", "model/encoder/epipolar/conversions.py")
+    ty = load(f"{root}.model.types", "model/types.py")
+    cs = load(f"{root}.model.decoder.cuda_splatting", "model/decoder/cuda_splatting.py")
+    load(f"{root}.model.decoder.decoder", "model/decoder/decoder.py")
+    dsc = load(f"{root}.model.decoder.decoder_splatting_cuda", "model/decoder/decoder_splatting_cuda.py")
+    return cs.render_cuda, dsc.DecoderSplattingCUDA, ty.Gaussians, DatasetCfg

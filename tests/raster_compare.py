@@ -104,7 +104,7 @@ def forward_ok(metrics: dict, max_bad_frac=2e-5, n_pixels=None) -> list:
     return fails
 
 
-def compare_backward(scene, st, views, dL_dcolor, dL_ddepth=None, bg=(0.0, 0.0, 0.0), scale_invariant=True) -> dict:
+def compare_backward(scene, st, views, dL_dcolor, dL_ddepth=None, bg=(0.0, 0.0, 0.0), scale_invariant=True, dL_dalpha=None) -> dict:
     """CUDA backward (summed over views) vs the sum of per-view oracle backwards, mapped back through
     the scene rescale (means*s, cov*s^2) the adapter applies."""
     dev = st.rec.device
@@ -113,7 +113,8 @@ def compare_backward(scene, st, views, dL_dcolor, dL_ddepth=None, bg=(0.0, 0.0, 
     shs = sc.harmonics.transpose(1, 2).contiguous()
     g = rasterizer.raster_backward_raw(st, sc.means, sc.opacities, dL_dcolor.to(dev), shs=shs,
                                        cov3D_precomp=sc.covariances[:, row, col].contiguous(),
-                                       dL_ddepth=None if dL_ddepth is None else dL_ddepth.to(dev))
+                                       dL_ddepth=None if dL_ddepth is None else dL_ddepth.to(dev),
+                                       dL_dalpha=None if dL_dalpha is None else dL_dalpha.to(dev))
     P = st.P
     want = dict(means3D=np.zeros((P, 3)), cov3D=np.zeros((P, 6)), shs=np.zeros(tuple(shs.shape)), opacities=np.zeros((P, 1)))
     want2d = []
@@ -125,29 +126,23 @@ def compare_backward(scene, st, views, dL_dcolor, dL_ddepth=None, bg=(0.0, 0.0, 
                              projmatrix=inp["projmatrix"], campos=inp["campos"], means3D=inp["means3D"],
                              dL_dcolor=dL_dcolor[v].cpu().numpy(),
                              dL_ddepth=None if dL_ddepth is None else dL_ddepth[v].cpu().numpy(),
+                             dL_dalpha=None if dL_dalpha is None else dL_dalpha[v].cpu().numpy(),
                              shs=inp["shs"], sh_degree=inp["sh_degree"])
         want["means3D"] += go["means3D"].astype(np.float64) * s
         want["cov3D"] += go["cov3D"].astype(np.float64) * s * s
         want["shs"] += go["shs"]; want["opacities"] += go["opacities"]
         want2d.append(go["means2D"])
+    from tests.helpers import grad_report
     out = {}
     got = dict(means3D=g["means3D"], cov3D=g["cov3D"], shs=g["shs"], opacities=g["opacities"])
     for k in want:
-        a = got[k].cpu().numpy().astype(np.float64); b = want[k]
-        scale = np.abs(b).max() + 1e-20
-        err = np.abs(a - b)
-        out[k] = dict(max_rel_to_max=float(err.max() / scale), scale=float(scale),
-                      frac_within_1e4=float((err <= 1e-4 * np.abs(b) + 1e-5 * scale).mean()))
-    a = g["means2D"].cpu().numpy().astype(np.float64); b = np.stack(want2d).astype(np.float64)
-    scale = np.abs(b).max() + 1e-20
-    out["means2D"] = dict(max_rel_to_max=float(np.abs(a - b).max() / scale), scale=float(scale),
-                          frac_within_1e4=float((np.abs(a - b) <= 1e-4 * np.abs(b) + 1e-5 * scale).mean()))
+        out[k] = grad_report(got[k].cpu().numpy(), want[k])
+    out["means2D"] = grad_report(g["means2D"].cpu().numpy(), np.stack(want2d))
     return out
 
 
 def backward_ok(metrics: dict) -> list:
-    fails = []
-    for k, m in metrics.items():
-        if m["max_rel_to_max"] > 2e-4 or m["frac_within_1e4"] < 0.9995:
-            fails.append(f"grad {k}: {m}")
-    return fails
+    """Element-wise criterion of tests.helpers.grad_report: |got - want| <= 1e-4 |want| + 1e-5 max|want|, at most 5e-4 of the
+    elements outside (counted in the report: a pixel whose alpha >= 1/255 or T < 1e-4 decision flips between MUFU.EX2 and libm
+    changes the gradient of the Gaussians that cover it), nothing further than 2e-4 of the maximum."""
+    return [f"grad {k}: {m}" for k, m in metrics.items() if not m["ok"]]

@@ -1,5 +1,5 @@
-"""GPU, BASELINE full sizes: size-independent properties (the oracles finish in seconds only at reduced sizes for
-the cost volume and PTF; the rasterizer is compared with its oracle at full size in test_raster_gpu.py)."""
+"""GPU, BASELINE full sizes: comparisons with the oracles where they finish in seconds (PTF config 4, raster backward
+config 3, one view of the cost volume) plus size-independent properties."""
 import numpy as np
 import pytest
 import torch
@@ -98,3 +98,38 @@ def test_ptf_full_size_config4_counts():
     assert torch.isfinite(F_).all() and torch.isfinite(X_).all() and torch.isfinite(E_).all() and (Z_ > 0).all()
     # density is conserved: every view pixel is either appended or added to (at least) one global Gaussian
     assert float(D_.double().sum()) >= float(torch.from_numpy(dens).double().sum()) * (1 - 1e-6)
+
+
+def test_ptf_full_size_config4_vs_oracle():
+    """BASELINE config 4 (10 views of 640x480) through the PUBLIC path (in-kernel canonical inverse, sync-free fold) against
+    the CPU restatement: order, coordinates, depths, extrinsics bit-exact; fused latents 1e-4."""
+    from freesplat_b200 import ptf
+    from oracle import ptf as optf
+    from tests.test_ptf_gpu import _gru
+    from tests.ptf_helpers import flat_inputs
+    V, h, w = 10, 480, 640
+    inp = synth.ptf_inputs(6, V, h, w)
+    feats, coords, dens, wemb, depths, ext, K, hw = flat_inputs(inp)
+    oF, oX, oE, oZ = optf.fuse(feats, coords, dens, wemb, depths, ext, K, hw, optf.torch_gru_fn(synth.gru_state(6)))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    with torch.no_grad():
+        F_, X_, E_, Z_ = ptf.fuse_views(_gru(6, DEV), t(feats), t(coords), t(dens), t(wemb), t(depths), t(ext), t(K), hw)
+    bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+    assert F_.shape[0] == oF.shape[0]
+    assert np.array_equal(bits(X_.cpu().numpy()), bits(oX))
+    assert np.array_equal(bits(Z_.cpu().numpy()), bits(oZ))
+    assert np.array_equal(bits(E_.cpu().numpy()), bits(oE))
+    np.testing.assert_allclose(F_.cpu().numpy(), oF, rtol=1e-4, atol=2e-5)
+
+
+def test_raster_backward_full_size_config3_vs_oracle():
+    """BASELINE config 3 raster size: P = 460 800 (3 context views, one Gaussian per pixel before fusion), 4 target views,
+    gradients of an MSE-like loss against the oracle's (fp64-accumulated) backward."""
+    from tests import raster_compare as rc
+    sc = synth.pixel_aligned_scene(seed=3, h=480, w=640, n_context=3, n_target=4, keep=460800)
+    st, views = rc.run_cuda(sc)
+    assert st.P == 460800 and st.V == 4
+    g = torch.Generator().manual_seed(21)
+    dC = torch.randn((st.V, 3, st.H, st.W), generator=g)
+    m = rc.compare_backward(sc, st, views, dC)
+    assert not rc.backward_ok(m), m

@@ -61,6 +61,7 @@ def test_backward_matches_autograd(seed, use_sr):
     H, W = inp["H"], inp["W"]
     dL_dcolor = torch.randn((3, H, W), generator=g, dtype=torch.float64)
     dL_ddepth = torch.randn((H, W), generator=g, dtype=torch.float64) * 0.3
+    dL_dalpha = torch.randn((H, W), generator=g, dtype=torch.float64) * 0.5
     scale = float(1.0 / sc.near[0])
     if use_sr:
         inp = dict(inp); inp.pop("cov3D_precomp")
@@ -70,7 +71,8 @@ def test_backward_matches_autograd(seed, use_sr):
         gr = oracle.backward(st, tanfovx=inp["tanfovx"], tanfovy=inp["tanfovy"], bg=inp["bg"],
                              viewmatrix=inp["viewmatrix"], projmatrix=inp["projmatrix"], campos=inp["campos"],
                              means3D=inp["means3D"], dL_dcolor=dL_dcolor.numpy(),
-                             dL_ddepth=dL_ddepth.numpy() if with_depth else None, shs=inp["shs"],
+                             dL_ddepth=dL_ddepth.numpy() if with_depth else None,
+                             dL_dalpha=dL_dalpha.numpy() if with_depth else None, shs=inp["shs"],
                              scales=inp.get("scales"), rotations=inp.get("rotations"), sh_degree=inp["sh_degree"])
         t = {k: torch.tensor(inp[k], dtype=torch.float64, requires_grad=True)
              for k in ("means3D", "opacities", "shs") }
@@ -81,13 +83,13 @@ def test_backward_matches_autograd(seed, use_sr):
         else:
             t["cov6"] = torch.tensor(inp["cov3D_precomp"], dtype=torch.float64, requires_grad=True)
             extra = dict(cov6=t["cov6"])
-        color, depth, _, _ = dense.render(H=H, W=W, tanfovx=inp["tanfovx"], tanfovy=inp["tanfovy"], bg=inp["bg"],
+        color, depth, fT, _ = dense.render(H=H, W=W, tanfovx=inp["tanfovx"], tanfovy=inp["tanfovy"], bg=inp["bg"],
                                           viewmatrix=inp["viewmatrix"], projmatrix=inp["projmatrix"],
                                           campos=inp["campos"], means3D=t["means3D"], opacities=t["opacities"],
                                           shs=t["shs"], sh_degree=inp["sh_degree"], **extra)
         loss = (color * dL_dcolor).sum()
         if with_depth:
-            loss = loss + (depth * dL_ddepth).sum()
+            loss = loss + (depth * dL_ddepth).sum() + ((1.0 - fT) * dL_dalpha).sum()   # 4th output of the op: 1 - final_T
         loss.backward()
         pairs = [("means3D", gr["means3D"], t["means3D"].grad), ("opacities", gr["opacities"][:, 0], t["opacities"].grad),
                  ("shs", gr["shs"], t["shs"].grad)]

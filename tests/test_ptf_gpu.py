@@ -86,7 +86,10 @@ def test_vs_oracle_medium_and_reference_signature():
     for got, want in ((X_, oX), (Z_, oZ), (E_, oE), (D_, oD), (W_, oW)):
         assert np.array_equal(bits(got.cpu().numpy()), bits(want))
     np.testing.assert_allclose(F_.cpu().numpy(), oF, rtol=1e-4, atol=2e-5)
-    # the reference's call signature (encoder_freesplat.py:364-368)
+    # the reference's call signature (encoder_freesplat.py:364-368): the PUBLIC path computes extrinsic.inverse() itself, in the
+    # canonical arithmetic (fs_ptf_view_setup == oracle.canonical_inverse) -> bit-exact against the oracle's default inverse
+    (cF, cX, cE, cZ, cD, cW), _ = optf.fuse(feats, coords, dens, wemb, depths, ext, K, hw, optf.torch_gru_fn(synth.gru_state(seed)),
+                                            return_steps=True)
     dev = "cuda:0"
     self = SimpleNamespace(gru=_gru(seed, dev))
     mv = lambda v: [x.to(dev) for x in v] if isinstance(v, list) else (v.to(dev) if isinstance(v, torch.Tensor) else v)
@@ -94,7 +97,35 @@ def test_vs_oracle_medium_and_reference_signature():
         r = ptf.fuse_gaussians(self, *[mv(inp[k]) for k in ("gaussians", "coords", "densities", "weight_emb", "depths",
                                                             "extrinsics", "intrinsics")], inp["image_shape"])
     assert r[0].shape[0] == 1 and r[0].shape[2] == 64 and r[1].shape[-1] == 3 and r[2].shape[-2:] == (4, 4) and r[3].dim() == 2
-    assert abs(r[0].shape[1] - F_.shape[0]) <= 8     # E_inv computed on the GPU here: a few rounding ties may flip
+    assert r[0].shape[1] == cF.shape[0]
+    for got, want in ((r[1][0], cX), (r[3][0], cZ), (r[2][0], cE)):
+        assert np.array_equal(bits(got.cpu().numpy()), bits(want))
+    np.testing.assert_allclose(r[0][0].cpu().numpy(), cF, rtol=1e-4, atol=2e-5)
+
+
+def test_canonical_inverse_kernel_is_bit_exact():
+    """fs_ptf_view_setup: E^-1 (fp64 cofactors, one rounding) and the pixel-space intrinsics, against the oracle's restatement."""
+    import ctypes as C
+    from freesplat_b200 import _lib
+    from oracle import ptf as optf
+    g = torch.Generator().manual_seed(0)
+    V, h, w = 37, 480, 640
+    ext = synth.camera_path(V, spacing=0.31)
+    ext[:, :3, :3] = ext[:, :3, :3] + 0.01 * torch.randn((V, 3, 3), generator=g)     # not exactly rigid
+    K = synth.intrinsics(V)
+    dev = "cuda:0"
+    e, k = ext.to(dev).contiguous(), K.to(dev).contiguous()
+    Ei, Kp = torch.empty((V, 4, 4), device=dev), torch.empty((V, 3, 3), device=dev)
+    L = _lib.lib()
+    _lib.check(L.fs_ptf_view_setup(C.c_int32(V), C.c_int32(h), C.c_int32(w), C.c_void_p(e.data_ptr()), C.c_void_p(k.data_ptr()),
+                                   C.c_void_p(Ei.data_ptr()), C.c_void_p(Kp.data_ptr()), C.c_void_p(0)), "fs_ptf_view_setup")
+    torch.cuda.synchronize()
+    want = np.stack([optf.canonical_inverse(ext[v].numpy()) for v in range(V)])
+    assert np.array_equal(bits(Ei.cpu().numpy()), bits(want))
+    kp = K.numpy().copy(); kp[:, 0, :] *= np.float32(w); kp[:, 1, :] *= np.float32(h)
+    assert np.array_equal(bits(Kp.cpu().numpy()), bits(kp))
+    # and it is an inverse: within fp32 rounding of LAPACK's
+    assert np.abs(want - np.linalg.inv(ext.numpy().astype(np.float64))).max() < 1e-6
 
 
 def test_no_match_and_single_view():
@@ -157,3 +188,43 @@ def test_gru_paths_agree():
     assert outs["tc"].shape == want.shape
     np.testing.assert_allclose(outs["cublas"], want, rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(outs["tc"], want, rtol=1e-4, atol=2e-5)
+
+
+def test_mid_size_reference_golden_forward_and_backward():
+    """120x160, 4 views: outputs and autograd gradients of the REFERENCE's own fuse_gaussians (tests/golden/mid_ptf_v4.npz;
+    the reference's LAPACK inverse is passed in, as stored).  Order / coordinates / depths / extrinsics bit-exact."""
+    from freesplat_b200 import ptf
+    from tests import mid_golden
+    from tests.helpers import grad_report
+    z, inp, (wF, wX, wE, wZ), (seed, V, h, w, S, N) = mid_golden.ptf()
+    feats, coords, dens, wemb, depths, ext, K, hw = flat_inputs(inp)
+    dev = "cuda:0"
+    t = lambda a, g=True: torch.from_numpy(np.ascontiguousarray(a)).to(dev).requires_grad_(g)
+    with torch.no_grad():
+        F_, X_, E_, Z_ = ptf.fuse_views(_gru(seed, dev), t(feats, False), t(coords, False), t(dens, False), t(wemb, False),
+                                        t(depths, False), t(ext, False), t(K, False), hw, E_inv=t(z["E_inv"], False))
+    assert F_.shape[0] == N
+    assert np.array_equal(bits(X_.cpu().numpy()), bits(z["out_coords"])) and np.array_equal(bits(Z_.cpu().numpy()), bits(z["out_depths"]))
+    assert np.array_equal(bits(E_.cpu().numpy()[::S]), bits(z["out_ext_sub"]))
+    assert abs(float(E_.double().sum()) - float(z["out_ext_sum"])) < 1e-6 * N
+    np.testing.assert_allclose(F_.cpu().numpy()[::S], z["out_feats_sub"], rtol=1e-4, atol=2e-5)
+    # training path: gradients against the reference's own autograd
+    tf, tx, td, tw, tz = t(feats), t(coords), t(dens), t(wemb), t(depths)
+    gru = _gru(seed, dev)
+    F_, X_, E_, Z_ = ptf.fuse_views(gru, tf, tx, td, tw, tz, t(ext, False), t(K, False), hw, E_inv=t(z["E_inv"], False))
+    ((F_ * wF.to(dev)).sum() + (X_ * wX.to(dev)).sum() + (E_ * wE.to(dev)).sum() + (Z_ * wZ.to(dev)).sum()).backward()
+    pairs = [("feats", tf.grad[:, ::S], z["g_in_feats_sub"]), ("coords", tx.grad, z["g_in_coords"]), ("dens", td.grad, z["g_in_dens"]),
+             ("wemb", tw.grad, z["g_in_wemb"]), ("depths", tz.grad, z["g_in_depths"])]
+    pairs += [("gru." + n, p.grad, z["g_gru." + n]) for n, p in gru.named_parameters()]
+    report, bad = [], []
+    for name, got, want in pairs:
+        assert got is not None, name
+        rep = grad_report(got.cpu().numpy(), want)
+        report.append((name, rep))
+        if not rep["ok"]:
+            bad.append((name, rep))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "ptf_mid_golden_report.txt"), "w") as f:
+            f.write("\n".join(map(str, report)))
+    assert not bad, bad

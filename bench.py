@@ -9,18 +9,28 @@ one scene of 307 200 pixel-aligned Gaussians (SH degree 2, precomputed covarianc
 T=3 target views (assets/evaluation_index_scannet_2views.json holds 3 targets per scene) at 640x480.
 A step = one pass of the hot path over that batch: preprocess -> tile binning -> render, all views.
 
-value  : views/s with the scene and camera records resident in HBM (CUDA events, per-step, L2 flushed
-         between steps by writing a 256 MiB buffer outside the timed events).
-e2e    : the same metric through the public call a user makes (`freesplat_b200.decoder.render_views`)
-         starting from PINNED HOST tensors: H2D of Gaussians + cameras, render, D2H of colour + depth.
+value  : views/s with the scene resident in HBM: one CUDA-graph launch of the step per iteration
+         (rasterizer.RasterPlan -> fs_graph_launch), per-step CUDA events, L2 flushed between steps by a
+         256 MiB write outside the events.  `per_rank_ms` carries every rank's min / median / max step.
+api    : the same steps through the public device-resident call (`decoder.render_views`, default
+         deferred overflow check: no host sync), K calls bracketed by two events: host overhead included.
+e2e    : the same metric host-to-host through `pipeline.HostRenderPipeline`: H2D of Gaussians + cameras
+         from pinned memory, render, D2H of colour + depth, every step.  With N > 1 ranks the Gaussian set
+         (the same scene for all ranks: SURVEY 8e, target views shard over GPUs) is uploaded ONCE in total
+         -- each rank copies its 1/N slice over PCIe -- and replicated over NVLink by in-place all-gathers.
+ops    : (N = 1) the other operators of the path at BASELINE config 3 / 4 sizes, each with its own roofline
+         line and CPU baseline: cost volume fwd / bwd (tensor pipe), PTF folds (HBM), raster fwd+bwd.
+config5: (N > 1) BASELINE config 5: 10 context views -> cross-view candidate exchange over NCCL -> PTF fold
+         (replicated) -> 18 target views sharded over the ranks.
 Multi-GPU: target views shard over ranks (each rank renders its own T views of the replicated
-Gaussian set; no data-path collective) -> weak scaling; value = all views / max-over-ranks time.
+Gaussian set; no data-path collective in `value`) -> weak scaling; value = all views / max-over-ranks time.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -34,72 +44,114 @@ WORKLOAD = f"scannet_2views_{W}x{H}_P{P}_targets{T_VIEWS}_raster_fwd"
 METRIC = "rendered views/sec @640x480"
 
 
+def base_config(world: int) -> dict:
+    """The `config` object BOTH arms print (the driver compares them key by key)."""
+    return {"workload": WORKLOAD, "views_per_step_per_gpu": T_VIEWS, "gaussians": P, "image": [H, W], "sh_degree": 2,
+            "l2": "flushed between steps (256 MiB write)", "parallelism": f"view-sharded x{world}"}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return d, "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
 def _ncu_traffic(kernel_substr: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the committed ncu export (profiles/), bytes per launch."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the newest committed ncu export (profiles/), bytes per launch."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_fwd_step_ncu_raw.csv")
-    try:
-        rows = list(csv.reader(open(path)))
-        hdr, units = rows[0], rows[1]
-        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        for r in rows[2:]:
-            if kernel_substr in r[ik]:
-                return float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]]
-    except Exception:
-        return None
-    return None
+    for name in ("r2_fwd_step_ncu_raw.csv", "r1_fwd_step_ncu_raw.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for r in rows[2:]:
+                if kernel_substr in r[ik]:
+                    return float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]], f"profiles/{name}"
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled every 100 ms while the timed regions run: NVML in-process (the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; a forked nvidia-smi per rank costs the host a core
+    each, which at 8 ranks showed up inside the timed region), nvidia-smi as the fallback."""
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stop_flag, self.thread, self.mode = index, [], None, False, None, None
+        self.mx = None
+
+    def _phys_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._phys_index())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        self.rows.append((sm, [n for n, b in names.items() if bits & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.1)
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
                                           str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            self.mode = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[0])); mx = float(r[1])
-                for n, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self.mx = float(r[1])
+                self.rows.append((float(r[0]), [n for n, v in zip(names, r[2:6]) if v.lower().startswith("active")]))
             except Exception:
                 continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+    def stop(self) -> dict:
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source available"]}
+        time.sleep(0.15)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({n for r in self.rows for n in r[1]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": reasons, "samples": len(sm),
+                "source": self.mode}
 
 
 def host_threads() -> int:
@@ -127,19 +179,41 @@ def make_scene(rank: int):
     return sc
 
 
-def cpu_reference_views_per_s(sc, n_views: int, repeats: int):
-    """Times the CPU restatement of the reference rasterizer (oracle/raster_oracle.c, all host cores)."""
-    from oracle import raster as oracle
-    from tests.helpers import view_inputs
-    inps = [view_inputs(sc, v)[0] for v in range(n_views)]
+def oracle_view_inputs(sc, i: int):
+    """Oracle inputs of target view i prepared the way the reference adapter prepares the rasterizer call
+    (cuda_splatting.py:64-127: scene rescale by 1/near, transposed matrices, [P,M,3] harmonics, upper-triangle covariances)."""
+    import torch
+    from freesplat_b200 import decoder
+    V = sc.extrinsics.shape[0]
+    views, _ = decoder.camera_records(sc.extrinsics, sc.intrinsics, sc.near, sc.far, torch.zeros((V, 3)), True)
+    rec = views[i]
+    s = rec[40]
+    iu = torch.triu_indices(3, 3)
+    d_sh = sc.harmonics.shape[-1]
+    return dict(H=sc.image_shape[0], W=sc.image_shape[1], tanfovx=float(rec[38]), tanfovy=float(rec[39]), bg=rec[35:38].numpy(),
+                viewmatrix=rec[0:16].numpy(), projmatrix=rec[16:32].numpy(), campos=rec[32:35].numpy(), means3D=(sc.means * s).numpy(),
+                opacities=sc.opacities.numpy(), shs=sc.harmonics.transpose(1, 2).contiguous().numpy(),
+                cov3D_precomp=(sc.covariances * (s * s))[:, iu[0], iu[1]].contiguous().numpy(), sh_degree=int(round(d_sh ** 0.5)) - 1)
+
+
+def _pick_oracle_threads(oracle, inp):
+    # torchrun exports OMP_NUM_THREADS=1; pick the best of {all allowed threads, half of them (SMT siblings)}
     best = None
     for n in sorted({host_threads(), max(1, host_threads() // 2)}, reverse=True):
         oracle.set_num_threads(n)
-        oracle.forward(**inps[0])  # warm (page in, OpenMP pool)
-        t0 = time.perf_counter(); oracle.forward(**inps[0]); dt = time.perf_counter() - t0
+        oracle.forward(**inp)                      # warm (page in, OpenMP pool)
+        t0 = time.perf_counter(); oracle.forward(**inp); dt = time.perf_counter() - t0
         if best is None or dt < best[1]:
             best = (n, dt)
     oracle.set_num_threads(best[0])
+    return best[0]
+
+
+def cpu_reference_views_per_s(sc, n_views: int, repeats: int):
+    """Times the CPU restatement of the reference rasterizer (oracle/raster_oracle.c, all host cores)."""
+    from oracle import raster as oracle
+    inps = [oracle_view_inputs(sc, v) for v in range(n_views)]
+    _pick_oracle_threads(oracle, inps[0])
     t0 = time.perf_counter()
     for _ in range(repeats):
         for inp in inps:
@@ -148,61 +222,206 @@ def cpu_reference_views_per_s(sc, n_views: int, repeats: int):
     return n_views * repeats / dt, oracle.num_threads(), dt
 
 
-def ops_section(dev):
-    """Cost volume and PTF at BASELINE config-3 sizes: GPU time of the product kernels next to the CPU restatements
-    (oracle/, the cpu_baseline leg) on bounded samples, scaled to the full size (the sample is stated)."""
+class PlainGRU:
+    """networks.py:188-214 by name only: the module tree fs_ptf_gru reads its weights from."""
+
+    def __new__(cls, state, dev):
+        import torch
+        mk = lambda din: torch.nn.Sequential(torch.nn.Linear(din, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64))
+        g = torch.nn.Module()
+        g.mlp_z, g.mlp_r, g.mlp_n = mk(176), mk(176), mk(152)
+        g.load_state_dict(state)
+        return g.to(dev)
+
+
+def _flat_ptf(inp):
+    """synth.ptf_inputs (encoder-shaped) -> flat per-view tensors (feats [V,HW,F], coords [V,HW,3], dens, wemb, depths [V,HW])."""
+    V = inp["gaussians"][0].shape[1]
+    return (inp["gaussians"][0][0], inp["coords"][0][0, :, :, 0, 0, :], inp["densities"][0, :, :, 0, 0], inp["weight_emb"][0, :, :, 0, 0],
+            inp["depths"].reshape(V, -1), inp["extrinsics"][0], inp["intrinsics"][0], tuple(inp["depths"].shape[-2:]))
+
+
+def gpu_ms(fn, n=5, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def ops_section(dev, peaks):
+    """The other operators of the path at BASELINE config 3 / 4 sizes: device time of the product kernels, their roofline line
+    (SURVEY 8d byte / flop counts), and CPU baselines: the oracle port timed here on bounded samples (stated), and the
+    reference's OWN PyTorch code timed on a full unit of work in the build container (profiles/r2_reference_cpu_timings.json:
+    /root/reference does not exist on this box)."""
     import numpy as np
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from freesplat_b200 import ptf, synth
+    from freesplat_b200 import decoder, ptf, synth
     from freesplat_b200.cost_volume import AVGFeatureVolumeManager
     from oracle import cost_volume as ocv, ptf as optf
-    from ptf_helpers import flat_inputs, torch_inverses
-    from test_ptf_gpu import GRU
     out = {}
     torch.set_num_threads(host_threads())
+    hbm, tf = float(peaks["hbm_gbs"]), float(peaks.get("bf16_tflops", 1590.0))
+    try:
+        ref_cpu = json.load(open(os.path.join(ROOT, "profiles", "r2_reference_cpu_timings.json")))
+    except Exception:
+        ref_cpu = {}
 
-    def gpu_ms(fn, n=5):
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record(); torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
+    # ---- cost volume: config 3 = 3 reference views, K = 2 ; config 4 = 10 views, K = 8 ; 48 x 120 x 160, D = 128 ----
+    Hf, Wf, D, C = 120, 160, 128, 48
+    for tag, V, K in (("cfg3", 3, 2), ("cfg4", 10, 8)):
+        inp = synth.cost_volume_inputs(0, V, K, C, Hf, Wf)
+        mlp = synth.cost_volume_mlp(0)
+        m = AVGFeatureVolumeManager(Hf, Wf, num_depth_bins=D, matching_dim_size=C).to(dev)
+        with torch.no_grad():
+            for p_, w_ in zip([m.mlp.net[0].weight, m.mlp.net[0].bias, m.mlp.net[2].weight, m.mlp.net[2].bias, m.mlp.net[4].weight,
+                               m.mlp.net[4].bias], mlp):
+                p_.copy_(w_)
+        ginp = {k: v.to(dev) for k, v in inp.items()}
+        with torch.no_grad():
+            f_ms = gpu_ms(lambda: m(**ginp))
+        rows = V * D * Hf * Wf
+        flops = rows * (2 * 2624 + K * (2 * 4 * C + 2 * C))             # SURVEY 8d
+        tflops_tensor = rows * 2 * 2624 * 3 / (f_ms * 1e-3) / 1e12      # 3xTF32: three tensor-core products per useful one
+        nbytes = V * ((1 + K) * C * Hf * Wf * 4 + D * Hf * Wf * 4)
+        e = {"gpu_ms": f_ms, "views": V, "K": K, "useful_tflops": flops / (f_ms * 1e-3) / 1e12,
+             "roofline": {"bound": "tensor", "achieved": tflops_tensor, "peak": tf / 2, "unit": "TFLOP/s",
+                          "frac": tflops_tensor / (tf / 2), "note": "issued 3xTF32 MLP flops vs the tf32 dense peak (= half the measured bf16 "
+                          "peak); the gather, not the tensor pipe, bounds this kernel (DESIGN 4)"},
+             "hbm_gbs": nbytes / (f_ms * 1e-3) / 1e9}
+        if tag == "cfg3":
+            cur = ginp["cur_feats"].clone().requires_grad_(True); src = ginp["src_feats"].clone().requires_grad_(True)
+            gw = torch.randn((V, D, Hf, Wf), device=dev)
 
-    # ---- cost volume: 3 reference views, K = 2, 48 x 120 x 160, D = 128 ----
-    V, K, Hf, Wf, D = 3, 2, 120, 160, 128
-    inp = synth.cost_volume_inputs(0, V, K, 48, Hf, Wf)
-    mlp = synth.cost_volume_mlp(0)
-    m = AVGFeatureVolumeManager(Hf, Wf, num_depth_bins=D, matching_dim_size=48).to(dev)
-    ginp = {k: v.to(dev) for k, v in inp.items()}
+            def fb():
+                cur.grad = None; src.grad = None
+                m(**{**ginp, "cur_feats": cur, "src_feats": src}).backward(gw)
+            e["fwd_bwd_gpu_ms"] = gpu_ms(fb, n=3)
+            Dsub = 32                                                  # CPU sample: 1 reference view, 32 of the 128 planes
+            sub = {k: v[:1] for k, v in inp.items() if k not in ("min_depth", "max_depth")}
+            t0 = time.perf_counter()
+            ocv.forward(sub["cur_feats"], sub["src_feats"], sub["src_extrinsics"], sub["src_Ks"], sub["cur_invK"], inp["min_depth"],
+                        inp["max_depth"], mlp, Dsub, plane_chunk=8)
+            c_s = time.perf_counter() - t0
+            e["cpu_baseline"] = {"kind": "port", "ms_per_view": c_s * 1e3 * (D / Dsub), "cores": host_threads(),
+                                 "sample": f"1 reference view, {Dsub} of {D} planes ({c_s:.1f} s), scaled by {D // Dsub}"}
+            if "cost_volume_fwd_one_view_K2_D128_120x160_s" in ref_cpu:
+                e["reference_cpu"] = {"kind": "reference (its own PyTorch code, pre-timed in the build container)",
+                                      "ms_per_view": ref_cpu["cost_volume_fwd_one_view_K2_D128_120x160_s"] * 1e3,
+                                      "fwd_bwd_ms_per_view": ref_cpu.get("cost_volume_fwd_bwd_one_view_s", 0) * 1e3,
+                                      "cores": ref_cpu.get("host_threads"), "sample": "one full reference view, all 128 planes, unscaled"}
+        out[f"cost_volume_{tag}_fwd"] = e
+        del m, ginp
+
+    # ---- PTF: 3 views (config 3) and 10 views (config 4) of 640 x 480 ----
+    state = synth.gru_state(0)
+    gru = PlainGRU(state, dev)
+    for tag, V in (("cfg3_3views", 3), ("cfg4_10views", 10)):
+        feats, coords, dens, wemb, depths, ext, Kn, hw = _flat_ptf(synth.ptf_inputs(0, V, H, W))
+        gargs = [x.to(dev).contiguous() for x in (feats, coords, dens, wemb, depths, ext, Kn)]
+        with torch.no_grad():
+            res = ptf.fuse_views(gru, *gargs, hw)
+            g_ms = gpu_ms(lambda: ptf.fuse_views(gru, *gargs, hw), n=3)
+        N_out = int(res[0].shape[0])
+        HW = H * W
+        # SURVEY 8d per merge step: 16 N + 8 HW + 344 N_out + 280 HW; N grows from HW to N_out: bounded below by the inputs read
+        # once and the final state written once
+        nbytes = V * HW * 280 + N_out * 344
+        e = {"gpu_ms": g_ms, "views": V, "N_out": N_out,
+             "roofline": {"bound": "hbm", "achieved": nbytes / (g_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                          "frac": nbytes / (g_ms * 1e-3) / 1e9 / hbm,
+                          "note": "algorithmic bytes = V*HW*280 (candidates read once) + 344*N_out (state written once); the GRU of the "
+                                  "matched pairs (tensor cores) is inside the time"}}
+        if V == 3:
+            np_args = [x.numpy() for x in (feats, coords, dens, wemb, depths, ext, Kn)]
+            t0 = time.perf_counter()
+            optf.fuse(*np_args, hw, optf.torch_gru_fn(state))
+            c_s = time.perf_counter() - t0
+            e["cpu_baseline"] = {"kind": "port", "ms": c_s * 1e3, "cores": host_threads(), "sample": f"the full 3-view fold ({c_s:.1f} s)"}
+            if "ptf_3views_640x480_s" in ref_cpu:
+                e["reference_cpu"] = {"kind": "reference (its own PyTorch code, pre-timed in the build container)",
+                                      "ms": ref_cpu["ptf_3views_640x480_s"] * 1e3, "cores": ref_cpu.get("host_threads"),
+                                      "sample": "the full 3-view fold, unscaled"}
+        out[f"ptf_{tag}"] = e
+        del gargs, res
+
+    # ---- raster forward + backward, config 3: P = 460 800, 4 target views ----
+    sc = synth.pixel_aligned_scene(seed=3, h=H, w=W, n_context=3, n_target=4, keep=460800).to(dev)
+    bg = torch.zeros((4, 3), device=dev)
+    leaves = [t.clone().requires_grad_(True) for t in (sc.means, sc.covariances, sc.harmonics, sc.opacities)]
+    gC = torch.randn((4, 3, H, W), device=dev)
+
+    def train_step():
+        for t in leaves:
+            t.grad = None
+        c, _ = decoder.render_views(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (H, W), bg, *leaves)
+        c.backward(gC)
     with torch.no_grad():
-        g_ms = gpu_ms(lambda: m(**ginp))
-    Dsub = 32                                                  # CPU sample: 1 reference view, 32 of the 128 planes
-    sub = {k: v[:1] for k, v in inp.items() if k not in ("min_depth", "max_depth")}
-    t0 = time.perf_counter()
-    ocv.forward(sub["cur_feats"], sub["src_feats"], sub["src_extrinsics"], sub["src_Ks"], sub["cur_invK"], inp["min_depth"],
-                inp["max_depth"], mlp, Dsub, plane_chunk=8)
-    c_s = time.perf_counter() - t0
-    out["cost_volume_cfg3_fwd"] = {"gpu_ms": g_ms, "cpu_port_ms": c_s * 1e3 * (D / Dsub) * V, "cores": host_threads(),
-                                   "sample": f"1 of {V} reference views, {Dsub} of {D} planes ({c_s:.1f} s), scaled"}
-    # ---- PTF: 3 views of 640 x 480 ----
-    pin = synth.ptf_inputs(0, 3, 480, 640)
-    feats, coords, dens, wemb, depths, ext, Kn, hw = flat_inputs(pin)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    gru = GRU(); gru.load_state_dict(synth.gru_state(0)); gru = gru.to(dev)
-    gargs = [t(x) for x in (feats, coords, dens, wemb, depths, ext, Kn)]
-    with torch.no_grad():
-        g_ms = gpu_ms(lambda: ptf.fuse_views(gru, *gargs, hw), n=3)
-    t0 = time.perf_counter()
-    optf.fuse(feats, coords, dens, wemb, depths, ext, Kn, hw, optf.torch_gru_fn(synth.gru_state(0)), E_invs=torch_inverses(ext))
-    c_s = time.perf_counter() - t0
-    out["ptf_3views_640x480"] = {"gpu_ms": g_ms, "cpu_port_ms": c_s * 1e3, "cores": host_threads(),
-                                 "sample": f"the full 3-view fold ({c_s:.1f} s)"}
+        f_ms = gpu_ms(lambda: decoder.render_views(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (H, W), bg, sc.means, sc.covariances,
+                                                   sc.harmonics, sc.opacities), n=5)
+    out["raster_cfg3_P460800_4views"] = {"fwd_gpu_ms": f_ms, "fwd_bwd_gpu_ms": gpu_ms(train_step, n=5)}
     return out
+
+
+def config5_section(dev, rank, world, steps=3):
+    """BASELINE config 5: 10 context views (owned round-robin by the ranks) -> cross-view exchange of the per-view candidates
+    (70 floats per pixel) straight into the [V,HW,...] buffers the PTF kernels read (parallel.ViewExchange: one broadcast per
+    view and tensor on a side stream; fold step i waits only for view i) -> PTF fold, replicated -> 18 target views sharded over
+    the ranks.  Device-timed per stage, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from freesplat_b200 import decoder, parallel, ptf, synth
+    V, T = 10, 18
+    feats, coords, dens, wemb, depths, ext, Kn, hw = _flat_ptf(synth.ptf_inputs(0, V, H, W))
+    mine = parallel.shard_views(V, rank, world)
+    local = [x[mine].to(dev).contiguous() for x in (feats, coords, dens, wemb, depths)]
+    ext_d, K_d = ext.to(dev), Kn.to(dev)
+    gru = PlainGRU(synth.gru_state(0), dev)
+    tgt_ext = synth.camera_path(T, spacing=0.05, t0=0.1).to(dev)
+    tgt_K = synth.intrinsics(T).to(dev)
+    near = torch.full((T,), synth.NEAR, device=dev); far = torch.full((T,), synth.FAR, device=dev)
+    my_t = parallel.shard_views(T, rank, world)
+    sel = torch.tensor(my_t, dtype=torch.long, device=dev)
+    bg = torch.zeros((len(my_t), 3), device=dev)
+    ex = parallel.ViewExchange(V, H * W, 64, dev)
+    rows = []
+    N = 0
+    for it in range(steps + 1):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            ev[0].record()
+            full = ex.exchange(*local)                                 # enqueues the broadcasts on the side stream
+            ev[1].record()
+            F_, X_, E_, Z_ = ptf.fuse_views(gru, *full, ext_d, K_d, hw, view_ready=ex.ready_events)
+            ev[2].record()
+            N = int(F_.shape[0])
+            # a fixed Gaussian head stands in for the (out-of-scope) decoder MLP: means = fused coordinates
+            cov = torch.eye(3, device=dev)[None].expand(N, 3, 3).contiguous() * 4e-4
+            sh = torch.zeros((N, 3, 9), device=dev); sh[:, :, 0] = F_[:, :3]
+            op = torch.full((N,), 0.5, device=dev)
+            if my_t:
+                decoder.render_views(tgt_ext[sel], tgt_K[sel], near[sel], far[sel], (H, W), bg, X_, cov, sh, op)
+            ev[3].record()
+        torch.cuda.synchronize()
+        if it:
+            rows.append([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), ev[0].elapsed_time(ev[3])])
+    t = torch.tensor(rows, dtype=torch.float64, device=dev).median(0).values
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gather_bytes = (V - len(mine)) * H * W * 70 * 4
+    return {"workload": f"replica_10views_{W}x{H}_ptf_then_{T}_targets_sharded_x{world}", "fused_gaussians": N,
+            "exchange_enqueue_ms": float(t[0]), "ptf_fold_ms": float(t[1]), "render_share_ms": float(t[2]), "total_ms": float(t[3]),
+            "exchange_bytes_received_per_rank": gather_bytes, "targets_per_rank": len(my_t),
+            "note": "exchange overlaps the fold (step i waits for view i only): its exposed time is inside ptf_fold_ms; "
+                    "max over ranks, median of %d steps" % steps}
 
 
 def run_reference(args):
@@ -211,18 +430,8 @@ def run_reference(args):
         return
     sc = make_scene(0)
     from oracle import raster as oracle
-    from tests.helpers import view_inputs
-    # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host thread it is allowed to
-    # torchrun exports OMP_NUM_THREADS=1; pick the best of {all allowed threads, half of them (SMT siblings)}
-    best = None
-    for n in sorted({host_threads(), max(1, host_threads() // 2)}, reverse=True):
-        oracle.set_num_threads(n)
-        oracle.forward(**view_inputs(sc, 0)[0])
-        t0 = time.perf_counter(); oracle.forward(**view_inputs(sc, 0)[0]); dt = time.perf_counter() - t0
-        if best is None or dt < best[1]:
-            best = (n, dt)
-    oracle.set_num_threads(best[0])
-    inps = [view_inputs(sc, v)[0] for v in range(T_VIEWS)]
+    inps = [oracle_view_inputs(sc, v) for v in range(T_VIEWS)]
+    _pick_oracle_threads(oracle, inps[0])
     for _ in range(max(args.warmup, 1)):
         oracle.forward(**inps[0])
     # bounded sample: a step renders all T views of the scene; beyond 120 steps only view (k mod T) of step k, so that
@@ -241,8 +450,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "views/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference's (CUDA-only, un-vendored) "
-                   "rasterizer: oracle/raster_oracle.c, OpenMP; the reference has no CPU implementation"},
+        "config": base_config(args.gpus),
+        "reference_note": "CPU restatement of the reference's (CUDA-only, un-vendored) rasterizer: oracle/raster_oracle.c, OpenMP; "
+                          "the reference has no CPU implementation of this path",
         "cpu_baseline": {"value": val, "unit": "views/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps x {per_step} view(s) of the full workload"},
         "e2e": {"value": val, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -257,9 +467,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ops", action="store_true",
-                    help="also time the cost volume and PTF (BASELINE config 3 sizes) on the GPU and their CPU restatements "
-                         "on bounded samples; adds an `ops` object to the JSON line")
+    ap.add_argument("--no-ops", action="store_true", help="skip the `ops` (N = 1) / `config5` (N > 1) sections")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager launch sequence instead of the CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -276,7 +485,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # NUMA placement of the pinned staging buffers (host-to-host path): stay on the CPUs next to this rank's GPU
-    from freesplat_b200.pipeline import bind_to_gpu_numa
+    from freesplat_b200.pipeline import HostRenderPipeline, bind_to_gpu_numa
     numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -285,63 +494,78 @@ def main():
     sc = sc_cpu.to(dev)
     V = T_VIEWS
     bg = torch.zeros((V, 3), device=dev)
-    row, col = torch.triu_indices(3, 3)
-    shs = sc.harmonics.transpose(1, 2).contiguous()
-    cov6 = sc.covariances[:, row, col].contiguous()
-    views, _ = decoder.camera_records(sc.extrinsics, sc.intrinsics, sc.near, sc.far, bg, True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step(stage_events=None, check="deferred"):
-        return rasterizer.raster_forward_raw(sc.means, sc.opacities, views, H, W, shs=shs, cov3D_precomp=cov6,
-                                             sh_degree=2, check_overflow=check, stage_events=stage_events)
-
-    st = step(check="sync")          # sizes the workspace (R is only known on the device)
-    R = st.num_rendered()
+    cov9 = sc.covariances.reshape(-1, 9)
+    # the step on a static workspace, recorded once as a CUDA graph (camera records + memset + preprocess + tile scan +
+    # scatter + sort/render): one launch per step
+    plan = rasterizer.RasterPlan(sc.means, sc.opacities, H, W, shs=sc.harmonics, cov3D_precomp=cov9,
+                                 cameras=(sc.extrinsics, sc.intrinsics, sc.near, sc.far, bg), sh_degree=2, sh_layout=1, cov_stride=9,
+                                 graph=not args.no_graph)
+    R = plan.run_checked()
     for _ in range(args.warmup):
-        step()
+        plan.run()
     torch.cuda.synchronize()
 
-    # ---- device-resident timing: per-step CUDA events, L2 flushed between steps -----------------
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # (a) the timed region proper: one fs_raster_forward per step, events around the whole step
+    # ---- (a) device-resident: per-step CUDA events around the graph launch, L2 flushed between steps ----
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
-        st = step(stage_events=list(evs[k]))
+        evs[k][0].record()
+        plan.run()
+        evs[k][1].record()
     barrier()
-    assert not st.overflowed()
+    assert not plan.check()[1]
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = sum(step_ms)
-    # (b) the same steps again with events BETWEEN the three stages of the ABI (roofline of the render kernel)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    for k in range(args.steps):
+
+    # ---- (b) the same work, eager, with events BETWEEN the three stages of the ABI (roofline of the render kernel) ----
+    views = decoder.camera_records_fused(sc.extrinsics, sc.intrinsics, sc.near, sc.far, bg, True)
+    n_stage = min(args.steps, 100)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_stage)]
+    st = None
+    for k in range(n_stage):
         flush.fill_(k & 0xFF)
-        st = step(stage_events=ev[k])
+        st = rasterizer.raster_forward_raw(sc.means, sc.opacities, views, H, W, shs=sc.harmonics, cov3D_precomp=cov9, sh_degree=2,
+                                           sh_layout=1, cov_stride=9, check_overflow="deferred", stage_events=ev[k], reuse_scratch=True)
     barrier()
     render_ms = [e[2].elapsed_time(e[3]) for e in ev]
     pre_ms = [e[0].elapsed_time(e[1]) for e in ev]
     bin_ms = [e[1].elapsed_time(e[2]) for e in ev]
 
-    # ---- end to end from pinned host memory through the public API ------------------------------
-    pin = lambda t: t.contiguous().pin_memory()
-    h = dict(ext=pin(sc_cpu.extrinsics), K=pin(sc_cpu.intrinsics), near=pin(sc_cpu.near), far=pin(sc_cpu.far),
-             means=pin(sc_cpu.means), cov=pin(sc_cpu.covariances), sh=pin(sc_cpu.harmonics), op=pin(sc_cpu.opacities))
-    h2d = sum(t.numel() * t.element_size() for t in h.values())
-    d2h = (V * 3 * H * W + V * H * W) * 4
+    # ---- (c) the public device-resident call, default (deferred) overflow check: K calls between two events ----
+    with torch.no_grad():
+        for _ in range(3):
+            decoder.render_views(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (H, W), bg, sc.means, sc.covariances, sc.harmonics,
+                                 sc.opacities)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host0 = time.perf_counter()
+        a0.record()
+        for k in range(args.steps):
+            decoder.render_views(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (H, W), bg, sc.means, sc.covariances, sc.harmonics,
+                                 sc.opacities)
+        a1.record()
+        t_host = time.perf_counter() - t_host0
+        barrier()
+        rasterizer.poll_deferred(block=True)
+    api_ms = a0.elapsed_time(a1)
 
-    # public API for host-resident data: freesplat_b200.pipeline.HostRenderPipeline (3 streams, double buffering).
-    # Every step moves its inputs H2D and its results D2H; copies of neighbouring steps overlap the kernels.
-    from freesplat_b200.pipeline import HostRenderPipeline
-    host = dict(extrinsics=h["ext"], intrinsics=h["K"], near=h["near"], far=h["far"], means=h["means"], covariances=h["cov"],
-                harmonics=h["sh"], opacities=h["op"])
-    pipe = HostRenderPipeline(dev, (H, W), V, depth=2)
+    # ---- (d) end to end from pinned host memory through the public host-to-host API ----
+    pin = lambda t: t.contiguous().pin_memory()
+    host = dict(extrinsics=pin(sc_cpu.extrinsics), intrinsics=pin(sc_cpu.intrinsics), near=pin(sc_cpu.near), far=pin(sc_cpu.far),
+                means=pin(sc_cpu.means), covariances=pin(sc_cpu.covariances), harmonics=pin(sc_cpu.harmonics),
+                opacities=pin(sc_cpu.opacities))
+    h2d_full = sum(t.numel() * t.element_size() for t in host.values())
+    d2h = (V * 3 * H * W + V * H * W) * 4
+    pipe = HostRenderPipeline(dev, (H, W), V, depth=2, shard_group=None if world > 1 else "none")
     for _ in range(4):
         pipe.submit(host)
     pipe.drain()
@@ -363,54 +587,84 @@ def main():
         t1.record(cur_s)
         barrier()
         e2e_runs.append(t0.elapsed_time(t1))
-    clocks = sampler.stop()          # sampled across the timed regions (device-resident, per-stage, host-to-host)
+    clocks = sampler.stop()          # sampled across the timed regions (device-resident, per-stage, API, host-to-host)
     out_c, out_d = pipe.wait(last)
-    assert torch.isfinite(out_c).all()
+    assert torch.isfinite(out_c).all() and pipe.reruns == 0
+    h2d_rank = pipe.h2d_bytes
 
-    # ---- max over ranks -------------------------------------------------------------------------
-    t = torch.tensor([total_ms] + e2e_runs, dtype=torch.float64, device=dev)
+    # ---- max over ranks; every rank's own step statistics ----
+    t = torch.tensor([total_ms, api_ms] + e2e_runs, dtype=torch.float64, device=dev)
+    mine = torch.tensor([min(step_ms), statistics.median(step_ms), max(step_ms), sum(step_ms) / len(step_ms)], dtype=torch.float64, device=dev)
+    per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t[0])
-    e2e_all = sorted(float(x) for x in t[1:])
+        dist.all_gather(per_rank, mine)
+    total_ms, api_ms = float(t[0]), float(t[1])
+    e2e_all = sorted(float(x) for x in t[2:])
     e2e_ms = e2e_all[1]
+    cfg5 = None
+    if world > 1 and not args.no_ops:
+        try:
+            cfg5 = config5_section(dev, rank, world)
+        except Exception as exc:             # keep the headline line even if the side section fails
+            cfg5 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank == 0:
-        peak, peak_src = _peaks()
+        peaks, peak_src = _peaks()
+        peak = float(peaks["hbm_gbs"])
         HW = H * W
         # render fwd = 44 R + 24 HW per view; the kernel also depth-sorts its tile first (8 B key read,
         # 8 B key + 4 B index written per instance): + 20 R
         alg_bytes = 64.0 * R + 24.0 * HW * V
         rd = sum(render_ms) / len(render_ms)
         achieved = alg_bytes / (rd * 1e-3) / 1e9
+        traffic, traffic_src = _ncu_traffic("render_fwd_kernel")
+        launches = plan.launches_per_run()
         line = {
             "metric": METRIC, "value": world * V * args.steps / (total_ms * 1e-3), "unit": "views/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "views_per_step_per_gpu": V, "gaussians": P, "tile_instances_R": R,
-                       "l2": "flushed between steps (256 MiB write)", "parallelism": f"view-sharded x{world}"},
-            "e2e": {"value": world * V * args.steps / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d,
+            "config": base_config(world),
+            "tile_instances_R": R,
+            "launch": "one CUDA graph launch per step (fs_graph_launch)" if not args.no_graph else "eager",
+            "per_rank_ms": [{"rank": r, "min": float(x[0]), "median": float(x[1]), "max": float(x[2]), "mean": float(x[3])}
+                            for r, x in enumerate(per_rank)],
+            "api": {"value": world * V * args.steps / (api_ms * 1e-3), "unit": "views/s", "ms_per_step": api_ms / args.steps,
+                    "call": "freesplat_b200.decoder.render_views (device-resident inputs, deferred overflow check, no host sync)",
+                    "host_ms_per_call_rank0": 1e3 * t_host / args.steps},
+            "e2e": {"value": world * V * args.steps / (e2e_ms * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d_rank,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                    "api": "freesplat_b200.pipeline.HostRenderPipeline (3 streams, depth 2)",
+                    "api": "freesplat_b200.pipeline.HostRenderPipeline (3 streams, depth 2, one CUDA graph per slot)",
+                    "upload": ("each rank uploads 1/%d of the Gaussian set (%d of %d bytes) + its cameras; in-place NCCL all-gathers "
+                               "replicate it over NVLink" % (world, h2d_rank, h2d_full)) if world > 1 else "full scene per step",
                     "protocol": "median of 3 timings of K steps", "ms_per_step_all": [x / args.steps for x in e2e_all],
-                    "h2d_gbs": h2d / (e2e_ms / args.steps * 1e-3) / 1e9, "numa": numa},
-            "gpu_launches": 4 * args.steps,      # preprocess, tile scan, scatter, sort+render
+                    "h2d_gbs_per_rank": h2d_rank / (e2e_ms / args.steps * 1e-3) / 1e9,
+                    "d2h_gbs_per_rank": d2h / (e2e_ms / args.steps * 1e-3) / 1e9, "numa": numa},
+            "gpu_launches": launches * args.steps,      # camera records, preprocess, tile scan, scatter, sort+render (graph nodes)
             "stage_ms": {"preprocess": sum(pre_ms) / len(pre_ms), "binning": sum(bin_ms) / len(bin_ms), "render": rd},
             "roofline": {"kernel": "render_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": _ncu_traffic("render_fwd_kernel"),
-                         "traffic_source": "profiles/r1_fwd_step_ncu_raw.csv (ncu --set full, same workload)", "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "per-tile depth sort + alpha blend in one kernel; FP32/SFU-issue bound at this size (SURVEY §7), reported against HBM as BASELINE asks"},
+                         "strict_8d_frac": (44.0 * R + 24.0 * HW * V) / (rd * 1e-3) / 1e9 / peak,
+                         "note": "per-tile depth sort + alpha blend in one kernel (64 R + 24 HW V bytes; SURVEY 8d's render-only 44 R + "
+                                 "24 HW V in strict_8d_frac); FP32/SFU-issue bound at this size (SURVEY §7), reported against HBM as "
+                                 "BASELINE asks"},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             reps = 25                  # ~10 s of host work at ~8 views/s
             v, cores, dt = cpu_reference_views_per_s(sc_cpu, n_views=T_VIEWS, repeats=reps)
             line["cpu_baseline"] = {"value": v, "unit": "views/s", "cores": cores, "kind": "port",
                                     "sample": f"{reps} x {T_VIEWS} views of the full workload ({dt:.1f} s)"}
-        if args.ops:
-            line["ops"] = ops_section(dev)
+        if world == 1 and not args.no_ops:
+            try:
+                line["ops"] = ops_section(dev, peaks)
+            except Exception as exc:
+                line["ops"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        if cfg5 is not None:
+            line["configs"] = {"config5": cfg5}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

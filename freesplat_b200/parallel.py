@@ -67,6 +67,139 @@ def all_gather_candidates(feats, coords, dens, wemb, depths, num_views: int, gro
             full[..., F + 4].contiguous(), full[..., F + 5].contiguous())
 
 
+class _AllGatherViewsGrad(torch.autograd.Function):
+    """all_gather_views with a gradient: every rank back-propagates into ALL views' features (its cost volumes read the
+    other ranks' maps as sources), so the backward is one all-reduce(SUM) of the [V, ...] gradient, of which each rank
+    keeps the rows of the views it owns."""
+
+    @staticmethod
+    def forward(ctx, local, num_views, group):
+        ctx.num_views, ctx.group = num_views, group
+        return all_gather_views(local, num_views, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        world = dist.get_world_size(ctx.group)
+        if world > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        mine = shard_views(ctx.num_views, dist.get_rank(ctx.group), world)
+        return g[torch.tensor(mine, dtype=torch.long, device=g.device)], None, None
+
+
+def source_view_indices(num_views: int) -> torch.Tensor:
+    """[V, V-1]: the sources of reference view v are all other views in index order (encoder_freesplat.py:236-238, the
+    `not use_local` branch that ScanNet 2/3-view and the 10-view FVT configs with num_views >= V take)."""
+    full = torch.arange(num_views)[None].repeat(num_views, 1)
+    return full[full != torch.arange(num_views)[:, None]].view(num_views, num_views - 1)
+
+
+def cost_volume_sharded(cost_volume_fn, local_feats, extrinsics, feat_intrinsics, near, far, group=None, src_indices=None):
+    """context views shard over the ranks (view v on rank v % world); ONE all-gather of the stride-4
+    matching features (3.7 MB per 640x480 view) and every rank builds the cost volumes of ITS reference views against
+    sources that may live anywhere.
+
+    local_feats [n_local, C, H', W'] (this rank's views, increasing global index); extrinsics [V,4,4] (c2w) and
+    feat_intrinsics [V,3,3] (pixel intrinsics at feature resolution) of ALL views; near / far: scalars or [1,1,1,1] tensors.
+    cost_volume_fn(cur_feats=, src_feats=, src_extrinsics=, src_poses=, src_Ks=, cur_invK=, min_depth=, max_depth=) is the
+    operator (freesplat_b200.cost_volume.AVGFeatureVolumeManager instance).  The geometry follows
+    encoder_freesplat.py:248-273.  Returns (volume [n_local, D, H', W'], owned view ids)."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    V = extrinsics.shape[0]
+    mine = shard_views(V, rank, world)
+    if world > 1:
+        feats = _AllGatherViewsGrad.apply(local_feats, V, group) if local_feats.requires_grad else all_gather_views(local_feats, V, group)
+    else:
+        feats = local_feats
+    if src_indices is None:
+        src_indices = source_view_indices(V)
+    dev = feats.device
+    cur = torch.tensor(mine, dtype=torch.long, device=dev)
+    if not mine:
+        return feats.new_zeros((0,)), mine
+    src = src_indices.to(dev)[cur]                                         # [n, K]
+    src_ext = extrinsics[src]                                              # [n, K, 4, 4]
+    cur_ext = extrinsics[cur]
+    src_cam_T_cur_cam = src_ext.inverse() @ cur_ext[:, None]
+    cur_cam_T_src_cam = cur_ext.inverse()[:, None] @ src_ext
+    n, K = src.shape
+    src_K = torch.eye(4, device=dev)[None, None].repeat(n, K, 1, 1)
+    src_K[:, :, :3, :3] = feat_intrinsics[src]
+    cur_invK = torch.eye(4, device=dev)[None].repeat(n, 1, 1)
+    cur_invK[:, :3, :3] = feat_intrinsics[cur].inverse()
+    vol = cost_volume_fn(cur_feats=feats[cur], src_feats=feats[src], src_extrinsics=src_cam_T_cur_cam, src_poses=cur_cam_T_src_cam,
+                         src_Ks=src_K, cur_invK=cur_invK, min_depth=near, max_depth=far)
+    return vol, mine
+
+
+class ViewExchange:
+    """The cross-view PTF gather without staging copies and without a bulk barrier.
+
+    Every rank keeps ONE packed block per context view, [feats HW x F | coords HW x 3 | dens HW | wemb HW | depth HW]
+    (F + 6 floats per candidate: 86 MB per 640 x 480 view at F = 64), and hands the PTF kernels strided views of those blocks:
+    the fields of a view are dense sub-arrays, so nothing is re-packed on either side.  `exchange` copies the views this rank
+    owns (view v belongs to rank v % world) into their blocks and enqueues one broadcast per view, in view order, on a side
+    stream; `ready_events[v]` fires when view v has landed.  The fold is sequential in v and step v needs view v only
+    (encoder_freesplat.py:443-519), so `ptf.fuse_views(..., view_ready=ready_events)` folds view v while views v+1.. are
+    still in flight over NVLink: the exchange costs its first two views, not all ten."""
+
+    def __init__(self, num_views: int, HW: int, F: int, device, group=None):
+        self.V, self.HW, self.F, self.dev, self.group = num_views, HW, F, device, group
+        self.block = torch.empty((num_views, HW * (F + 6)), dtype=torch.float32, device=device)
+        self.ready_events = [torch.cuda.Event() for _ in range(num_views)]
+        self.stream = torch.cuda.Stream(device) if (isinstance(device, torch.device) and device.type == "cuda") or \
+            str(device).startswith("cuda") else None
+        o = 0
+        self._fields = []
+        for width in (F, 3, 1, 1, 1):
+            self._fields.append((o, width))
+            o += HW * width
+
+    def fields(self):
+        """(feats [V,HW,F], coords [V,HW,3], dens [V,HW], wemb [V,HW], depths [V,HW]): views into the blocks."""
+        out = []
+        for o, width in self._fields:
+            t = self.block[:, o:o + self.HW * width]
+            out.append(t.view(self.V, self.HW, width) if width > 1 else t)
+        return tuple(out)
+
+    def exchange(self, feats, coords, dens, wemb, depths):
+        """Arguments: this rank's views ([n_local, HW, ...], increasing global index).  Returns fields()."""
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if world > 1 else 0
+        mine = shard_views(self.V, rank, world)
+        full = self.fields()
+        for k, v in enumerate(mine):
+            for dst, src in zip(full, (feats, coords, dens, wemb, depths)):
+                dst[v].copy_(src[k].reshape(dst[v].shape))
+        if world == 1:
+            if self.stream is not None:
+                for e in self.ready_events:
+                    e.record()
+            return full
+        cuda = self.stream is not None
+        if cuda:
+            self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+        ctx = torch.cuda.stream(self.stream) if cuda else _null()
+        with ctx:
+            for v in range(self.V):
+                src = dist.get_global_rank(self.group, owner_of(v, world)) if self.group is not None else owner_of(v, world)
+                w = dist.broadcast(self.block[v], src=src, group=self.group, async_op=True)
+                w.wait()                                  # the side stream (not the host) waits for NCCL
+                if cuda:
+                    self.ready_events[v].record(self.stream)
+        return full
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def max_over_ranks(values: Sequence[float], device, group=None) -> List[float]:
     """Timing reduction used by bench.py (device-timed milliseconds, max over ranks)."""
     t = torch.tensor(list(values), dtype=torch.float64, device=device)

@@ -53,9 +53,15 @@ class HostRenderPipeline:
     results and is looked at when the slot is next touched (wait() or the submit that reuses it): an overflowed step is
     re-run on a grown workspace from the inputs still resident in the slot, transparently."""
     KEYS = ("extrinsics", "intrinsics", "near", "far", "means", "covariances", "harmonics", "opacities")
+    GAUSSIAN_KEYS = ("means", "covariances", "harmonics", "opacities")
 
     def __init__(self, device, image_shape: Tuple[int, int], n_views: int, depth: int = 2, background=(0.0, 0.0, 0.0),
-                 graph: bool = True):
+                 graph: bool = True, shard_group="none"):
+        """shard_group: a torch.distributed process group (None = the default group) whose ranks all render views of the SAME
+        scene (target views shard over GPUs, the Gaussian set is replicated).  Each rank then uploads only its
+        1/world slice of the Gaussian tensors over PCIe and one in-place all-gather per tensor replicates the set over
+        NVLink / NVSwitch -- the host link carries the scene once per step instead of once per rank.  submit() becomes a
+        collective call (all ranks, same order).  "none": every rank uploads everything."""
         self.dev = torch.device(device)
         self.h, self.w = image_shape
         self.V = n_views
@@ -72,6 +78,12 @@ class HostRenderPipeline:
         self.ev_copied = [torch.cuda.Event() for _ in range(depth)]
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]        # kernels of slot finished
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]         # host outputs of slot are valid
+        self.group, self.world, self.rank = None, 1, 0
+        if shard_group != "none":
+            import torch.distributed as dist
+            self.group = shard_group
+            self.world, self.rank = dist.get_world_size(shard_group), dist.get_rank(shard_group)
+        self.h2d_bytes = 0                 # bytes the last submit() moved over the host link
         self.unresolved = [False] * depth  # slot holds a step whose status word has not been looked at yet
         self.reruns = 0
         self.n = 0
@@ -134,8 +146,28 @@ class HostRenderPipeline:
             if d is None:
                 d = self.dev_in[slot] = {k: torch.empty(host[k].shape, dtype=torch.float32, device=self.dev) for k in self.KEYS}
                 self.plans[slot] = None
+            G = host["means"].shape[0]
+            sharded = self.world > 1 and G % self.world == 0
+            moved = 0
+            works = []
             for k in self.KEYS:
-                d[k].copy_(host[k], non_blocking=True)
+                if sharded and k in self.GAUSSIAN_KEYS:
+                    n = G // self.world
+                    part = d[k][self.rank * n:(self.rank + 1) * n]
+                    part.copy_(host[k][self.rank * n:(self.rank + 1) * n], non_blocking=True)
+                    moved += part.numel() * 4
+                else:
+                    d[k].copy_(host[k], non_blocking=True)
+                    moved += d[k].numel() * 4
+            if sharded:
+                import torch.distributed as dist
+                for k in self.GAUSSIAN_KEYS:             # in place: this rank's slice already sits where it belongs
+                    n = G // self.world
+                    works.append(dist.all_gather_into_tensor(d[k], d[k][self.rank * n:(self.rank + 1) * n], group=self.group,
+                                                             async_op=True))
+                for wk in works:
+                    wk.wait()                            # s_h2d waits for the NCCL stream (no host block)
+            self.h2d_bytes = moved
             self.ev_copied[slot].record(self.s_h2d)
         if self.plans[slot] is None:
             with torch.cuda.stream(self.s_run):

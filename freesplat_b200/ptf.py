@@ -228,17 +228,27 @@ class _PtfMerge(torch.autograd.Function):
 
 
 def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, image_shape, depth_thres=0.1,
-               E_inv=None, return_debug=False, timings=None):
+               E_inv=None, return_debug=False, timings=None, view_ready=None):
     """Flat form: feats [V,HW,F], coords [V,HW,3], dens/wemb [V,HW], depths [V,HW], extrinsics [V,4,4] (c2w),
     intrinsics [V,3,3] (normalised).  Returns (feats [N,F], coords [N,3], ext [N,4,4], depth [N]) (+ debug).
     With autograd enabled and differentiable inputs the result is differentiable w.r.t. feats, coords, dens,
-    wemb, depths and the GRU parameters (index decisions are piecewise constant, as in the reference)."""
+    wemb, depths and the GRU parameters (index decisions are piecewise constant, as in the reference).
+    view_ready: optional list of V CUDA events; fold step i (and the initial copy of view 0) waits for view_ready[i] on the
+    current stream before touching view i -- the cross-view exchange of the candidates (parallel.ViewExchange) then overlaps
+    the fold of the views that have already arrived."""
     L = _lib.lib()
     if not feats.is_cuda:
         raise _lib.FreeSplatB200Error("fuse_gaussians needs CUDA tensors (no CPU fallback exists)")
     dev = feats.device
     f32 = lambda t: t.float().contiguous()
-    feats, coords, dens, wemb, depths, extrinsics, intrinsics = map(f32, (feats, coords, dens, wemb, depths, extrinsics, intrinsics))
+
+    def per_view(t):
+        # the kernels read ONE view at a time: a [V, ...] tensor only needs contiguous slices t[i] (parallel.ViewExchange hands
+        # over strided views of its packed per-view blocks; a global .contiguous() would re-copy the whole candidate set)
+        t = t.float()
+        return t if all(t[i].is_contiguous() for i in range(t.shape[0])) else t.contiguous()
+    feats, coords, dens, wemb, depths = map(per_view, (feats, coords, dens, wemb, depths))
+    extrinsics, intrinsics = f32(extrinsics), f32(intrinsics)
     V, HW, F = feats.shape
     h, w = image_shape
     assert HW == h * w
@@ -269,6 +279,9 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
     nb = (cap + 511) // 512 + 1              # blocks of the flag scans (csrc/ptf.cu: kPtfItems = 512)
     block_counts, pair_j, pair_p = i32(3 * nb), i32(cap), i32(cap)
     scratch = (zbuf, pix, zeta, match, append, block_counts, pair_j, pair_p)
+    ts = torch.cuda.current_stream(dev)
+    if view_ready is not None:
+        ts.wait_event(view_ready[0])
     if need_grad:
         state = (feats[0], coords[0], dens[0], wemb[0], ext16[0][None].expand(HW, 16).contiguous(), depths[0])
         nxt = None
@@ -290,6 +303,8 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
         gru_buf = torch.empty((min(cap, max(V - 1, 1) * HW), F), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             for i in range(1, V):
+                if view_ready is not None:
+                    ts.wait_event(view_ready[i])
                 cin = counts[i - 1, 4:5]
                 view = (feats[i], coords[i], dens[i], wemb[i], depths[i], ext16[i], E_inv[i], K_px[i])
                 out_bufs = (nxt.feats, nxt.coords, nxt.dens, nxt.wemb, nxt.ext, nxt.depth)
@@ -304,6 +319,8 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
         return (state[0][:N], state[1][:N], state[4][:N].reshape(N, 4, 4), state[5][:N])
     with torch.cuda.device(dev):
         for i in range(1, V):
+            if view_ready is not None:
+                ts.wait_event(view_ready[i])
             cin = counts[i - 1, 4:5]                      # N of the current state, on the device
             view = (feats[i], coords[i], dens[i], wemb[i], depths[i], ext16[i], E_inv[i], K_px[i])
             det = tuple(t.detach() for t in state)

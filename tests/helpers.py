@@ -41,7 +41,7 @@ def frac_within(a, b, rtol=1e-4, atol=1e-5):
     return float(ok.mean())
 
 
-def grad_report(got, want, rtol=1e-4, atol_of_max=1e-5, max_outlier_frac=5e-4, gross=2e-4) -> dict:
+def grad_report(got, want, rtol=1e-4, atol_of_max=1e-5, max_outlier_frac=5e-4, gross=1e-2) -> dict:
     """Element-wise gradient check with an explicit, counted exclusion list.
 
     An element passes if |got - want| <= rtol * |want| + atol_of_max * max|want| (the additive term covers elements that are

@@ -30,3 +30,17 @@ def test_product_arm_needs_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                          timeout=600, cwd=ROOT)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_both_arms_print_the_same_config_and_bench_does_not_import_tests():
+    """The driver compares the two arms' `config` objects: both come from bench.base_config.  bench.py may execute oracle/
+    (cpu_baseline / reference arm) but must not import model or helper code from tests/."""
+    import importlib.util
+    import re
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.base_config(1)["workload"] == b.WORKLOAD and set(b.base_config(1)) == set(b.base_config(8))
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count("base_config(") >= 3                    # definition + the two arms
+    assert not re.search(r"^\s*(from|import)\s+tests\b", src, re.M) and "sys.path.insert(0, os.path.join(ROOT, \"tests\"))" not in src

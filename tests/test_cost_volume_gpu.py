@@ -187,7 +187,7 @@ def test_backward_tensor_core_and_fp32_vs_oracle_autograd(zero_source):
     for mode in (0, 1):
         for n, g, w in zip(names, grads[mode], want):
             assert torch.isfinite(g).all(), (mode, n)
-            rep = grad_report(g.cpu().numpy(), w.numpy(), max_outlier_frac=0.0)
+            rep = grad_report(g.cpu().numpy(), w.numpy(), max_outlier_frac=0.0, atol_of_max=5e-5 if n[0] in "Wb" else 1e-5)
             report.append((mode, n, rep))
             if not rep["ok"]:
                 bad.append((mode, n, rep))
@@ -213,7 +213,9 @@ def test_mid_size_reference_golden_forward_and_backward():
     report, bad = [("kink_rows_excluded", int(z["kink_rows"]))], []
     for name, got, want in [("cur", cur.grad[:, ::2], z["g_cur_sub"]), ("src", src.grad[:, :, ::cs], z["g_src_sub"])] + \
             [(f"mlp{i}", p.grad, z[f"g_mlp{i}"]) for i, p in enumerate(params)]:
-        rep = grad_report(got.cpu().numpy(), want, max_outlier_frac=0.0)
+        # parameter gradients are sums of 4.4e5 cancelling row terms evaluated in 3xTF32 (relative to the sum of |terms| the
+        # error is ~1e-6; relative to the much smaller maximum of the result 2.5e-5 was measured): additive term 5e-5 of max
+        rep = grad_report(got.cpu().numpy(), want, max_outlier_frac=0.0, atol_of_max=5e-5 if name.startswith("mlp") else 1e-5)
         report.append((name, rep))
         if not rep["ok"]:
             bad.append((name, rep))

@@ -34,6 +34,11 @@ def _worker(rank, world, port, num_views, q):
         ok = ok and torch.equal(gf, torch.stack([mk(v, F) for v in range(num_views)]))
         ok = ok and torch.equal(gc, torch.stack([mk(v, 3) * 2 for v in range(num_views)]))
         ok = ok and all(torch.equal(g_, torch.stack([mk(v, 1)[:, 0] * k for v in range(num_views)])) for g_, k in ((gd, 3), (gw, 5), (gz, 7)))
+        # ViewExchange: per-view broadcasts into the packed blocks the PTF kernels read (strided field views, no re-packing)
+        ex = parallel.ViewExchange(num_views, HW, F, "cpu")
+        ef, ec, ed, ew, ez = ex.exchange(*loc)
+        ok = ok and torch.equal(ef, gf) and torch.equal(ec, gc) and torch.equal(ed, gd) and torch.equal(ew, gw) and torch.equal(ez, gz)
+        ok = ok and all(ef[v].is_contiguous() and ec[v].is_contiguous() for v in range(num_views)) and ef.data_ptr() == ex.block.data_ptr()
         t = parallel.max_over_ranks([1.0 + rank, 5.0 - rank], "cpu")
         q.put((rank, mine, ok, t))
     finally:
@@ -131,3 +136,51 @@ def test_sharded_render_sums_gaussian_gradients_over_ranks():
     for r in res:
         for got, want in zip(r[2], leaf):
             torch.testing.assert_close(got, want.grad, rtol=1e-6, atol=1e-6)
+
+
+def _fake_cost_volume(cur_feats, src_feats, src_extrinsics, src_poses, src_Ks, cur_invK, min_depth, max_depth):
+    """Stand-in operator (the real one needs a GPU): mixes the reference map with every source map and the relative pose."""
+    w = src_extrinsics[:, :, 0, 3].abs() + 1.0                                        # [n, K]
+    return (cur_feats[:, None] * src_feats * w[:, :, None, None, None]).sum(2).cumsum(1) + cur_invK[:, 0, 0].reshape(-1, 1, 1, 1)
+
+
+def _cv_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        V, C, Hf, Wf = 5, 4, 3, 6
+        g = torch.Generator().manual_seed(1)
+        feats = torch.randn((V, C, Hf, Wf), generator=g)
+        ext = torch.eye(4).repeat(V, 1, 1); ext[:, 0, 3] = torch.arange(V) * 0.3
+        Kf = torch.eye(3).repeat(V, 1, 1); Kf[:, 0, 0] = 40.0; Kf[:, 1, 1] = 30.0; Kf[:, 0, 2] = Wf / 2; Kf[:, 1, 2] = Hf / 2
+        mine = parallel.shard_views(V, rank, world)
+        local = feats[mine].clone().requires_grad_(True)
+        vol, ids = parallel.cost_volume_sharded(_fake_cost_volume, local, ext, Kf, 0.5, 15.0)
+        vol.sum().backward()                                                          # loss over the LOCAL volumes only
+        q.put((rank, ids, vol.detach(), local.grad.clone()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_cost_volume_matches_single_rank_forward_and_backward():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_cv_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda r: r[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    V, C, Hf, Wf = 5, 4, 3, 6
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn((V, C, Hf, Wf), generator=g).requires_grad_(True)
+    ext = torch.eye(4).repeat(V, 1, 1); ext[:, 0, 3] = torch.arange(V) * 0.3
+    Kf = torch.eye(3).repeat(V, 1, 1); Kf[:, 0, 0] = 40.0; Kf[:, 1, 1] = 30.0; Kf[:, 0, 2] = Wf / 2; Kf[:, 1, 2] = Hf / 2
+    vol, ids = parallel.cost_volume_sharded(_fake_cost_volume, feats, ext, Kf, 0.5, 15.0)      # no process group: one rank owns all
+    vol.sum().backward()
+    assert ids == list(range(V)) and tuple(parallel.source_view_indices(3).tolist()) == ([1, 2], [0, 2], [0, 1])
+    for rank, rids, rvol, rgrad in res:
+        torch.testing.assert_close(rvol, vol.detach()[rids], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(rgrad, feats.grad[rids], rtol=1e-5, atol=1e-6)

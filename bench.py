@@ -375,7 +375,7 @@ def config5_section(dev, rank, world, steps=3):
     the ranks.  Device-timed per stage, max over ranks."""
     import torch
     import torch.distributed as dist
-    from freesplat_b200 import decoder, parallel, ptf, synth
+    from freesplat_b200 import adapter, decoder, parallel, ptf, synth
     V, T = 10, 18
     feats, coords, dens, wemb, depths, ext, Kn, hw = _flat_ptf(synth.ptf_inputs(0, V, H, W))
     mine = parallel.shard_views(V, rank, world)
@@ -389,6 +389,7 @@ def config5_section(dev, rank, world, steps=3):
     sel = torch.tensor(my_t, dtype=torch.long, device=dev)
     bg = torch.zeros((len(my_t), 3), device=dev)
     ex = parallel.ViewExchange(V, H * W, 64, dev)
+    raw_gain = torch.ones(34, device=dev); raw_bias = torch.zeros(34, device=dev); raw_bias[:3] = -3.0
     rows = []
     N = 0
     for it in range(steps + 1):
@@ -403,12 +404,13 @@ def config5_section(dev, rank, world, steps=3):
             F_, X_, E_, Z_ = ptf.fuse_views(gru, *full, ext_d, K_d, hw, view_ready=ex.ready_events)
             ev[2].record()
             N = int(F_.shape[0])
-            # a fixed Gaussian head stands in for the (out-of-scope) decoder MLP: means = fused coordinates
-            cov = torch.eye(3, device=dev)[None].expand(N, 3, 3).contiguous() * 4e-4
-            sh = torch.zeros((N, 3, 9), device=dev); sh[:, :, 0] = F_[:, :3]
-            op = torch.full((N,), 0.5, device=dev)
+            # Gaussian head (fs_gaussian_head) on the fused state; the first 34 latent channels stand in for the output of the
+            # (out-of-scope) decoder MLP, shifted so that the scales land where trained FreeSplat's do (sigma ~ 0.5-3 px)
+            raw = F_[:, :34] * raw_gain + raw_bias
+            gs = adapter.gaussian_head(raw, Z_, torch.full((N,), 0.5, device=dev), X_, E_, K_d[0], (H, W))
             if my_t:
-                decoder.render_views(tgt_ext[sel], tgt_K[sel], near[sel], far[sel], (H, W), bg, X_, cov, sh, op)
+                decoder.render_views(tgt_ext[sel], tgt_K[sel], near[sel], far[sel], (H, W), bg, gs.means, gs.covariances,
+                                     gs.harmonics, gs.opacities)
             ev[3].record()
         torch.cuda.synchronize()
         if it:

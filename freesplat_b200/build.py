@@ -68,9 +68,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed (see log above)")
-    cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static",
+    tmp = LIB + ".tmp"
+    cmd = [NVCC, *ARCH, "-shared", "-o", tmp, *objs, "-cudart", "static",
            "-ccbin", COMMON[-1]]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)          # atomic: a snapshot of the tree (gpurun) never sees a half-written library
     return LIB
 
 

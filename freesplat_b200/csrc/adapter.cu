@@ -63,6 +63,140 @@ __global__ void __launch_bounds__(256) gaussian_head_kernel(FsAdapterArgs a) {
   a.opacities_out[i] = a.opacities[i];
 }
 
+// Backward of gaussian_head_kernel (training path; the reference gets it from autograd through the ~25 torch ops of
+// gaussian_adapter.py:151-172 / gaussians.py:8-44).  One thread per Gaussian re-derives the forward intermediates and
+// applies the chain rule by hand:
+//   cov = M M^T, M = C R S      ->  dM = (G + G^T) M ;  ds_c = sum_r dM[r][c] (CR)[r][c] ;  d(CR) = dM S ;
+//                                   dR = C^T d(CR) ;  dC = d(CR) R^T
+//   R(q) = I + two_s B(q), two_s = 2 / (|q|^2 + 1e-8)   (pytorch3d quaternion_to_matrix, xyzw)
+//   q = raw_q / (|raw_q| + eps) ;  s = (smin + (smax - smin) sigmoid(raw_s)) * depth * mult
+// Gradients w.r.t. raw [N,7+3 d_sh], depths, opacities, coords and the rotation block of the per-Gaussian c2w matrix
+// (PTF's density-weighted average: the reference back-propagates through it into the densities).
+__global__ void __launch_bounds__(256) gaussian_head_bwd_kernel(FsAdapterBwdArgs a) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.N) return;
+  const int dsh = (a.sh_degree + 1) * (a.sh_degree + 1);
+  const int din = 7 + 3 * dsh;
+  const float* raw = a.raw + (size_t)i * din;
+  float* d_raw = a.d_raw + (size_t)i * din;
+  const float depth = a.depths[i];
+  const float k00 = a.K[0], k01 = a.K[1], k10 = a.K[3], k11 = a.K[4];
+  const float idet = 1.0f / (k00 * k11 - k01 * k10);
+  const float pw = 1.0f / (float)a.W, ph = 1.0f / (float)a.H;
+  const float mult = 0.1f * ((k11 * pw - k01 * ph) * idet) + 0.1f * ((-k10 * pw + k00 * ph) * idet);
+  float s[3], sg[3], base[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    sg[k] = 1.0f / (1.0f + expf(-raw[k]));
+    base[k] = a.scale_min + (a.scale_max - a.scale_min) * sg[k];
+    s[k] = base[k] * depth * mult;
+  }
+  const float rq[4] = {raw[3], raw[4], raw[5], raw[6]};
+  const float nq = sqrtf(rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3]);
+  const float den = nq + a.eps;
+  const float q[4] = {rq[0] / den, rq[1] / den, rq[2] / den, rq[3] / den};
+  const float qi = q[0], qj = q[1], qk = q[2], qr = q[3];
+  const float n2 = qi * qi + qj * qj + qk * qk + qr * qr + 1e-8f;
+  const float two_s = 2.0f / n2;
+  // B(q): R = I + two_s * B
+  const float B[9] = {-(qj * qj + qk * qk), qi * qj - qk * qr, qi * qk + qj * qr,
+                      qi * qj + qk * qr, -(qi * qi + qk * qk), qj * qk - qi * qr,
+                      qi * qk - qj * qr, qj * qk + qi * qr, -(qi * qi + qj * qj)};
+  float R[9];
+#pragma unroll
+  for (int e = 0; e < 9; e++) R[e] = ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f) + two_s * B[e];
+  const float* E = a.ext + 16 * (size_t)i;
+  float CR[9], M[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      CR[3 * r + c] = E[4 * r] * R[c] + E[4 * r + 1] * R[3 + c] + E[4 * r + 2] * R[6 + c];
+      M[3 * r + c] = CR[3 * r + c] * s[c];
+    }
+  // upstream gradient of the covariance (any of the g_* may be NULL)
+  float G[9];
+#pragma unroll
+  for (int e = 0; e < 9; e++) G[e] = a.g_cov ? a.g_cov[9 * (size_t)i + e] : 0.f;
+  float dM[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; k++) acc += (G[3 * r + k] + G[3 * k + r]) * M[3 * k + c];
+      dM[3 * r + c] = acc;
+    }
+  float ds[3], dCR[9];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    ds[c] = dM[c] * CR[c] + dM[3 + c] * CR[3 + c] + dM[6 + c] * CR[6 + c];
+    if (a.g_scales) ds[c] += a.g_scales[3 * (size_t)i + c];
+#pragma unroll
+    for (int r = 0; r < 3; r++) dCR[3 * r + c] = dM[3 * r + c] * s[c];
+  }
+  // dR = C^T dCR ; dC = dCR R^T
+  float dR[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) dR[3 * r + c] = E[r] * dCR[c] + E[4 + r] * dCR[3 + c] + E[8 + r] * dCR[6 + c];
+  if (a.d_ext) {
+    float* dE = a.d_ext + 16 * (size_t)i;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        float v = 0.f;
+        if (r < 3 && c < 3) v = dCR[3 * r] * R[3 * c] + dCR[3 * r + 1] * R[3 * c + 1] + dCR[3 * r + 2] * R[3 * c + 2];
+        dE[4 * r + c] = v;
+      }
+  }
+  // dR -> dq (normalised quaternion): R = I + two_s B
+  float dB[9], dtwo = 0.f;
+#pragma unroll
+  for (int e = 0; e < 9; e++) { dB[e] = dR[e] * two_s; dtwo += dR[e] * B[e]; }
+  float dq[4];
+  dq[0] = (dB[1] + dB[3]) * qj + (dB[2] + dB[6]) * qk + (dB[7] - dB[5]) * qr - 2.f * qi * (dB[4] + dB[8]);
+  dq[1] = (dB[1] + dB[3]) * qi + (dB[5] + dB[7]) * qk + (dB[2] - dB[6]) * qr - 2.f * qj * (dB[0] + dB[8]);
+  dq[2] = (dB[2] + dB[6]) * qi + (dB[5] + dB[7]) * qj + (dB[3] - dB[1]) * qr - 2.f * qk * (dB[0] + dB[4]);
+  dq[3] = -dB[1] * qk + dB[2] * qj + dB[3] * qk - dB[5] * qi - dB[6] * qj + dB[7] * qi;
+  const float dn2 = dtwo * (-2.0f / (n2 * n2));
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    dq[k] += dn2 * 2.f * q[k];
+    if (a.g_rotations) dq[k] += a.g_rotations[4 * (size_t)i + k];
+  }
+  // q = rq / (|rq| + eps):  d rq_j = dq_j / den - (sum_i dq_i rq_i) rq_j / (|rq| den^2)
+  const float dot = dq[0] * rq[0] + dq[1] * rq[1] + dq[2] * rq[2] + dq[3] * rq[3];
+  const float f = nq > 0.f ? dot / (nq * den * den) : 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) d_raw[3 + k] = dq[k] / den - f * rq[k];
+  float d_depth = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    d_raw[k] = ds[k] * (a.scale_max - a.scale_min) * sg[k] * (1.0f - sg[k]) * depth * mult;
+    d_depth += ds[k] * base[k] * mult;
+  }
+  a.d_depths[i] = d_depth;
+  for (int c = 0; c < 3; c++)
+    for (int d = 0; d < dsh; d++) {
+      const int deg = d == 0 ? 0 : (d < 4 ? 1 : (d < 9 ? 2 : 3));
+      const float mask = deg == 0 ? 1.0f : 0.1f * (deg == 1 ? 0.25f : deg == 2 ? 0.0625f : 0.015625f);
+      d_raw[7 + c * dsh + d] = a.g_harmonics ? a.g_harmonics[(size_t)i * 3 * dsh + c * dsh + d] * mask : 0.f;
+    }
+#pragma unroll
+  for (int k = 0; k < 3; k++) a.d_coords[3 * (size_t)i + k] = a.g_means ? a.g_means[3 * (size_t)i + k] : 0.f;
+  a.d_opacities[i] = a.g_opacities ? a.g_opacities[i] : 0.f;
+}
+
+int launch_gaussian_head_bwd(const FsAdapterBwdArgs& a, cudaStream_t s) {
+  if (a.N <= 0) return FS_OK;
+  gaussian_head_bwd_kernel<<<(a.N + 255) / 256, 256, 0, s>>>(a);
+  return check_cuda(cudaGetLastError(), "gaussian_head_bwd_kernel");
+}
+
 // Depth back-projection of the context views: GaussianAdapter.forward(fusion=True)
 // (gaussian_adapter.py:175-189) -> Create_from_depth_map.project (:48-68): per pixel (i, j)
 //   cam = ((j - cx) / fx * z, (i - cy) / fy * z, z, 1),  world = c2w . cam

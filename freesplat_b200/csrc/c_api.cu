@@ -39,6 +39,9 @@ int fs_struct_size(int32_t which) {
     case 6: return (int)sizeof(FsDepthHeadArgs);
     case 7: return (int)sizeof(FsBackprojectArgs);
     case 8: return (int)sizeof(FsPlyArgs);
+    case 9: return (int)sizeof(FsPtfMergeBwdArgs);
+    case 10: return (int)sizeof(FsAdapterBwdArgs);
+    case 11: return (int)sizeof(FsDepthHeadBwdArgs);
     default: return -1;
   }
 }
@@ -157,6 +160,16 @@ int fs_ptf_merge(const FsPtfArgs* a, void* stream) {
   return launch_ptf_merge(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int fs_ptf_merge_backward(const FsPtfMergeBwdArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr && a->H >= 1 && a->W >= 1 && a->F >= 4 && (a->F & 3) == 0 && a->N >= 0 && a->n_keep >= 0 && a->n_match >= 0,
+             "bad sizes (F must be a multiple of 4)");
+  FS_REQUIRE(a->coords && a->dens && a->ext && a->depth && a->v_coords && a->v_dens && a->v_depth && a->v_ext && a->match && a->pix &&
+                 a->map_old && a->map_px, "NULL forward state");
+  FS_REQUIRE(a->d_feats && a->d_coords && a->d_dens && a->d_wemb && a->d_ext && a->d_depth && a->dv_feats && a->dv_coords && a->dv_dens &&
+                 a->dv_wemb && a->dv_depth && (a->n_match == 0 || a->d_gru), "NULL output buffer");
+  return launch_ptf_merge_bwd(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int fs_ptf_gru_inputs(int32_t M, int32_t F, const int32_t* pair_j, const int32_t* pair_p, const float* feats, const float* dens,
                       const float* wemb, const float* v_feats, const float* v_dens, const float* v_wemb, float* A1, void* stream) {
   FS_REQUIRE(M >= 0 && F >= 1 && (M == 0 || (pair_j && pair_p && feats && dens && wemb && v_feats && v_dens && v_wemb && A1)), "bad arguments");
@@ -176,6 +189,19 @@ int fs_gaussian_head(const FsAdapterArgs* a, void* stream) {
   FS_REQUIRE(a->N == 0 || (a->raw && a->depths && a->opacities && a->coords && a->ext && a->K && a->means && a->covariances &&
                            a->harmonics && a->opacities_out && a->scales && a->rotations), "NULL buffer");
   return launch_gaussian_head(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_gaussian_head_backward(const FsAdapterBwdArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr && a->N >= 0 && a->H >= 1 && a->W >= 1 && a->sh_degree >= 0 && a->sh_degree <= 3, "bad arguments");
+  FS_REQUIRE(a->N == 0 || (a->raw && a->depths && a->ext && a->K && a->d_raw && a->d_depths && a->d_opacities && a->d_coords), "NULL buffer");
+  return launch_gaussian_head_bwd(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_depth_head_backward(const FsDepthHeadBwdArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr && a->B >= 0 && a->D >= 1 && a->h >= 1 && a->w >= 1 && a->B <= 65535, "bad sizes");
+  FS_REQUIRE(a->B == 0 || (a->logits && a->candi && a->stats && a->d_logits), "NULL buffer");
+  FS_REQUIRE(a->B == 0 || !(a->upsample && a->g_weights_up) || (a->argmax_up && a->D <= 256), "g_weights_up needs argmax_up scratch and D <= 256");
+  return launch_depth_head_bwd(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fs_ply_vertices(const FsPlyArgs* a, void* stream) {

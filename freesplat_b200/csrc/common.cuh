@@ -33,10 +33,13 @@ int launch_cost_volume_bwd(const FsCostVolumeArgs& a, cudaStream_t s);  // cost_
 int launch_ptf_view_setup(int V, int H, int W, const float* ext, const float* K, float* E_inv, float* K_px, cudaStream_t s);  // ptf.cu
 int launch_ptf_match(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
 int launch_ptf_merge(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
+int launch_ptf_merge_bwd(const FsPtfMergeBwdArgs& a, cudaStream_t s);   // ptf.cu
 int launch_gaussian_head(const FsAdapterArgs& a, cudaStream_t s);   // adapter.cu
 int launch_backproject(const FsBackprojectArgs& a, cudaStream_t s);   // adapter.cu
 int launch_ply_vertices(const FsPlyArgs& a, cudaStream_t s);          // adapter.cu
 int launch_depth_head(const FsDepthHeadArgs& a, cudaStream_t s);    // depth_head.cu
+int launch_depth_head_bwd(const FsDepthHeadBwdArgs& a, cudaStream_t s);   // depth_head.cu
+int launch_gaussian_head_bwd(const FsAdapterBwdArgs& a, cudaStream_t s);  // adapter.cu
 int launch_ptf_gru_tc(const FsPtfGruArgs& a, cudaStream_t s);
 size_t ptf_gru_wscratch_bytes();
 int launch_ptf_gru_inputs(int M, int F, const int* pj, const int* pp, const float* feats, const float* dens, const float* wemb,

@@ -296,6 +296,130 @@ __global__ void __launch_bounds__(256) depth_head_expect_kernel(FsDepthHeadArgs 
   a.depth[(size_t)b * HW + i] = a.log_planes ? expf(E) : 1.0f / E;
 }
 
+// ---------------------------------------------------------------------------------------------------- backward (training)
+// The reference differentiates the tail through softmax, the expectation, exp / reciprocal, two bilinear x2 upsamplings and
+// a max over the upsampled planes (networks.py:130-152).  Here: (1) per coarse pixel the softmax statistics (max, sum exp,
+// expectation) are recomputed in one coalesced pass; (2) if depth_weights received a gradient, the plane that attains the
+// maximum of every fine pixel is found (4 taps x D planes from L2); (3) one thread per coarse pixel gathers what reaches it
+// -- its own expectation / depth gradients, the <= 6x6 fine pixels whose bilinear taps include it (aten's align_corners
+// rule, the same fp32 arithmetic as the forward) -- and writes the whole logit column:
+//   d logit_d = p_d (candi_d dE + dP_d - sum_j p_j (candi_j dE + dP_j)),  dP_d = sum over fine pixels with arg max d of g w_tap.
+__device__ __forceinline__ void up_taps(int dst, int n_in, int n_out, int& i0, int& i1, float& w0, float& w1) {
+  const float scale = n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
+  const float src = scale * (float)dst;
+  i0 = min((int)src, n_in - 1);
+  const float lam = fminf(fmaxf(src - (float)i0, 0.f), 1.f);
+  i1 = min(i0 + 1, n_in - 1);
+  w0 = 1.f - lam; w1 = lam;
+}
+
+__global__ void __launch_bounds__(256) depth_head_stats_kernel(FsDepthHeadBwdArgs a) {
+  const size_t HW = (size_t)a.h * a.w;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= HW) return;
+  const int b = blockIdx.y;
+  const float* lp = a.logits + (size_t)b * a.D * HW + i;
+  float m = -INFINITY;
+  for (int d = 0; d < a.D; d++) m = fmaxf(m, __ldg(lp + (size_t)d * HW));
+  float s = 0.f, acc = 0.f;
+  for (int d = 0; d < a.D; d++) {
+    const float e = expf(__ldg(lp + (size_t)d * HW) - m);
+    s += e; acc = fmaf(__ldg(a.candi + d), e, acc);
+  }
+  float* st = a.stats + 3 * ((size_t)b * HW + i);
+  st[0] = m; st[1] = s; st[2] = acc / s;
+}
+
+__global__ void __launch_bounds__(256) depth_head_argmax_kernel(FsDepthHeadBwdArgs a) {
+  const int Ho = 2 * a.h, Wo = 2 * a.w;
+  const size_t HWo = (size_t)Ho * Wo, HW = (size_t)a.h * a.w;
+  const size_t f = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (f >= HWo) return;
+  const int b = blockIdx.y;
+  const int Y = (int)(f / Wo), X = (int)(f - (size_t)Y * Wo);
+  int y0, y1, x0, x1; float wy0, wy1, wx0, wx1;
+  up_taps(Y, a.h, Ho, y0, y1, wy0, wy1);
+  up_taps(X, a.w, Wo, x0, x1, wx0, wx1);
+  const size_t t[4] = {(size_t)y0 * a.w + x0, (size_t)y0 * a.w + x1, (size_t)y1 * a.w + x0, (size_t)y1 * a.w + x1};
+  float mm[4], ws[4];
+  const float wt[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float* st = a.stats + 3 * ((size_t)b * HW + t[k]);
+    mm[k] = st[0]; ws[k] = wt[k] / st[1];
+  }
+  const float* lp = a.logits + (size_t)b * a.D * HW;
+  float best = -INFINITY;
+  int arg = 0;
+  for (int d = 0; d < a.D; d++) {
+    // bilinear of the softmax planes in aten's order: (top-left wx0 + top-right wx1) wy0 + (bottom ...) wy1
+    const float* l = lp + (size_t)d * HW;
+    const float p00 = expf(__ldg(l + t[0]) - mm[0]) * ws[0], p01 = expf(__ldg(l + t[1]) - mm[1]) * ws[1];
+    const float p10 = expf(__ldg(l + t[2]) - mm[2]) * ws[2], p11 = expf(__ldg(l + t[3]) - mm[3]) * ws[3];
+    const float v = (p00 + p01) + (p10 + p11);
+    if (v > best) { best = v; arg = d; }
+  }
+  a.argmax_up[(size_t)b * HWo + f] = (uint8_t)arg;
+}
+
+__global__ void __launch_bounds__(128) depth_head_bwd_kernel(FsDepthHeadBwdArgs a) {
+  const size_t HW = (size_t)a.h * a.w;
+  const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= HW) return;
+  const int b = blockIdx.y;
+  const int y = (int)(i / a.w), x = (int)(i - (size_t)y * a.w);
+  const float* stb = a.stats + 3 * (size_t)b * HW;
+  const float m = stb[3 * i], s = stb[3 * i + 1], E = stb[3 * i + 2];
+  float dE = a.g_expect ? a.g_expect[(size_t)b * HW + i] : 0.f;
+  if (a.g_depth) dE += a.g_depth[(size_t)b * HW + i] * (a.log_planes ? expf(E) : -1.0f / (E * E));
+  // contributions of the fine grid (scale 0 only)
+  constexpr int kMaxList = 36;
+  int ld[kMaxList];
+  float lc[kMaxList];
+  int nl = 0;
+  if (a.upsample && (a.g_depth_up || a.g_weights_up)) {
+    const int Ho = 2 * a.h, Wo = 2 * a.w;
+    const size_t HWo = (size_t)Ho * Wo;
+    for (int Y = max(0, 2 * y - 2); Y <= min(Ho - 1, 2 * y + 3); Y++) {
+      int y0, y1; float wy0, wy1;
+      up_taps(Y, a.h, Ho, y0, y1, wy0, wy1);
+      const float wy = (y0 == y ? wy0 : 0.f) + (y1 == y ? wy1 : 0.f);
+      if (wy == 0.f && y0 != y && y1 != y) continue;
+      for (int X = max(0, 2 * x - 2); X <= min(Wo - 1, 2 * x + 3); X++) {
+        int x0, x1; float wx0, wx1;
+        up_taps(X, a.w, Wo, x0, x1, wx0, wx1);
+        if (x0 != x && x1 != x) continue;
+        const float wx = (x0 == x ? wx0 : 0.f) + (x1 == x ? wx1 : 0.f);
+        const float wgt = wy * wx;
+        const size_t f = (size_t)b * HWo + (size_t)Y * Wo + X;
+        if (a.g_depth_up) {
+          const float fine = (stb[3 * ((size_t)y0 * a.w + x0) + 2] * wx0 + stb[3 * ((size_t)y0 * a.w + x1) + 2] * wx1) * wy0 +
+                             (stb[3 * ((size_t)y1 * a.w + x0) + 2] * wx0 + stb[3 * ((size_t)y1 * a.w + x1) + 2] * wx1) * wy1;
+          dE += a.g_depth_up[f] * (a.log_planes ? expf(fine) : -1.0f / (fine * fine)) * wgt;
+        }
+        if (a.g_weights_up && nl < kMaxList) {
+          const float g = a.g_weights_up[f] * wgt;
+          if (g != 0.f) { ld[nl] = (int)a.argmax_up[f]; lc[nl] = g; nl++; }
+        }
+      }
+    }
+  }
+  const float* lp = a.logits + (size_t)b * a.D * HW + i;
+  float* dp = a.d_logits + (size_t)b * a.D * HW + i;
+  const float inv_s = 1.0f / s;
+  float S = dE * E;
+  for (int k = 0; k < nl; k++) {
+    const float p = expf(__ldg(lp + (size_t)ld[k] * HW) - m) * inv_s;
+    lc[k] *= p;                      // p_{d*} g w
+    S += lc[k];
+  }
+  for (int d = 0; d < a.D; d++) {
+    const float p = expf(__ldg(lp + (size_t)d * HW) - m) * inv_s;
+    dp[(size_t)d * HW] = p * (__ldg(a.candi + d) * dE - S);
+  }
+  for (int k = 0; k < nl; k++) dp[(size_t)ld[k] * HW] += lc[k];
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -321,6 +445,24 @@ static int encode_tile_map(const FsDepthHeadArgs& a, CUtensorMap* out) {
 }
 
 }  // namespace dh
+
+int launch_depth_head_bwd(const FsDepthHeadBwdArgs& a, cudaStream_t s) {
+  using namespace dh;
+  if (a.B == 0) return FS_OK;
+  const size_t HW = (size_t)a.h * a.w;
+  dim3 g1((unsigned)((HW + 255) / 256), (unsigned)a.B);
+  depth_head_stats_kernel<<<g1, 256, 0, s>>>(a);
+  int rc;
+  if ((rc = check_cuda(cudaGetLastError(), "depth_head_stats_kernel"))) return rc;
+  if (a.upsample && a.g_weights_up) {
+    dim3 g2((unsigned)((4 * HW + 255) / 256), (unsigned)a.B);
+    depth_head_argmax_kernel<<<g2, 256, 0, s>>>(a);
+    if ((rc = check_cuda(cudaGetLastError(), "depth_head_argmax_kernel"))) return rc;
+  }
+  dim3 g3((unsigned)((HW + 127) / 128), (unsigned)a.B);
+  depth_head_bwd_kernel<<<g3, 128, 0, s>>>(a);
+  return check_cuda(cudaGetLastError(), "depth_head_bwd_kernel");
+}
 
 int launch_depth_head(const FsDepthHeadArgs& a, cudaStream_t s) {
   using namespace dh;

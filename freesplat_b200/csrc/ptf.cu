@@ -21,6 +21,11 @@ namespace fs {
 constexpr int kPtfThreads = 256;
 constexpr int kPtfItems = 512;    // items per block in the flag scans (2 per thread; 1024 left the merge kernel below one wave)
 
+static inline int ptf_blocks(int n_upper, int HW) {
+  const int m = n_upper > HW ? n_upper : HW;
+  return (m + kPtfItems - 1) / kPtfItems;
+}
+
 // counters (int32[8]) of one step: [0] N_in  [1] n_keep  [2] n_match  [3] n_append  [4] N_out
 __global__ void __launch_bounds__(kPtfThreads) ptf_project_kernel(FsPtfArgs a) {
   const int N = a.counts_in[0];
@@ -203,6 +208,8 @@ __global__ void __launch_bounds__(kPtfThreads) ptf_compact_kernel(FsPtfArgs a) {
     }
     if (k < HW && a.append[k]) d_px = n_keep + n_match + off_app + ra[r];
     s_dst_old[t] = d_old; s_dst_px[t] = d_px; s_pair[t] = pr;
+    if (a.map_old != nullptr && k < N) a.map_old[k] = d_old;
+    if (a.map_px != nullptr && k < HW) a.map_px[k] = d_px;
     // ---- scalar / small fields: one thread per item ----
     if (d_old >= 0) {
       if (pr < 0) {
@@ -277,6 +284,117 @@ __global__ void __launch_bounds__(kPtfThreads) ptf_compact_kernel(FsPtfArgs a) {
       }
     }
   }
+}
+
+// ---- backward of the merge (training).  Same block shape as ptf_compact_kernel: 512 old items and 512 pixels per block;
+// scalar fields by one thread per item, feature rows as 16-byte chunks by the whole block (coalesced).
+__global__ void __launch_bounds__(kPtfThreads) ptf_merge_bwd_kernel(FsPtfMergeBwdArgs a) {
+  constexpr int R = kPtfItems / kPtfThreads;
+  const int N = a.N, HW = a.H * a.W, F = a.F;
+  const int base = blockIdx.x * kPtfItems;
+  __shared__ int s_src_old[kPtfItems], s_src_px[kPtfItems], s_pair[kPtfItems];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int t = r * kPtfThreads + threadIdx.x, k = base + t;
+    int so = -1, sp = -1, pr = -1;
+    if (k < N) {
+      const int d = a.map_old[k];
+      so = d;
+      auto G = [&](const float* g, size_t idx) { return g ? g[idx] : 0.f; };
+      if (!a.match[k]) {
+#pragma unroll
+        for (int e = 0; e < 3; e++) a.d_coords[3 * (size_t)k + e] = G(a.g_coords, 3 * (size_t)d + e);
+        a.d_dens[k] = G(a.g_dens, d); a.d_wemb[k] = G(a.g_wemb, d); a.d_depth[k] = G(a.g_depth, d);
+#pragma unroll
+        for (int e = 0; e < 16; e++) a.d_ext[16 * (size_t)k + e] = G(a.g_ext, 16 * (size_t)d + e);
+      } else {
+        pr = d - a.n_keep;
+        so = -2;                                        // fused row: the latent gradient goes to the GRU, not to feats[k]
+        const int p = a.pix[k];
+        const float w0 = a.dens[k], w1 = a.v_dens[p], ws = w0 + w1;
+        const float r0 = w0 / ws, r1 = w1 / ws;
+        float gw0 = G(a.g_dens, d), gw1 = gw0;
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+          const float g = G(a.g_coords, 3 * (size_t)d + e);
+          const float x0 = a.coords[3 * (size_t)k + e], x1 = a.v_coords[3 * (size_t)p + e];
+          const float o = wmean(x0, w0, x1, w1, ws);
+          a.d_coords[3 * (size_t)k + e] = g * r0;
+          atomicAdd(a.dv_coords + 3 * (size_t)p + e, g * r1);
+          gw0 += g * (x0 - o) / ws; gw1 += g * (x1 - o) / ws;
+        }
+        {
+          const float g = G(a.g_depth, d);
+          const float x0 = a.depth[k], x1 = a.v_depth[p];
+          const float o = wmean(x0, w0, x1, w1, ws);
+          a.d_depth[k] = g * r0;
+          atomicAdd(a.dv_depth + p, g * r1);
+          gw0 += g * (x0 - o) / ws; gw1 += g * (x1 - o) / ws;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          const float g = G(a.g_ext, 16 * (size_t)d + e);
+          const float x0 = a.ext[16 * (size_t)k + e], x1 = a.v_ext[e];
+          const float o = wmean(x0, w0, x1, w1, ws);
+          a.d_ext[16 * (size_t)k + e] = g * r0;
+          gw0 += g * (x0 - o) / ws; gw1 += g * (x1 - o) / ws;
+        }
+        a.d_dens[k] = gw0;
+        atomicAdd(a.dv_dens + p, gw1);
+        const float gw = G(a.g_wemb, d);
+        a.d_wemb[k] = gw;
+        atomicAdd(a.dv_wemb + p, gw);
+      }
+    }
+    if (k < HW) {
+      const int d = a.map_px[k];
+      sp = d;
+      if (d >= 0) {                                     // appended pixel: plain copies (never a partner of a fused row)
+#pragma unroll
+        for (int e = 0; e < 3; e++) a.dv_coords[3 * (size_t)k + e] = a.g_coords ? a.g_coords[3 * (size_t)d + e] : 0.f;
+        a.dv_dens[k] = a.g_dens ? a.g_dens[d] : 0.f;
+        a.dv_wemb[k] = a.g_wemb ? a.g_wemb[d] : 0.f;
+        a.dv_depth[k] = a.g_depth ? a.g_depth[d] : 0.f;
+      }
+    }
+    s_src_old[t] = so; s_src_px[t] = sp; s_pair[t] = pr;
+  }
+  __syncthreads();
+  const int cpr = F >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(a.g_feats);
+  float4* d4 = reinterpret_cast<float4*>(a.d_feats);
+  float4* dv4 = reinterpret_cast<float4*>(a.dv_feats);
+  float4* dg4 = reinterpret_cast<float4*>(a.d_gru);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < kPtfItems * cpr; idx += kPtfThreads) {
+    const int t = idx / cpr, ch = idx - t * cpr;
+    const int k = base + t;
+    if (k < N) {
+      const int so = s_src_old[t];
+      const int row = so == -2 ? a.n_keep + s_pair[t] : so;
+      const float4 g = g4 ? g4[(size_t)row * cpr + ch] : zero;
+      if (so == -2) { dg4[(size_t)s_pair[t] * cpr + ch] = g; d4[(size_t)k * cpr + ch] = zero; }
+      else d4[(size_t)k * cpr + ch] = g;
+    }
+    if (k < HW) {
+      const int sp = s_src_px[t];
+      dv4[(size_t)k * cpr + ch] = (sp >= 0 && g4) ? g4[(size_t)sp * cpr + ch] : zero;
+    }
+  }
+}
+
+int launch_ptf_merge_bwd(const FsPtfMergeBwdArgs& a, cudaStream_t s) {
+  const int HW = a.H * a.W;
+  int rc;
+  // the view-side scalars of matched pixels accumulate with atomics (z-buffer ties: several globals per pixel)
+  if ((rc = check_cuda(cudaMemsetAsync(a.dv_coords, 0, (size_t)HW * 3 * sizeof(float), s), "memset dv_coords"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(a.dv_dens, 0, (size_t)HW * sizeof(float), s), "memset dv_dens"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(a.dv_wemb, 0, (size_t)HW * sizeof(float), s), "memset dv_wemb"))) return rc;
+  if ((rc = check_cuda(cudaMemsetAsync(a.dv_depth, 0, (size_t)HW * sizeof(float), s), "memset dv_depth"))) return rc;
+  const int nb = ptf_blocks(a.N, HW);
+  ptf_merge_bwd_kernel<<<nb, kPtfThreads, 0, s>>>(a);
+  return check_cuda(cudaGetLastError(), "ptf_merge_bwd_kernel");
 }
 
 __global__ void ptf_fill_kernel(uint32_t* p, uint32_t v, int n) {
@@ -366,10 +484,7 @@ int launch_ptf_gru_output(int M, int F, const float* A1, const float* z_lin, con
   return check_cuda(cudaGetLastError(), "ptf_gru_output_kernel");
 }
 
-static inline int ptf_blocks(int n_upper, int HW) {
-  const int m = n_upper > HW ? n_upper : HW;
-  return (m + kPtfItems - 1) / kPtfItems;
-}
+
 
 // ---- per-view constants of the fold: E_i^-1 and the pixel-space intrinsics (encoder_freesplat.py:445-454) ----
 // The reference calls extrinsic.inverse() (LAPACK on the CPU, cuSOLVER / MAGMA on the GPU: the two differ in the last

@@ -37,8 +37,16 @@ class FsPtfArgs(C.Structure):
         ("block_counts", C.c_void_p), ("pair_j", C.c_void_p), ("pair_p", C.c_void_p), ("counts_out", C.c_void_p),
         ("gru_out", C.c_void_p),
         ("o_feats", C.c_void_p), ("o_coords", C.c_void_p), ("o_dens", C.c_void_p), ("o_wemb", C.c_void_p),
-        ("o_ext", C.c_void_p), ("o_depth", C.c_void_p),
+        ("o_ext", C.c_void_p), ("o_depth", C.c_void_p), ("map_old", C.c_void_p), ("map_px", C.c_void_p),
     ]
+
+
+class FsPtfMergeBwdArgs(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("F", C.c_int32), ("N", C.c_int32), ("n_keep", C.c_int32), ("n_match", C.c_int32)] + \
+        [(n, C.c_void_p) for n in ("coords", "dens", "ext", "depth", "v_coords", "v_dens", "v_depth", "v_ext", "match", "pix", "map_old",
+                                   "map_px", "g_feats", "g_coords", "g_dens", "g_wemb", "g_ext", "g_depth", "d_feats", "d_coords",
+                                   "d_dens", "d_wemb", "d_ext", "d_depth", "dv_feats", "dv_coords", "dv_dens", "dv_wemb", "dv_depth",
+                                   "d_gru")]
 
 
 def positional_encoding(positions: torch.Tensor, freqs: int) -> torch.Tensor:
@@ -142,7 +150,7 @@ def _gru_fused(gru, M, F, pair_j, pair_p, state, view_feats, view_dens, view_wem
     return out
 
 
-def _ptf_args(h, w, F, n_upper, depth_thres, state, cin, view, scratch, counts_out, out=None, gru_out=None):
+def _ptf_args(h, w, F, n_upper, depth_thres, state, cin, view, scratch, counts_out, out=None, gru_out=None, maps=(None, None)):
     feats, coords, dens, wemb, ext, depth = state
     v_feats, v_coords, v_dens, v_wemb, v_depth, v_ext, E_inv, K_px = view
     zbuf, pix, zeta, match, append, block_counts, pair_j, pair_p = scratch
@@ -154,13 +162,15 @@ def _ptf_args(h, w, F, n_upper, depth_thres, state, cin, view, scratch, counts_o
         v_depth=ptr(v_depth), v_ext=ptr(v_ext), E_inv=ptr(E_inv), K_px=ptr(K_px),
         zbuf=ptr(zbuf), pix=ptr(pix), zeta=ptr(zeta), match=ptr(match), append=ptr(append), block_counts=ptr(block_counts),
         pair_j=ptr(pair_j), pair_p=ptr(pair_p), counts_out=ptr(counts_out), gru_out=ptr(gru_out),
-        o_feats=ptr(o[0]), o_coords=ptr(o[1]), o_dens=ptr(o[2]), o_wemb=ptr(o[3]), o_ext=ptr(o[4]), o_depth=ptr(o[5]))
+        o_feats=ptr(o[0]), o_coords=ptr(o[1]), o_dens=ptr(o[2]), o_wemb=ptr(o[3]), o_ext=ptr(o[4]), o_depth=ptr(o[5]),
+        map_old=ptr(maps[0]), map_px=ptr(maps[1]))
 
 
 class _PtfMerge(torch.autograd.Function):
-    """Differentiable wrapper of fs_ptf_merge (training path).  forward = the compaction / merge kernel;
-    backward routes gradients through the saved index maps (kept -> old state, appended -> view i,
-    fused -> both, including the derivative of the density-weighted means w.r.t. the densities)."""
+    """Differentiable wrapper of fs_ptf_merge (training path).  forward = the compaction / merge kernel, which also leaves
+    the index maps (where every old row / appended pixel went); backward = fs_ptf_merge_backward: one kernel routes the
+    gradients back (kept -> old state, appended -> view i, fused -> both by their density weights plus the derivative of the
+    weighted means w.r.t. the densities; the latent rows of fused Gaussians go to the GRU output)."""
 
     @staticmethod
     def forward(ctx, feats, coords, dens, wemb, ext, depth, v_feats, v_coords, v_dens, v_wemb, v_depth, gru_out, meta):
@@ -174,57 +184,43 @@ class _PtfMerge(torch.autograd.Function):
         state = tuple(t.contiguous() for t in (feats, coords, dens, wemb, ext, depth))
         view = (v_feats.contiguous(), v_coords.contiguous(), v_dens.contiguous(), v_wemb.contiguous(), v_depth.contiguous(),
                 v_ext, E_inv, K_px)
+        zbuf, pix, zeta, match, append, block_counts, pair_j, pair_p = scratch
+        map_old = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+        map_px = torch.empty(h * w, dtype=torch.int32, device=dev)
         a = _ptf_args(h, w, F, N, depth_thres, state, cin, view, scratch, counts_row, out,
-                      None if gru_out is None else gru_out.contiguous())
+                      None if gru_out is None else gru_out.contiguous(), maps=(map_old, map_px))
         with torch.cuda.device(dev):
             check(L.fs_ptf_merge(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs_ptf_merge")
-        zbuf, pix, zeta, match, append, block_counts, pair_j, pair_p = scratch
-        keep_idx = torch.nonzero(match[:N] == 0).squeeze(1)
-        app_idx = torch.nonzero(append).squeeze(1)
-        pj, pp = pair_j[:M].long(), pair_p[:M].long()
-        ctx.sizes = (N, nk, M, na, h * w, F)
-        ctx.save_for_backward(keep_idx, app_idx, pj, pp, coords, dens, ext, depth, v_coords, v_dens, v_depth, v_ext,
-                              out[1], out[4], out[5])
+        ctx.sizes = (N, nk, M, na, h, w, F)
+        # the scratch buffers are reused by the next fold step: keep private copies of the two that backward reads
+        ctx.save_for_backward(state[1], state[2], state[4], state[5], view[1], view[2], view[4], v_ext,
+                              match[:max(N, 1)].clone(), pix[:max(N, 1)].clone(), map_old, map_px)
         ctx.has_gru = gru_out is not None
         return out
 
     @staticmethod
     def backward(ctx, gF, gX, gD, gW, gE, gZ):
-        (keep_idx, app_idx, pj, pp, coords, dens, ext, depth, v_coords, v_dens, v_depth, v_ext, oX, oE, oZ) = ctx.saved_tensors
-        N, nk, M, na, HW, F = ctx.sizes
+        L = _lib.lib()
+        (coords, dens, ext, depth, v_coords, v_dens, v_depth, v_ext, match, pix, map_old, map_px) = ctx.saved_tensors
+        N, nk, M, na, h, w, F = ctx.sizes
         dev = coords.device
-        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
-        g_feats, g_coords, g_dens, g_wemb, g_ext, g_depth = z(N, F), z(N, 3), z(N), z(N), z(N, 16), z(N)
-        gv_feats, gv_coords, gv_dens, gv_wemb, gv_depth = z(HW, F), z(HW, 3), z(HW), z(HW), z(HW)
-        # kept rows and appended rows are plain copies
-        g_feats[keep_idx] = gF[:nk]; g_coords[keep_idx] = gX[:nk]; g_dens[keep_idx] = gD[:nk]; g_wemb[keep_idx] = gW[:nk]
-        g_ext[keep_idx] = gE[:nk]; g_depth[keep_idx] = gZ[:nk]
-        s0 = nk + M
-        gv_feats[app_idx] = gF[s0:]; gv_coords[app_idx] = gX[s0:]; gv_dens[app_idx] = gD[s0:]; gv_wemb[app_idx] = gW[s0:]
-        gv_depth[app_idx] = gZ[s0:]
-        g_gru = None
-        if M > 0:
-            sl = slice(nk, s0)
-            g_gru = gF[sl] if ctx.has_gru else None
-            w0, w1 = dens[pj], v_dens[pp]
-            ws = w0 + w1
-            r0, r1 = w0 / ws, w1 / ws
-            gw0 = gD[sl].clone(); gw1 = gD[sl].clone()                    # dens' = w0 + w1
-            # coords
-            g = gX[sl]
-            g_coords[pj] = g * r0[:, None]; gv_coords.index_add_(0, pp, g * r1[:, None])
-            gw0 += (g * (coords[pj] - oX[sl])).sum(-1) / ws; gw1 += (g * (v_coords[pp] - oX[sl])).sum(-1) / ws
-            # depth
-            g = gZ[sl]
-            g_depth[pj] = g * r0; gv_depth.index_add_(0, pp, g * r1)
-            gw0 += g * (depth[pj] - oZ[sl]) / ws; gw1 += g * (v_depth[pp] - oZ[sl]) / ws
-            # extrinsics (view i's matrix is a constant)
-            g = gE[sl]
-            g_ext[pj] = g * r0[:, None]
-            gw0 += (g * (ext[pj] - oE[sl])).sum(-1) / ws; gw1 += (g * (v_ext[None] - oE[sl])).sum(-1) / ws
-            g_dens[pj] = gw0; gv_dens.index_add_(0, pp, gw1)
-            g_wemb[pj] = gW[sl]; gv_wemb.index_add_(0, pp, gW[sl])          # wemb' = wemb_j + wemb_p
-        return (g_feats, g_coords, g_dens, g_wemb, g_ext, g_depth, gv_feats, gv_coords, gv_dens, gv_wemb, gv_depth, g_gru, None)
+        HW = h * w
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        c = lambda g: None if g is None else g.contiguous()
+        gF, gX, gD, gW, gE, gZ = map(c, (gF, gX, gD, gW, gE, gZ))
+        d_state = (e(N, F), e(N, 3), e(N), e(N), e(N, 16), e(N))
+        d_view = (e(HW, F), e(HW, 3), e(HW), e(HW), e(HW))
+        d_gru = e(M, F) if M > 0 else None
+        a = FsPtfMergeBwdArgs(H=h, W=w, F=F, N=N, n_keep=nk, n_match=M, coords=ptr(coords), dens=ptr(dens), ext=ptr(ext),
+                              depth=ptr(depth), v_coords=ptr(v_coords), v_dens=ptr(v_dens), v_depth=ptr(v_depth), v_ext=ptr(v_ext),
+                              match=ptr(match), pix=ptr(pix), map_old=ptr(map_old), map_px=ptr(map_px),
+                              g_feats=ptr(gF), g_coords=ptr(gX), g_dens=ptr(gD), g_wemb=ptr(gW), g_ext=ptr(gE), g_depth=ptr(gZ),
+                              d_feats=ptr(d_state[0]), d_coords=ptr(d_state[1]), d_dens=ptr(d_state[2]), d_wemb=ptr(d_state[3]),
+                              d_ext=ptr(d_state[4]), d_depth=ptr(d_state[5]), dv_feats=ptr(d_view[0]), dv_coords=ptr(d_view[1]),
+                              dv_dens=ptr(d_view[2]), dv_wemb=ptr(d_view[3]), dv_depth=ptr(d_view[4]), d_gru=ptr(d_gru))
+        with torch.cuda.device(dev):
+            check(L.fs_ptf_merge_backward(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs_ptf_merge_backward")
+        return (*d_state, *d_view, d_gru if ctx.has_gru else None, None)
 
 
 def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, image_shape, depth_thres=0.1,

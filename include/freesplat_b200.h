@@ -214,10 +214,40 @@ typedef struct FsPtfArgs {
   /* merge inputs / outputs */
   const float* gru_out;    /* [n_match,F] fused features of the matched pairs                */
   float* o_feats; float* o_coords; float* o_dens; float* o_wemb; float* o_ext; float* o_depth;
+  /* optional (training): where every input row went.  map_old[j] = output row of global Gaussian j (kept or fused),
+   * map_px[p] = output row of appended pixel p or -1.  NULL = not written.                                          */
+  int32_t* map_old;        /* [n_upper] */
+  int32_t* map_px;         /* [HW]      */
 } FsPtfArgs;
 
 int fs_ptf_match(const FsPtfArgs* args, void* stream);
 int fs_ptf_merge(const FsPtfArgs* args, void* stream);
+
+/* Backward of fs_ptf_merge (training; the reference gets it from autograd through its index / cat ops,
+ * encoder_freesplat.py:492-519): gradients of the new state -> gradients of the old state, of view i's candidates and of
+ * the GRU output rows.  Kept / appended rows are copies; a fused row j (partner pixel p) splits by the density weights
+ * r0 = w0/(w0+w1), r1 = w1/(w0+w1), and the densities receive the derivative of the weighted means.  Several globals may
+ * share a partner pixel (z-buffer ties): the view-side scalars accumulate with atomics (zeroed by the call).
+ * Any g_* input may be NULL (= zero).                                                                              */
+typedef struct FsPtfMergeBwdArgs {
+  int32_t H, W, F;
+  int32_t N;               /* old state size */
+  int32_t n_keep, n_match; /* counters of the step (counts_out[1], [2])                                             */
+  /* forward inputs */
+  const float* coords; const float* dens; const float* ext; const float* depth;       /* old state [N,...]          */
+  const float* v_coords; const float* v_dens; const float* v_depth; const float* v_ext;/* view i                    */
+  const uint8_t* match;    /* [N]  */
+  const int32_t* pix;      /* [N]  partner pixel of a matched global                                                */
+  const int32_t* map_old;  /* [N]  */
+  const int32_t* map_px;   /* [HW] */
+  /* upstream gradients w.r.t. the NEW state [N_out, ...] */
+  const float* g_feats; const float* g_coords; const float* g_dens; const float* g_wemb; const float* g_ext; const float* g_depth;
+  /* outputs */
+  float* d_feats;  float* d_coords;  float* d_dens;  float* d_wemb;  float* d_ext;  float* d_depth;     /* [N, ...]  */
+  float* dv_feats; float* dv_coords; float* dv_dens; float* dv_wemb; float* dv_depth;                   /* [HW, ...] */
+  float* d_gru;            /* [n_match, F] gradient of the GRU output rows (NULL if n_match == 0)                   */
+} FsPtfMergeBwdArgs;
+int fs_ptf_merge_backward(const FsPtfMergeBwdArgs* args, void* stream);
 /* Per-view constants of the fold for all V views in one launch: E_inv[v] = extrinsics[v]^-1 (encoder_freesplat.py:454;
  * canonical arithmetic: fp64 cofactor expansion, one rounding to fp32) and the pixel-space intrinsics K_px[v]
  * (rows 0 / 1 of the normalised K times W / H, :445-447).  extrinsics [V,16], intrinsics [V,9] -> E_inv [V,16], K_px [V,9]. */
@@ -271,6 +301,27 @@ typedef struct FsAdapterArgs {
 } FsAdapterArgs;
 int fs_gaussian_head(const FsAdapterArgs* args, void* stream);
 
+/* Backward of fs_gaussian_head (training): upstream gradients of the head's outputs (any may be NULL = zero) -> gradients
+ * of raw, depths, opacities, coords and the per-Gaussian c2w matrices (the reference: autograd through
+ * gaussian_adapter.py:151-172).                                                                                     */
+typedef struct FsAdapterBwdArgs {
+  int32_t N, H, W, sh_degree;
+  float scale_min, scale_max, eps;
+  const float* raw; const float* depths; const float* ext; const float* K;       /* forward inputs                 */
+  const float* g_means;      /* [N,3]      */
+  const float* g_cov;        /* [N,3,3]    */
+  const float* g_harmonics;  /* [N,3,d_sh] */
+  const float* g_opacities;  /* [N]        */
+  const float* g_scales;     /* [N,3]      */
+  const float* g_rotations;  /* [N,4]      */
+  float* d_raw;              /* [N,7+3*d_sh] */
+  float* d_depths;           /* [N]        */
+  float* d_opacities;        /* [N]        */
+  float* d_coords;           /* [N,3]      */
+  float* d_ext;              /* [N,16] or NULL */
+} FsAdapterBwdArgs;
+int fs_gaussian_head_backward(const FsAdapterBwdArgs* args, void* stream);
+
 /* ------------------------------------------------------------ .ply vertex table */
 /* The per-Gaussian part of export_ply (src/model/ply_export.py:26-92): [N,17] float rows
  * (x y z nx ny nz f_dc_0..2 opacity scale_0..2 rot_0..3) ready to be written after a binary_little_endian header.   */
@@ -319,6 +370,24 @@ typedef struct FsDepthHeadArgs {
 } FsDepthHeadArgs;
 int fs_depth_head(const FsDepthHeadArgs* args, void* stream);
 
+/* Backward of fs_depth_head (training): gradients of the tail's outputs (any may be NULL = zero) -> gradient of the plane
+ * logits.  The reference: autograd through networks.py:130-152 (softmax, expectation, exp / reciprocal, bilinear x2,
+ * max over the upsampled planes).  `stats` and `argmax_up` are scratch written by the call.                           */
+typedef struct FsDepthHeadBwdArgs {
+  int32_t B, D, h, w;
+  int32_t log_planes, upsample, reserved0, reserved1;
+  const float* logits;       /* [B,D,h,w]                                                         */
+  const float* candi;        /* [D]                                                               */
+  const float* g_expect;     /* [B,h,w]   d/d log_depth_pred_s{i}                                 */
+  const float* g_depth;      /* [B,h,w]   d/d depth_pred_s{i}                                     */
+  const float* g_depth_up;   /* [B,2h,2w] d/d depth_pred_s-1   (upsample only)                    */
+  const float* g_weights_up; /* [B,2h,2w] d/d depth_weights    (upsample only)                    */
+  float* stats;              /* scratch [B,h,w,3]: max, sum exp, expectation                      */
+  uint8_t* argmax_up;        /* scratch [B,2h,2w] (needed when g_weights_up is given; D <= 256)   */
+  float* d_logits;           /* [B,D,h,w]                                                         */
+} FsDepthHeadBwdArgs;
+int fs_depth_head_backward(const FsDepthHeadBwdArgs* args, void* stream);
+
 /* ------------------------------------------------------------ CUDA graphs */
 /* A launch sequence whose arguments (pointers, sizes) do not change between steps -- e.g. fs_raster_forward on a static
  * workspace -- can be recorded once and replayed with ONE cudaGraphLaunch: no host-side launch gaps between its kernels.
@@ -332,7 +401,7 @@ int fs_graph_destroy(void* graph_exec);
 
 int fs_abi_version(void);
 /* sizeof() of the argument structs as compiled (0: FsRasterFwdArgs, 1: FsRasterBwdArgs, 2: FsCostVolumeArgs, 3: FsPtfArgs,
- * 4: FsPtfGruArgs, 5: FsAdapterArgs, 6: FsDepthHeadArgs, 7: FsBackprojectArgs, 8: FsPlyArgs; -1 otherwise) so that a foreign-language binding can verify its layout.      */
+ * 4: FsPtfGruArgs, 5: FsAdapterArgs, 6: FsDepthHeadArgs, 7: FsBackprojectArgs, 8: FsPlyArgs, 9: FsPtfMergeBwdArgs, 10: FsAdapterBwdArgs, 11: FsDepthHeadBwdArgs; -1 otherwise) so that a foreign-language binding can verify its layout.      */
 int fs_struct_size(int32_t which);
 const char* fs_last_error(void);      /* thread-local, valid until the next call  */
 int fs_device_sm_count(void);         /* negative FsStatus on failure             */

@@ -25,14 +25,21 @@ def main():
         ext = synth.camera_path(4)[torch.randint(0, 4, (N,), generator=g)].clone()
         ext[:, :3, :] += 0.01 * torch.randn((N, 3, 4), generator=g)
         K = synth.intrinsics(1)[0]
+        leaves = [t.requires_grad_(True) for t in (raw, depths, opac, coords, ext)]      # gradients by the reference's own autograd
         out = ad.forward(ext[None, None, :, None, None], K[None, None, None, None, None].expand(1, 1, N, 1, 1, 3, 3),
                          torch.zeros(1, 1, N, 1, 1, 2), depths[None, None, :, None, None], opac[None, None, :, None, None],
                          raw[None, None, :, None, None, :], (h, w), coords=coords[None, None, :, None, None, :])
-        sq = lambda t: t[0, 0, :, 0, 0].numpy()
+        names = ("means", "covariances", "harmonics", "opacities", "scales", "rotations")
+        wts = {k: torch.randn(getattr(out, k)[0, 0, :, 0, 0].shape, generator=g) for k in names}
+        sum((getattr(out, k)[0, 0, :, 0, 0] * wts[k]).sum() for k in names).backward()
+        grads = dict(g_raw=raw.grad.numpy(), g_depths=depths.grad.numpy(), g_opac=opac.grad.numpy(), g_coords=coords.grad.numpy(),
+                     g_ext=ext.grad.numpy(), **{"w_" + k: v.numpy() for k, v in wts.items()})
+        raw, depths, opac, coords, ext = (t.detach() for t in leaves)
+        sq = lambda t: t[0, 0, :, 0, 0].detach().numpy()
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), meta=np.array([seed, N, h, w]), raw=raw.numpy(),
                             depths=depths.numpy(), opac=opac.numpy(), coords=coords.numpy(), ext=ext.numpy(), K=K.numpy(),
                             means=sq(out.means), covariances=sq(out.covariances), harmonics=sq(out.harmonics),
-                            opacities=sq(out.opacities), scales=sq(out.scales), rotations=sq(out.rotations))
+                            opacities=sq(out.opacities), scales=sq(out.scales), rotations=sq(out.rotations), **grads)
         print(name, N)
 
 

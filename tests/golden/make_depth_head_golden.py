@@ -29,16 +29,38 @@ def main():
                 dd.conv_depth[f"{i}"][1].weight.mul_(gain)
         feats = [torch.randn(B, 8, h0 // (2 ** i), w0 // (2 ** i)) for i in range(5)]
         cap = {}
+        live = {}
+
+        def hook(m, inp, out, i=None):
+            cap[i] = out.detach().clone()
+            out.retain_grad()                       # gradient of the tail's loss w.r.t. the plane logits (reference autograd)
+            live[i] = out
         for i in range(4):
-            dd.conv_depth[f"{i}"].register_forward_hook(lambda m, inp, out, i=i: cap.__setitem__(i, out.detach().clone()))
-        with torch.no_grad():
-            out = dd(feats)
+            dd.conv_depth[f"{i}"].register_forward_hook(lambda m, inp, out, i=i: hook(m, inp, out, i))
+        out = dd(feats)
+        gen = torch.Generator().manual_seed(300 + seed)
+        wts = {}
+        loss = 0.0
+        for i in range(4):
+            for key in (f"depth_pred_s{i}_b1hw", f"log_depth_pred_s{i}_b1hw"):
+                wts[key] = torch.randn(out[key].shape, generator=gen)
+                loss = loss + (out[key] * wts[key]).sum()
+        for key in ("depth_pred_s-1_b1hw", "depth_weights"):
+            wts[key] = torch.randn(out[key].shape, generator=gen)
+            loss = loss + (out[key] * wts[key]).sum()
+        loss.backward()
+        out = {k: v.detach() for k, v in out.items()}
         z = dict(meta=np.array([seed, B, D, h0, w0, int(logp)]), near_far=np.array([near, far], np.float32),
                  candi=dd.depth_candi_curr.reshape(-1).numpy().astype(np.float32))
         for i in range(4):
             z[f"logits_s{i}"] = cap[i].numpy()
             z[f"depth_s{i}"] = out[f"depth_pred_s{i}_b1hw"].numpy()
             z[f"log_depth_s{i}"] = out[f"log_depth_pred_s{i}_b1hw"].numpy()
+            z[f"g_logits_s{i}"] = live[i].grad.numpy()
+            z[f"w_depth_s{i}"] = wts[f"depth_pred_s{i}_b1hw"].numpy()
+            z[f"w_log_depth_s{i}"] = wts[f"log_depth_pred_s{i}_b1hw"].numpy()
+        z["w_depth_up"] = wts["depth_pred_s-1_b1hw"].numpy()
+        z["w_weights_up"] = wts["depth_weights"].numpy()
         z["depth_up"] = out["depth_pred_s-1_b1hw"].numpy()
         z["weights_up"] = out["depth_weights"].numpy()
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **z)

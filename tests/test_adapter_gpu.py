@@ -23,6 +23,26 @@ def test_vs_reference_golden(path):
         np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max() * 1e-3 + 1e-12, err_msg=k)
 
 
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_backward_vs_reference_autograd_golden(path):
+    """fs_gaussian_head_backward against the gradients the REFERENCE's own autograd produced for a seeded loss on all six
+    outputs (make_adapter_golden.py): raw features, depths, opacities, coordinates and the per-Gaussian c2w matrices."""
+    from freesplat_b200.adapter import gaussian_head
+    from tests.helpers import grad_report
+    z = np.load(path)
+    _, N, h, w = [int(x) for x in z["meta"]]
+    t = lambda k, g=True: torch.from_numpy(z[k]).to("cuda:0").requires_grad_(g)
+    raw, depths, opac, coords, ext = t("raw"), t("depths"), t("opac"), t("coords"), t("ext")
+    g = gaussian_head(raw, depths, opac, coords, ext, t("K", False), (h, w))
+    loss = sum((getattr(g, k) * torch.from_numpy(z["w_" + k]).to("cuda:0")).sum()
+               for k in ("means", "covariances", "harmonics", "opacities", "scales", "rotations"))
+    loss.backward()
+    for name, got, want in (("raw", raw.grad, z["g_raw"]), ("depths", depths.grad, z["g_depths"]), ("opac", opac.grad, z["g_opac"]),
+                            ("coords", coords.grad, z["g_coords"]), ("ext", ext.grad, z["g_ext"])):
+        rep = grad_report(got.cpu().numpy().reshape(want.shape), want, max_outlier_frac=0.0)
+        assert rep["ok"], (name, rep)
+
+
 def test_feeds_the_rasterizer_in_place():
     """The head's outputs go straight into render_views (layouts [N,3,3] / [N,3,d_sh])."""
     from freesplat_b200 import decoder, synth

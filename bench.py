@@ -222,16 +222,28 @@ def cpu_reference_views_per_s(sc, n_views: int, repeats: int):
     return n_views * repeats / dt, oracle.num_threads(), dt
 
 
-class PlainGRU:
-    """networks.py:188-214 by name only: the module tree fs_ptf_gru reads its weights from."""
+def PlainGRU(state, dev):
+    """The GRU of networks.py:188-214 (module / parameter names as in the reference, so that its state dict loads): the
+    module fs_ptf_gru reads its weights from in inference, and the torch module the training fold calls."""
+    import torch
 
-    def __new__(cls, state, dev):
-        import torch
-        mk = lambda din: torch.nn.Sequential(torch.nn.Linear(din, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64))
-        g = torch.nn.Module()
-        g.mlp_z, g.mlp_r, g.mlp_n = mk(176), mk(176), mk(152)
-        g.load_state_dict(state)
-        return g.to(dev)
+    class GRU(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            mk = lambda din: torch.nn.Sequential(torch.nn.Linear(din, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64))
+            self.mlp_z, self.mlp_r, self.mlp_n = mk(176), mk(176), mk(152)
+
+        def forward(self, input_feat, hidden_feat, input_weights_emb, hidden_weights_emb):
+            x1 = torch.cat((input_feat, input_weights_emb), dim=-1)
+            cat = torch.cat((hidden_feat, hidden_weights_emb, x1), dim=-1)
+            r, z = torch.sigmoid(self.mlp_r(cat)), torch.sigmoid(self.mlp_z(cat))
+            q = torch.tanh(self.mlp_n(torch.cat((r * hidden_feat, x1), dim=-1)))
+            return (1 - z) * hidden_feat + z * q
+    g = GRU()
+    g.load_state_dict(state)
+    for p_ in g.parameters():
+        p_.requires_grad_(False)
+    return g.to(dev)
 
 
 def _flat_ptf(inp):
@@ -350,6 +362,14 @@ def ops_section(dev, peaks):
         out[f"ptf_{tag}"] = e
         del gargs, res
 
+    # ---- BASELINE config 3 as ONE chained training step: cost volume -> depth-head tail -> back-projection -> PTF fold ->
+    #      Gaussian head -> raster forward, MSE loss, backward through every operator of the path.  The conv stacks between the
+    #      operators (CVEncoder / DepthDecoder / Gaussian MLP: cuDNN, out of scope) are replaced by fixed cheap stand-ins. ----
+    try:
+        out["config3_train_step"] = config3_step(dev, gru)
+    except Exception as exc:
+        out["config3_train_step"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     # ---- raster forward + backward, config 3: P = 460 800, 4 target views ----
     sc = synth.pixel_aligned_scene(seed=3, h=H, w=W, n_context=3, n_target=4, keep=460800).to(dev)
     bg = torch.zeros((4, 3), device=dev)
@@ -366,6 +386,65 @@ def ops_section(dev, peaks):
                                                    sc.harmonics, sc.opacities), n=5)
     out["raster_cfg3_P460800_4views"] = {"fwd_gpu_ms": f_ms, "fwd_bwd_gpu_ms": gpu_ms(train_step, n=5)}
     return out
+
+
+def config3_step(dev, gru):
+    import torch
+    import torch.nn.functional as Fn
+    from freesplat_b200 import adapter, decoder, depth_head, ptf, synth
+    from freesplat_b200.cost_volume import AVGFeatureVolumeManager
+    V, K, T, Hf, Wf, D, C = 3, 2, 4, 120, 160, 128, 48
+    HW = H * W
+    inp = {k: v.to(dev) for k, v in synth.cost_volume_inputs(0, V, K, C, Hf, Wf).items()}
+    m = AVGFeatureVolumeManager(Hf, Wf, num_depth_bins=D, matching_dim_size=C).to(dev)
+    with torch.no_grad():
+        for p_, w_ in zip([m.mlp.net[0].weight, m.mlp.net[0].bias, m.mlp.net[2].weight, m.mlp.net[2].bias, m.mlp.net[4].weight,
+                           m.mlp.net[4].bias], synth.cost_volume_mlp(0)):
+            p_.copy_(w_)
+    g = torch.Generator().manual_seed(0)
+    cur = inp["cur_feats"].clone().requires_grad_(True); src = inp["src_feats"].clone().requires_grad_(True)
+    latents = (0.5 * torch.randn((V, HW, 64), generator=g)).to(dev).requires_grad_(True)
+    candi = torch.linspace(float(torch.log(torch.tensor(synth.NEAR))), float(torch.log(torch.tensor(4.0))), D, device=dev)
+    ctx_ext = synth.camera_path(V, spacing=0.25).to(dev)
+    Kn = synth.intrinsics(V).to(dev)
+    tgt_ext = synth.camera_path(T, spacing=0.08, t0=0.2).to(dev)
+    tgt_K = synth.intrinsics(T).to(dev)
+    near = torch.full((T,), synth.NEAR, device=dev); far = torch.full((T,), synth.FAR, device=dev)
+    bg = torch.zeros((T, 3), device=dev)
+    target = torch.rand((T, 3, H, W), generator=g).to(dev)
+    raw_bias = torch.zeros(34, device=dev); raw_bias[:3] = -3.0
+    for p_ in gru.parameters():
+        p_.requires_grad_(True)
+    info = {}
+
+    def forward():
+        vol = m(**{**inp, "cur_feats": cur, "src_feats": src})                          # [3,128,120,160]   fs_cost_volume_forward
+        logits = Fn.interpolate(vol * 8.0, scale_factor=2, mode="nearest")                # stand-in: CVEncoder + DepthDecoder convs
+        o = depth_head.depth_regression(logits, candi, True, upsample=True)               # fs_depth_head (TMA)
+        depth = o["depth_up"].reshape(V, HW); dens = o["weights_up"].reshape(V, HW)
+        coords = adapter.backproject_depth(depth, Kn[0], ctx_ext, (H, W))                 # fs_backproject
+        F_, X_, E_, Z_ = ptf.fuse_views(gru, latents, coords, dens, dens, depth, ctx_ext, Kn, (H, W))   # fs_ptf_*
+        gs = adapter.gaussian_head(F_[:, :34] + raw_bias, Z_, torch.sigmoid(F_[:, 34]), X_, E_, Kn[0], (H, W))   # fs_gaussian_head
+        color, _ = decoder.render_views(tgt_ext, tgt_K, near, far, (H, W), bg, gs.means, gs.covariances, gs.harmonics, gs.opacities)
+        info["fused_gaussians"] = int(F_.shape[0])
+        return ((color - target) ** 2).mean()
+
+    def train():
+        for t_ in (cur, src, latents, *gru.parameters(), *m.parameters()):
+            t_.grad = None
+        forward().backward()
+
+    def infer():
+        with torch.no_grad():
+            forward()
+    res = {"fwd_bwd_gpu_ms": gpu_ms(train, n=3, warm=2), "fwd_only_gpu_ms": gpu_ms(infer, n=3, warm=1)}
+    for p_ in gru.parameters():
+        p_.requires_grad_(False)
+    res.update(info)
+    res["note"] = ("3 context views (cost volume K=2, D=128), PTF fold, Gaussian head, 4 target views, MSE; every operator of the path "
+                   "forward and backward in libfreesplat_b200.so except the GRU backward (torch autograd through its six nn.Linear); "
+                   "the fold reads its step counters on the host once per view in training")
+    return res
 
 
 def config5_section(dev, rank, world, steps=3):

@@ -42,6 +42,7 @@ class FsRasterBwdArgs(C.Structure):
         ("dL_dcolor", vp), ("dL_ddepth", vp), ("dL_dalpha", vp), ("dL_dscreen", vp),
         ("dL_dmeans2D", vp), ("dL_dmeans3D", vp), ("dL_dcov3D", vp), ("dL_dshs", vp),
         ("dL_dcolors", vp), ("dL_dopacities", vp), ("dL_dscales", vp), ("dL_drotations", vp),
+        ("peer_delta", vp), ("shard_rows", C.c_int32), ("world", C.c_int32),
     ]
 
 
@@ -51,7 +52,7 @@ EXPORTS = [
     "fs_raster_forward", "fs_raster_backward", "fs_mark_visible", "fs_camera_records",
     "fs_cost_volume_forward", "fs_cost_volume_backward",
     "fs_ptf_match", "fs_ptf_merge", "fs_ptf_gru_inputs", "fs_ptf_gru_update", "fs_ptf_gru_output",
-    "fs_ptf_view_setup", "fs_ptf_merge_backward", "fs_gaussian_head_backward", "fs_depth_head_backward", "fs_graph_capture_begin", "fs_graph_capture_end", "fs_graph_launch", "fs_graph_destroy",
+    "fs_ptf_view_setup", "fs_ptf_merge_backward", "fs_gaussian_head_backward", "fs_depth_head_backward", "fs_backproject_backward", "fs_graph_capture_begin", "fs_graph_capture_end", "fs_graph_launch", "fs_graph_destroy",
     "fs_ptf_gru", "fs_ptf_gru_wscratch_bytes", "fs_gaussian_head", "fs_depth_head", "fs_backproject", "fs_ply_vertices",
 ]
 

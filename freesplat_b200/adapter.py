@@ -36,27 +36,57 @@ class FsBackprojectArgs(C.Structure):
                 ("depth", C.c_void_p), ("K", C.c_void_p), ("c2w", C.c_void_p), ("means", C.c_void_p)]
 
 
+class _Backproject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, d, K, E, h, w):
+        L = _lib.lib()
+        dev = d.device
+        V = E.shape[0]
+        means = torch.empty((V, h * w, 3), dtype=torch.float32, device=dev)
+        a = FsBackprojectArgs(V=V, H=h, W=w, depth=ptr(d), K=ptr(K), c2w=ptr(E), means=ptr(means))
+        with torch.cuda.device(dev):
+            check(L.fs_backproject(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs_backproject")
+        ctx.save_for_backward(K, E)
+        ctx.hw = (h, w)
+        return means
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        K, E = ctx.saved_tensors
+        h, w = ctx.hw
+        dev = g.device
+        V = E.shape[0]
+        g = g.contiguous()
+        d_depth = torch.empty((V, h * w), dtype=torch.float32, device=dev)
+        a = FsBackprojectArgs(V=V, H=h, W=w, depth=None, K=ptr(K), c2w=ptr(E), means=None)
+        with torch.cuda.device(dev):
+            check(L.fs_backproject_backward(C.byref(a), C.c_void_p(ptr(g)), C.c_void_p(ptr(d_depth)),
+                                            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs_backproject_backward")
+        return d_depth, None, None, None, None
+
+
 def backproject_depth(depths, intrinsics, extrinsics, image_shape) -> torch.Tensor:
     """World coordinates of every pixel of the context views: what GaussianAdapter.forward(..., fusion=True) returns
     (/root/reference/src/model/encoder/common/gaussian_adapter.py:175-189, Create_from_depth_map.project :48-68; call site
     src/model/encoder/encoder_freesplat.py:318-327).  depths [V,H*W] or [V,H,W], intrinsics [3,3] NORMALISED (view 0's, as
-    the reference uses), extrinsics [V,4,4] camera-to-world -> means [V,H*W,3].  Inference path; CPU tensors raise."""
+    the reference uses), extrinsics [V,4,4] camera-to-world -> means [V,H*W,3].  Differentiable w.r.t. the depths; CPU tensors
+    raise."""
     if not depths.is_cuda:
         raise _lib.FreeSplatB200Error("backproject_depth needs CUDA tensors (no CPU fallback exists)")
-    if torch.is_grad_enabled() and (depths.requires_grad or extrinsics.requires_grad):
-        raise _lib.FreeSplatB200Error("backproject_depth is the inference path; wrap the call in torch.no_grad()")
-    L = _lib.lib()
-    dev = depths.device
     h, w = image_shape
     V = extrinsics.shape[0]
-    d = depths.detach().float().reshape(V, h * w).contiguous()
+    d = depths.float().reshape(V, h * w).contiguous()
     K = intrinsics.detach().float().reshape(9).contiguous()
     E = extrinsics.detach().float().reshape(V, 16).contiguous()
-    means = torch.empty((V, h * w, 3), dtype=torch.float32, device=dev)
-    a = FsBackprojectArgs(V=V, H=h, W=w, depth=ptr(d), K=ptr(K), c2w=ptr(E), means=ptr(means))
-    with torch.cuda.device(dev):
-        check(L.fs_backproject(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "fs_backproject")
-    return means
+    if torch.is_grad_enabled() and d.requires_grad:
+        return _Backproject.apply(d, K, E, h, w)
+    return _Backproject.forward(_NoCtx(), d.detach(), K, E, h, w)
+
+
+class _NoCtx:
+    def save_for_backward(self, *a):
+        pass
 
 
 @dataclass

@@ -222,6 +222,32 @@ __global__ void __launch_bounds__(256) backproject_kernel(FsBackprojectArgs a) {
     o[r] = __fmaf_rn(E[4 * r + 3], 1.0f, __fmaf_rn(E[4 * r + 2], z, __fmaf_rn(E[4 * r + 1], y, __fmul_rn(E[4 * r], x))));
 }
 
+// backward of backproject_kernel w.r.t. the depth map: world = c2w . (x z, y z, z, 1) with x = (j - cx)/fx, y = (i - cy)/fy
+//   d depth = sum_r g[r] (E[r][0] x + E[r][1] y + E[r][2])
+__global__ void __launch_bounds__(256) backproject_bwd_kernel(FsBackprojectArgs a, const float* __restrict__ g_means, float* __restrict__ d_depth) {
+  const int HW = a.H * a.W;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= HW) return;
+  const int v = blockIdx.y;
+  const int i = p / a.W, j = p - i * a.W;
+  const float fx = __fmul_rn(a.K[0], (float)a.W), cx = __fmul_rn(a.K[2], (float)a.W);
+  const float fy = __fmul_rn(a.K[4], (float)a.H), cy = __fmul_rn(a.K[5], (float)a.H);
+  const float x = ((float)j - cx) / fx, y = ((float)i - cy) / fy;
+  const float* E = a.c2w + 16 * (size_t)v;
+  const float* g = g_means + 3 * ((size_t)v * HW + p);
+  float acc = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; r++) acc += g[r] * (E[4 * r] * x + E[4 * r + 1] * y + E[4 * r + 2]);
+  d_depth[(size_t)v * HW + p] = acc;
+}
+
+int launch_backproject_bwd(const FsBackprojectArgs& a, const float* g_means, float* d_depth, cudaStream_t s) {
+  if (a.V <= 0) return FS_OK;
+  dim3 grid((unsigned)((a.H * a.W + 255) / 256), (unsigned)a.V);
+  backproject_bwd_kernel<<<grid, 256, 0, s>>>(a, g_means, d_depth);
+  return check_cuda(cudaGetLastError(), "backproject_bwd_kernel");
+}
+
 int launch_backproject(const FsBackprojectArgs& a, cudaStream_t s) {
   if (a.V <= 0) return FS_OK;
   dim3 grid((unsigned)((a.H * a.W + 255) / 256), (unsigned)a.V);

@@ -94,6 +94,7 @@ int fs_raster_backward(const FsRasterBwdArgs* a, void* stream) {
                  a->status && a->dL_dcolor && a->dL_dscreen && a->dL_dmeans2D && a->dL_dmeans3D && a->dL_dopacities,
              "NULL buffer");
   FS_REQUIRE(!a->has_depth_grad || a->dL_ddepth, "has_depth_grad set but dL_ddepth is NULL");
+  FS_REQUIRE(a->peer_delta == nullptr || (a->world >= 1 && a->shard_rows >= 1), "peer_delta given but world / shard_rows are not");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int rc;
   if ((rc = launch_render_bwd(*a, s))) return rc;
@@ -215,6 +216,12 @@ int fs_backproject(const FsBackprojectArgs* a, void* stream) {
   FS_REQUIRE(a != nullptr && a->V >= 0 && a->V <= 65535 && a->H >= 1 && a->W >= 1 && (long long)a->H * a->W < (1ll << 30), "bad sizes");
   FS_REQUIRE(a->V == 0 || (a->depth && a->K && a->c2w && a->means), "NULL buffer");
   return launch_backproject(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_backproject_backward(const FsBackprojectArgs* a, const float* g_means, float* d_depth, void* stream) {
+  FS_REQUIRE(a != nullptr && a->V >= 0 && a->V <= 65535 && a->H >= 1 && a->W >= 1 && (long long)a->H * a->W < (1ll << 30), "bad sizes");
+  FS_REQUIRE(a->V == 0 || (a->K && a->c2w && g_means && d_depth), "NULL buffer");
+  return launch_backproject_bwd(*a, g_means, d_depth, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fs_depth_head(const FsDepthHeadArgs* a, void* stream) {

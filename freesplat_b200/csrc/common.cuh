@@ -36,6 +36,7 @@ int launch_ptf_merge(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
 int launch_ptf_merge_bwd(const FsPtfMergeBwdArgs& a, cudaStream_t s);   // ptf.cu
 int launch_gaussian_head(const FsAdapterArgs& a, cudaStream_t s);   // adapter.cu
 int launch_backproject(const FsBackprojectArgs& a, cudaStream_t s);   // adapter.cu
+int launch_backproject_bwd(const FsBackprojectArgs& a, const float* g_means, float* d_depth, cudaStream_t s);   // adapter.cu
 int launch_ply_vertices(const FsPlyArgs& a, cudaStream_t s);          // adapter.cu
 int launch_depth_head(const FsDepthHeadArgs& a, cudaStream_t s);    // depth_head.cu
 int launch_depth_head_bwd(const FsDepthHeadBwdArgs& a, cudaStream_t s);   // depth_head.cu

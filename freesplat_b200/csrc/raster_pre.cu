@@ -361,9 +361,26 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
     }
     g_mean[0] += dm[0] * ss; g_mean[1] += dm[1] * ss; g_mean[2] += dm[2] * ss;
   }
+  if (a.peer_delta != nullptr) {
+    // fused reduce-scatter: this rank's partial sums go straight into the owner rank's buffers over NVLink (fire-and-forget
+    // reductions on peer-mapped memory; the buffers were zeroed on every rank and a cross-rank barrier follows the kernel)
+    const long long delta = a.peer_delta[min(i / a.shard_rows, a.world - 1)];
+    auto peer = [&](float* p) { return reinterpret_cast<float*>(reinterpret_cast<char*>(p) + delta); };
+    float* gm = peer(a.dL_dmeans3D + 3 * (size_t)i);
+    atomicAdd(gm, g_mean[0]); atomicAdd(gm + 1, g_mean[1]); atomicAdd(gm + 2, g_mean[2]);
+    atomicAdd(peer(a.dL_dopacities + i), g_op);
+    if (a.dL_dcov3D && a.cov_stride == 9) {
+      float* g = peer(a.dL_dcov3D + 9 * (size_t)i);
+      atomicAdd(g, g_cov[0]); atomicAdd(g + 1, g_cov[1]); atomicAdd(g + 2, g_cov[2]); atomicAdd(g + 4, g_cov[3]); atomicAdd(g + 5, g_cov[4]);
+      atomicAdd(g + 8, g_cov[5]);
+    } else if (a.dL_dcov3D) {
+      float* g = peer(a.dL_dcov3D + 6 * (size_t)i);
+#pragma unroll
+      for (int k = 0; k < 6; k++) atomicAdd(g + k, g_cov[k]);
+    }
+  } else {
   a.dL_dmeans3D[3 * (size_t)i] = g_mean[0]; a.dL_dmeans3D[3 * (size_t)i + 1] = g_mean[1]; a.dL_dmeans3D[3 * (size_t)i + 2] = g_mean[2];
   a.dL_dopacities[i] = g_op;
-  if (a.dL_dcolors) { a.dL_dcolors[3 * (size_t)i] = g_col[0]; a.dL_dcolors[3 * (size_t)i + 1] = g_col[1]; a.dL_dcolors[3 * (size_t)i + 2] = g_col[2]; }
   if (a.dL_dcov3D && a.cov_stride == 9) {      // gradient of the upper-triangle gather: lower triangle gets 0
     float* g = a.dL_dcov3D + 9 * (size_t)i;
     g[0] = g_cov[0]; g[1] = g_cov[1]; g[2] = g_cov[2]; g[3] = 0.f; g[4] = g_cov[3]; g[5] = g_cov[4]; g[6] = 0.f; g[7] = 0.f; g[8] = g_cov[5];
@@ -371,6 +388,8 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
 #pragma unroll
     for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)i + k] = g_cov[k];
   }
+  }
+  if (a.dL_dcolors) { a.dL_dcolors[3 * (size_t)i] = g_col[0]; a.dL_dcolors[3 * (size_t)i + 1] = g_col[1]; a.dL_dcolors[3 * (size_t)i + 2] = g_col[2]; }
   if (a.scales && a.rotations && a.dL_dscales && a.dL_drotations) {
     const float* q = a.rotations + 4 * (size_t)i;
     const float* s = a.scales + 3 * (size_t)i;
@@ -408,8 +427,15 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
     const int total = nblk * M3;
     const int qstep = kThreads / M3, rstep = kThreads - qstep * M3;
     int g = tid / M3, c = tid - g * M3;
+    const bool fused = a.peer_delta != nullptr;
     for (int k = tid; k < total; k += kThreads) {
-      dst[k] = s_gsh[g * sh_stride + c];
+      const float v = s_gsh[g * sh_stride + c];
+      if (fused) {
+        const long long delta = a.peer_delta[min((block_base + g) / a.shard_rows, a.world - 1)];
+        atomicAdd(reinterpret_cast<float*>(reinterpret_cast<char*>(dst + k) + delta), v);     // coalesced: 32 lanes, 128 contiguous bytes
+      } else {
+        dst[k] = v;
+      }
       g += qstep; c += rstep;
       if (c >= M3) { c -= M3; g++; }
     }

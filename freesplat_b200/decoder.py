@@ -105,7 +105,7 @@ def camera_records_fused(extrinsics, intrinsics, near, far, background_color, sc
 
 def render_views(extrinsics, intrinsics, near, far, image_shape, background_color, gaussian_means,
                  gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, scale_invariant=True,
-                 use_sh=True, depth_grad=False, check_overflow=None):
+                 use_sh=True, depth_grad=False, check_overflow=None, grad_reduce=None):
     """One scene, V target views.
 
     extrinsics [V,4,4], intrinsics [V,3,3], near/far [V], background_color [V,3],
@@ -126,7 +126,7 @@ def render_views(extrinsics, intrinsics, near, far, image_shape, background_colo
         shs=gaussian_sh_coefficients if use_sh else None,
         colors_precomp=None if use_sh else gaussian_sh_coefficients[:, :, 0],
         cov3D_precomp=gaussian_covariances, sh_degree=degree, depth_grad=depth_grad, sh_layout=1, cov_stride=9,
-        check_overflow=check_overflow)
+        check_overflow=check_overflow, grad_reduce=grad_reduce)
     return color, depth
 
 

@@ -423,8 +423,10 @@ class RasterPlan:
 
 
 def raster_backward_raw(st: RasterState, means3D, opacities, dL_dcolor, *, shs=None, colors_precomp=None,
-                        scales=None, rotations=None, cov3D_precomp=None, dL_ddepth=None, dL_dalpha=None):
-    """Gradients w.r.t. the op inputs, summed over the V views of `st`."""
+                        scales=None, rotations=None, cov3D_precomp=None, dL_ddepth=None, dL_dalpha=None, grad_reduce=None):
+    """Gradients w.r.t. the op inputs, summed over the V views of `st`.  grad_reduce: a parallel.FusedGradReduce -- the
+    per-Gaussian sums are then reduced over the RANKS inside the kernel (peer reductions over NVLink) and the returned
+    tensors are the fully summed, replicated gradients (views of the symmetric buffer, valid until its next begin())."""
     L = _lib.lib()
     dev = means3D.device
     P, V, H, W, M = st.P, st.V, st.H, st.W, st.M
@@ -444,6 +446,12 @@ def raster_backward_raw(st: RasterState, means3D, opacities, dL_dcolor, *, shs=N
             shs=None if shs is None else e(*shs.shape),
             colors=None if colors_precomp is None else e(P, 3),
             scales=e(P, 3) if use_sr else None, rotations=e(P, 4) if use_sr else None)
+        fused = grad_reduce is not None
+        if fused:
+            if use_sr or shs is None or st.cov_stride != 9 or not st.sh_layout:
+                raise _lib.FreeSplatB200Error("grad_reduce supports the in-place layouts of render_views ([G,3,3] covariances, [G,3,d] harmonics)")
+            grad_reduce.begin()
+            g.update(means3D=grad_reduce.means, cov3D=grad_reduce.cov, shs=grad_reduce.sh, opacities=grad_reduce.opac.view(P, 1))
         # the kernel needs somewhere to accumulate dL/dcov even when it is not returned
         cov_buf = g["cov3D"]
         dscreen = e(V, P, 12)
@@ -457,8 +465,13 @@ def raster_backward_raw(st: RasterState, means3D, opacities, dL_dcolor, *, shs=N
             dL_dcolor=ptr(dL_dcolor), dL_ddepth=ptr(dL_ddepth), dL_dalpha=ptr(dL_dalpha), dL_dscreen=ptr(dscreen),
             dL_dmeans2D=ptr(g["means2D"]), dL_dmeans3D=ptr(g["means3D"]), dL_dcov3D=ptr(cov_buf), dL_dshs=ptr(g["shs"]),
             dL_dcolors=ptr(g["colors"]), dL_dopacities=ptr(g["opacities"]), dL_dscales=ptr(g["scales"]),
-            dL_drotations=ptr(g["rotations"]))
+            dL_drotations=ptr(g["rotations"]), peer_delta=ptr(grad_reduce.peer_delta) if fused else None,
+            shard_rows=grad_reduce.shard_rows if fused else 0, world=grad_reduce.world if fused else 0)
         check(L.fs_raster_backward(C.byref(a), C.c_void_p(stream)), "fs_raster_backward")
+        if fused:
+            grad_reduce.finish()
+            m_, c_, s_, o_ = grad_reduce.result()
+            g.update(means3D=m_, cov3D=c_, shs=s_, opacities=o_.view(P, 1))
     g["screen"] = dscreen
     return g
 
@@ -469,7 +482,9 @@ class _RasterizeViews(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, views,
-                H, W, sh_degree, scale_modifier, prefiltered, depth_grad, sh_layout=0, cov_stride=6, check_overflow=None):
+                H, W, sh_degree, scale_modifier, prefiltered, depth_grad, sh_layout=0, cov_stride=6, check_overflow=None,
+                grad_reduce=None):
+        ctx.grad_reduce = grad_reduce
         if check_overflow is None:
             check_overflow = DEFAULT_CHECK
         needs_bwd = any(ctx.needs_input_grad)
@@ -507,17 +522,18 @@ class _RasterizeViews(torch.autograd.Function):
             g_color = torch.zeros((st.V, 3, st.H, st.W), dtype=torch.float32, device=means3D.device)
         dd = g_depth if (ctx.depth_grad and g_depth is not None) else None
         g = raster_backward_raw(st, means3D, opacities, g_color, shs=shs, colors_precomp=colors_precomp, scales=scales,
-                                rotations=rotations, cov3D_precomp=cov3D_precomp, dL_ddepth=dd, dL_dalpha=g_alpha)
+                                rotations=rotations, cov3D_precomp=cov3D_precomp, dL_ddepth=dd, dL_dalpha=g_alpha,
+                                grad_reduce=ctx.grad_reduce)
         gm2d = g["means2D"]
         return (g["means3D"], gm2d if st.V > 1 else gm2d[0], g["shs"], g["colors"],
                 g["opacities"].reshape(opacities.shape), g["scales"], g["rotations"],
                 None if g["cov3D"] is None else g["cov3D"].reshape(cov3D_precomp.shape), None,
-                None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None)
 
 
 def rasterize_views(means3D, opacities, views, image_height, image_width, *, shs=None, colors_precomp=None,
                     scales=None, rotations=None, cov3D_precomp=None, means2D=None, sh_degree=0, scale_modifier=1.0,
-                    prefiltered=False, depth_grad=False, sh_layout=0, cov_stride=6, check_overflow=None):
+                    prefiltered=False, depth_grad=False, sh_layout=0, cov_stride=6, check_overflow=None, grad_reduce=None):
     """Batched op: -> (color[V,3,H,W], radii[V,P], depth[V,H,W], alpha[V,H,W]).
 
     sh_layout=1 reads `shs` as [P,3,M] and cov_stride=9 reads `cov3D_precomp` as full [P,3,3] matrices -- the
@@ -534,7 +550,7 @@ def rasterize_views(means3D, opacities, views, image_height, image_width, *, shs
         means2D = torch.zeros((V, means3D.shape[0], 3), dtype=torch.float32, device=means3D.device)
     return _RasterizeViews.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
                                  views, image_height, image_width, sh_degree, scale_modifier, prefiltered, depth_grad,
-                                 sh_layout, cov_stride, check_overflow)
+                                 sh_layout, cov_stride, check_overflow, grad_reduce)
 
 
 class GaussianRasterizer(torch.nn.Module):

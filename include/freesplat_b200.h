@@ -140,6 +140,16 @@ typedef struct FsRasterBwdArgs {
   float* dL_dopacities;        /* [P]                                            */
   float* dL_dscales;           /* [P,3]  or NULL                                 */
   float* dL_drotations;        /* [P,4]  or NULL                                 */
+  /* Fused reduce-scatter over NVLink (optional, multi-GPU training: every rank back-propagates ITS target views into the
+   * replicated Gaussian set).  With peer_delta != NULL the per-Gaussian sums dL_dmeans3D / dL_dcov3D / dL_dshs /
+   * dL_dopacities are not stored locally but ADDED (red.global.add.f32 on peer-mapped memory) into the copy of these
+   * buffers that lives on rank owner(i) = min(i / shard_rows, world - 1).  peer_delta[r] = byte distance from this rank's
+   * buffers to rank r's (one symmetric allocation with the same layout on every rank; 0 for r = own rank).  The buffers
+   * must be zero on every rank before the first rank launches, and a cross-rank barrier must follow before they are read:
+   * the transfer then overlaps the kernel instead of following it as a separate all-reduce.                              */
+  const int64_t* peer_delta;   /* [world] device array, or NULL (plain local stores)                                   */
+  int32_t shard_rows;          /* Gaussians per owner rank                                                              */
+  int32_t world;
 } FsRasterBwdArgs;
 
 /* ------------------------------------------------------------- cost volume */
@@ -350,6 +360,8 @@ typedef struct FsBackprojectArgs {
   float* means;            /* [V,H*W,3]                                                               */
 } FsBackprojectArgs;
 int fs_backproject(const FsBackprojectArgs* args, void* stream);
+/* Backward w.r.t. the depth maps (training): g_means [V,H*W,3] -> d_depth [V,H,W]; `depth` / `means` of args are unused. */
+int fs_backproject_backward(const FsBackprojectArgs* args, const float* g_means, float* d_depth, void* stream);
 
 /* ------------------------------------------------------------ depth-regression head tail */
 /* Tail of DepthDecoder.forward (modules/networks.py:130-152) for one scale: softmax over the D planes, expectation of

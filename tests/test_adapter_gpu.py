@@ -87,3 +87,27 @@ def test_backproject_full_size_vs_oracle():
     with torch.no_grad():
         got = backproject_depth(depths.to("cuda:0"), K.to("cuda:0"), c2w.to("cuda:0"), (h, w)).cpu().numpy()
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_backproject_backward_vs_autograd():
+    """fs_backproject_backward against torch autograd through a plain restatement of Create_from_depth_map.project."""
+    from freesplat_b200 import synth
+    from freesplat_b200.adapter import backproject_depth
+    from tests.helpers import grad_report
+    dev = "cuda:0"
+    V, h, w = 3, 24, 40
+    g = torch.Generator().manual_seed(2)
+    depth = (0.5 + 4 * torch.rand((V, h * w), generator=g)).to(dev).requires_grad_(True)
+    Kn, c2w = synth.intrinsics(1)[0].to(dev), synth.camera_path(V).to(dev)
+    wts = torch.randn((V, h * w, 3), generator=g).to(dev)
+    (backproject_depth(depth, Kn, c2w, (h, w)) * wts).sum().backward()
+    got = depth.grad.clone()
+    d2 = depth.detach().clone().requires_grad_(True)
+    ii, jj = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
+    x = ((jj.reshape(-1) - Kn[0, 2] * w) / (Kn[0, 0] * w))[None] * d2
+    y = ((ii.reshape(-1) - Kn[1, 2] * h) / (Kn[1, 1] * h))[None] * d2
+    cam = torch.stack([x, y, d2, torch.ones_like(d2)], -1)                     # [V,HW,4]
+    world = torch.einsum("vrc,vnc->vnr", c2w[:, :3, :], cam)
+    (world * wts).sum().backward()
+    rep = grad_report(got.cpu().numpy(), d2.grad.cpu().numpy(), max_outlier_frac=0.0)
+    assert rep["ok"], rep

@@ -26,8 +26,24 @@ target = torch.rand((T, 3, h, w), generator=torch.Generator().manual_seed(1)).to
 leaf = lambda: [x.detach().clone().requires_grad_(True) for x in (sc.means, sc.covariances, sc.harmonics, sc.opacities)]
 
 
+FUSED = "--fused" in sys.argv and world > 1
+reducer = parallel.FusedGradReduce(int(sc.means.shape[0]), int(sc.harmonics.shape[-1]), dev) if FUSED else None
+
+
+def nvlink_tx_kib():
+    """Sum of the NVLink data TX counters of this rank's GPU (nvidia-smi nvlink -gt d), or None."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(local)], capture_output=True, text=True, timeout=20).stdout
+        return sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+    except Exception:
+        return None
+
+
 def sharded(params):
-    col, dep, ids = parallel.render_views_sharded(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (h, w), bg, *params)
+    col, dep, ids = parallel.render_views_sharded(sc.extrinsics, sc.intrinsics, sc.near, sc.far, (h, w), bg, *params,
+                                                  grad_reduce=reducer)
     loss = ((col - target[ids]) ** 2).sum() / (T * 3 * h * w)
     loss.backward()
     return loss.detach()
@@ -45,6 +61,7 @@ ps = leaf(); sharded(ps)
 err = max(float((a.grad - b.grad).abs().max() / (b.grad.abs().max() + 1e-30)) for a, b in zip(ps, pf))
 ms = []
 p = leaf()
+tx0 = nvlink_tx_kib()
 for it in range(12):                  # same parameter tensors every step (as in a training loop): the allocator reaches a steady state
     for x in p:
         x.grad = None
@@ -55,14 +72,18 @@ for it in range(12):                  # same parameter tensors every step (as in
     e0.record(); sharded(p); e1.record(); torch.cuda.synchronize()
     if it >= 6:
         ms.append(e0.elapsed_time(e1))
+tx1 = nvlink_tx_kib()
 t = parallel.max_over_ranks([sum(ms) / len(ms)], dev)[0]
 errs = parallel.max_over_ranks([err], dev)[0]
 if rank == 0:
     res = {"world": world, "target_views": T, "gaussians": int(sc.means.shape[0]), "ms_fwd_bwd_allreduce": t,
            "views_per_s_train": T / (t * 1e-3), "max_rel_grad_diff_vs_single_rank": errs,
-           "allreduce_bytes": int(sc.means.shape[0]) * (3 + 9 + 27 + 1) * 4}
+           "allreduce_bytes": int(sc.means.shape[0]) * (3 + 9 + 27 + 1) * 4,
+           "exchange": "reduce-scatter fused into preprocess_bwd_kernel (peer red.global.add over NVLink) + in-place all-gathers"
+                       if FUSED else "pack + NCCL all-reduce + unpack (parallel.sync_gaussian_grads)",
+           "nvlink_tx_kib_rank0_over_12_steps": None if tx0 is None or tx1 is None else tx1 - tx0}
     print(json.dumps(res))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"train_sharded_world{world}.json"), "w"))
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"train_sharded_world{world}{'_fused' if FUSED else ''}.json"), "w"))
 if world > 1:
     dist.destroy_process_group()

@@ -14,6 +14,8 @@
 // Per pixel and instance the arithmetic is the canonical order of oracle/raster_oracle.c:
 //   t = fma(cb, dy, ca*dx) ; power = fma(cc*dy, dy, t*dx) ; alpha = min(.99, o*exp(power)).
 // exp() is MUFU.EX2 (ex2.approx.ftz) of power*log2(e): |rel err| < 1e-6.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "raster_sort.cuh"
 
@@ -168,6 +170,186 @@ __global__ void __launch_bounds__(kThreads) render_fwd_kernel(
     out_depth[(size_t)v * HW + pix] = Dp;
     final_T[(size_t)v * HW + pix] = T_fin;
     n_contrib[(size_t)v * HW + pix] = last;
+  }
+}
+
+// ------------------------------------------------------------------------------- forward, two pixels per lane
+// Variant of render_fwd_kernel for the issue-bound regime (ncu r1: 75 % of the issue slots busy, 39 instructions per walked
+// (warp, instance)): a CTA of 128 threads renders the 16x16 tile, warp w owns an 8x8 sub-tile and every lane TWO vertically
+// adjacent pixels, (px, py) and (px, py + 1).  The two HALVES of a warp (lanes 0-15: rows 0-3, lanes 16-31: rows 4-7 of the
+// sub-tile) keep the 8x4 culling granularity of the one-pixel kernel: each half walks ITS OWN list of overlapping instances
+// (one ballot per half box; a lane reads the instance its half is at: two broadcast addresses per shared-memory load), so
+// one loop iteration retires an (8x4 region, instance) pair for both halves at once.
+// The pair shares dx; dy, the exponent, alpha, the transmittance test and the four
+// accumulations run on Blackwell's packed fp32 pipe (fma.rn.f32x2 / mul.rn.f32x2 / add.rn.f32x2 -> FFMA2 / FMUL2 / FADD2):
+// one instruction for both pixels.  Per-instance scalars (cb, cc, opacity, colour) enter as (s, s) pairs, which the SASS
+// encodes as a broadcast operand (`R.F32`) of the packed instruction: no duplicate staging, no MOVs.
+// Per pixel the arithmetic (and therefore every bit of the result) is that of
+// render_fwd_kernel:  t = fma(cb,dy,ca*dx); p = fma(cc*dy,dy,t*dx); alpha = min(.99, o*ex2(p)); T' = T*(1-alpha); C += c*(alpha*T).
+using f2 = unsigned long long;
+__device__ __forceinline__ f2 pk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// (lo, hi) += (s, s) * (wlo, whi): the loop-carried accumulators stay 32-bit values for the register allocator (64-bit
+// loop-carried asm operands cost two MOVs per accumulator and iteration: the destination pair was never coalesced)
+__device__ __forceinline__ void fma2_acc(float& lo, float& hi, float s, float wlo, float whi) {
+  asm("{\n\t.reg .b64 a, w, c;\n\tmov.b64 a, {%2, %2};\n\tmov.b64 w, {%3, %4};\n\tmov.b64 c, {%0, %1};\n\t"
+      "fma.rn.f32x2 c, a, w, c;\n\tmov.b64 {%0, %1}, c;\n\t}" : "+f"(lo), "+f"(hi) : "f"(s), "f"(wlo), "f"(whi));
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ void lds128_2(uint32_t addr, f2& a, f2& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ f2 lds64_1(uint32_t addr) { f2 a; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(a) : "r"(addr)); return a; }
+
+constexpr int kThreads2 = 128;
+constexpr int kSortSmemKeys2 = 2048;      // 16 KB: up to 14 CTAs of this kernel fit one SM; more crowded tiles sort in global memory
+
+struct __align__(16) Render2Smem {
+  float4 T[kThreads2];    // x, y, hx, hy           (sub-tile overlap test)
+  float4 L0[kThreads2];   // x, ca, y, cb
+  float4 L1[kThreads2];   // cc, o, r, g
+  float2 L2[kThreads2];   // b, depth
+};
+static_assert(sizeof(Render2Smem) <= (size_t)kSortSmemKeys2 * 8, "blend staging must fit in the sort buffer");
+
+__global__ void __launch_bounds__(kThreads2, 8) render_fwd2_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, unsigned long long* keybuf, uint32_t* point_list,
+    const float4* __restrict__ rec, const float* __restrict__ views, const uint32_t* __restrict__ status, int P, int H, int W,
+    int gx, int ntiles, float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
+    uint32_t* __restrict__ n_contrib) {
+  if (status[2]) return;
+  extern __shared__ unsigned long long skeys[];
+  Render2Smem& sm = *reinterpret_cast<Render2Smem*>(skeys);
+  const int t_flat = (int)order[blockIdx.x];
+  const int v = t_flat / ntiles, tile = t_flat - v * ntiles;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile_x = tile % gx, tile_y = tile / gx;
+  const int x0 = tile_x * 16 + (warp & 1) * 8, y0 = tile_y * 16 + (warp >> 1) * 8;
+  const int half = lane >> 4, hl = lane & 15;
+  const int px = x0 + (hl & 7), pyA = y0 + half * 4 + (hl >> 3) * 2, pyB = pyA + 1;
+  const bool insideA = px < W && pyA < H, insideB = px < W && pyB < H;
+  const float pxf = (float)px;
+  const f2 npy2 = pk2(-(float)pyA, -(float)pyB);
+  const float fx0 = (float)x0, fx1 = (float)(x0 + 7);
+  const float fyA0 = (float)y0, fyA1 = (float)(y0 + 3), fyB0 = (float)(y0 + 4), fyB1 = (float)(y0 + 7);
+  const uint2 range = ranges[t_flat];
+  const float4* __restrict__ rec_v = rec + (size_t)v * P * 3;
+  // ---- sort this tile's keys by (depth bits, Gaussian index) ----
+  {
+    const int n = (int)(range.y - range.x);
+    if (n > 0) {
+      unsigned long long* g = keybuf + range.x;
+      if (n <= kSortSmemKeys2) {
+        for (int k = tid; k < n; k += kThreads2) skeys[k] = g[k];
+        if (n <= 32) bitonic_sort_fixed<5, kThreads2>(skeys, n, tid);
+        else if (n <= 64) bitonic_sort_fixed<6, kThreads2>(skeys, n, tid);
+        else if (n <= 128) bitonic_sort_fixed<7, kThreads2>(skeys, n, tid);
+        else if (n <= 256) bitonic_sort_fixed<8, kThreads2>(skeys, n, tid);
+        else if (n <= 512) bitonic_sort_fixed<9, kThreads2>(skeys, n, tid);
+        else bitonic_sort_block<unsigned long long*, kThreads2>(skeys, n, tid);
+        for (int k = tid; k < n; k += kThreads2) {
+          const unsigned long long key = skeys[k];
+          g[k] = key;
+          point_list[range.x + k] = (uint32_t)(key & 0xffffffffull);
+        }
+      } else {
+        bitonic_sort_block<unsigned long long*, kThreads2>(g, n, tid);
+        for (int k = tid; k < n; k += kThreads2) point_list[range.x + k] = (uint32_t)(g[k] & 0xffffffffull);
+      }
+    }
+    __syncthreads();
+  }
+  const uint32_t aT = (uint32_t)__cvta_generic_to_shared(sm.T), a0 = (uint32_t)__cvta_generic_to_shared(sm.L0),
+                 a1 = (uint32_t)__cvta_generic_to_shared(sm.L1), a2 = (uint32_t)__cvta_generic_to_shared(sm.L2);
+
+  // T > 0: pixel still accumulating.  T < 0: finished, |T| is its final transmittance.
+  float TA = insideA ? 1.f : -1.f, TB = insideB ? 1.f : -1.f;
+  float c0A = 0.f, c0B = 0.f, c1A = 0.f, c1B = 0.f, c2A = 0.f, c2B = 0.f, dA = 0.f, dB = 0.f;
+  uint32_t lastA = 0, lastB = 0;
+  const f2 one2 = pk2(1.f, 1.f), mone2 = pk2(-1.f, -1.f);
+
+  for (uint32_t base = range.x; base < range.y; base += kThreads2) {
+    if (__syncthreads_count(TA < 0.f && TB < 0.f) == kThreads2) break;   // barrier also protects the smem reuse
+    const int n = min((int)kThreads2, (int)(range.y - base));
+    if (tid < n) {
+      const uint32_t id = point_list[base + tid];
+      const float4* r = rec_v + 3 * (size_t)id;
+      const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+      const float ca = (-0.5f * r0.z) * kLog2e, cb = (-r0.w) * kLog2e, cc = (-0.5f * r1.x) * kLog2e;
+      sm.T[tid] = make_float4(r0.x, r0.y, r2.z, r2.w);
+      sm.L0[tid] = make_float4(r0.x, ca, r0.y, cb);
+      sm.L1[tid] = make_float4(cc, r1.y, r1.z, r1.w);
+      sm.L2[tid] = make_float2(r2.x, r2.y);
+    }
+    __syncthreads();
+    if (__all_sync(kFull, TA < 0.f && TB < 0.f)) continue;
+    const uint32_t pos0 = base - range.x + 1u;      // contributor index of staged slot 0
+    for (int g = 0; g < n; g += 32) {
+      const int j = g + lane;
+      bool hitA = false, hitB = false;
+      if (j < n) {
+        const float4 q = lds128(aT + (uint32_t)j * 16u);
+        const bool hx = (q.x - q.z <= fx1) && (q.x + q.z >= fx0);
+        hitA = hx && (q.y - q.w <= fyA1) && (q.y + q.w >= fyA0);
+        hitB = hx && (q.y - q.w <= fyB1) && (q.y + q.w >= fyB0);
+      }
+      const unsigned mA = __ballot_sync(kFull, hitA), mB = __ballot_sync(kFull, hitB);
+      unsigned m = half ? mB : mA;                    // the instances THIS half of the warp still has to walk
+      while (__any_sync(kFull, m != 0u)) {
+        const bool valid = m != 0u;
+        const uint32_t jj = (uint32_t)g + (valid ? (uint32_t)(__ffs(m) - 1) : 0u);
+        m &= m - 1;
+        const float4 q0 = lds128(a0 + jj * 16u);     // x, ca, y, cb
+        const float4 q1 = lds128(a1 + jj * 16u);     // cc, o, r, g
+        const float dx = q0.x - pxf;
+        const float mm = q0.y * dx;
+        const f2 dy2 = add2(pk2(q0.z, q0.z), npy2);
+        const f2 t2 = fma2(pk2(q0.w, q0.w), dy2, pk2(mm, mm));
+        const f2 p2 = fma2(mul2(pk2(q1.x, q1.x), dy2), dy2, mul2(t2, pk2(dx, dx)));
+        float pA, pB;
+        unpk2(p2, pA, pB);
+        const f2 e2 = pk2(ex2_approx(pA), ex2_approx(pB));
+        float alA, alB;
+        unpk2(mul2(pk2(q1.y, q1.y), e2), alA, alB);
+        alA = fminf(0.99f, alA); alB = fminf(0.99f, alB);
+        const f2 al2 = pk2(alA, alB);
+        const f2 T2 = pk2(TA, TB);
+        float ttA, ttB;
+        unpk2(mul2(T2, fma2(al2, mone2, one2)), ttA, ttB);          // T * (1 - alpha)
+        const bool passA = valid && (pA <= 0.f) && (alA >= 1.f / 255.f) && (TA > 0.f);
+        const bool passB = valid && (pB <= 0.f) && (alB >= 1.f / 255.f) && (TB > 0.f);
+        const bool finA = passA && (ttA < 0.0001f), finB = passB && (ttB < 0.0001f);
+        const bool accA = passA && !finA, accB = passB && !finB;
+        float wA, wB;
+        unpk2(mul2(al2, T2), wA, wB);
+        wA = accA ? wA : 0.f; wB = accB ? wB : 0.f;
+        const float2 q2 = lds64(a2 + jj * 8u);       // b, depth
+        fma2_acc(c0A, c0B, q1.z, wA, wB); fma2_acc(c1A, c1B, q1.w, wA, wB);
+        fma2_acc(c2A, c2B, q2.x, wA, wB); fma2_acc(dA, dB, q2.y, wA, wB);
+        TA = finA ? -TA : (accA ? ttA : TA);
+        TB = finB ? -TB : (accB ? ttB : TB);
+        lastA = accA ? pos0 + jj : lastA;
+        lastB = accB ? pos0 + jj : lastB;
+      }
+      if (__all_sync(kFull, TA < 0.f && TB < 0.f)) break;
+    }
+  }
+  const float* bg = views + (size_t)v * kViewFloats + 35;
+  const size_t HW = (size_t)H * W;
+  float* oc = out_color + (size_t)v * 3 * HW;
+  if (insideA) {
+    const float T_fin = fabsf(TA);
+    const size_t pix = (size_t)pyA * W + px;
+    oc[pix] = fmaf(T_fin, bg[0], c0A); oc[HW + pix] = fmaf(T_fin, bg[1], c1A); oc[2 * HW + pix] = fmaf(T_fin, bg[2], c2A);
+    out_depth[(size_t)v * HW + pix] = dA; final_T[(size_t)v * HW + pix] = T_fin; n_contrib[(size_t)v * HW + pix] = lastA;
+  }
+  if (insideB) {
+    const float T_fin = fabsf(TB);
+    const size_t pix = (size_t)pyB * W + px;
+    oc[pix] = fmaf(T_fin, bg[0], c0B); oc[HW + pix] = fmaf(T_fin, bg[1], c1B); oc[2 * HW + pix] = fmaf(T_fin, bg[2], c2B);
+    out_depth[(size_t)v * HW + pix] = dB; final_T[(size_t)v * HW + pix] = T_fin; n_contrib[(size_t)v * HW + pix] = lastB;
   }
 }
 
@@ -339,8 +521,22 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
   }
 }
 
+// FS_RENDER_VARIANT=1 selects the one-pixel-per-lane kernel (A/B measurements); default: two pixels per lane, packed fp32
+static int render_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FS_RENDER_VARIANT"); v = (e && e[0] == '1') ? 1 : 2; }
+  return v;
+}
+
 int launch_render_fwd(const FsRasterFwdArgs& a, cudaStream_t s) {
   const int gx = tiles_x(a.W), gy = tiles_y(a.H);
+  if (render_variant() == 2) {
+    render_fwd2_kernel<<<gx * gy * a.V, kThreads2, kSortSmemKeys2 * 8, s>>>(
+        reinterpret_cast<const uint2*>(a.ranges), a.tile_count /* holds the tile order after binning */,
+        reinterpret_cast<unsigned long long*>(a.keybuf), a.point_list, reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P,
+        a.H, a.W, gx, gx * gy, a.out_color, a.out_depth, a.final_T, a.n_contrib);
+    return check_cuda(cudaGetLastError(), "render_fwd2_kernel");
+  }
   render_fwd_kernel<<<gx * gy * a.V, kThreads, kSortSmemKeys * 8, s>>>(
       reinterpret_cast<const uint2*>(a.ranges), a.tile_count /* holds the tile order after binning */,
       reinterpret_cast<unsigned long long*>(a.keybuf), a.point_list, reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P,

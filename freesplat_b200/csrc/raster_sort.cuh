@@ -15,7 +15,7 @@ __device__ __forceinline__ void stage_sync(bool block_wide) {
   if (block_wide) __syncthreads(); else __syncwarp();
 }
 
-template <typename KeyPtr>
+template <typename KeyPtr, int NT = kThreads>
 __device__ __forceinline__ void bitonic_sort_block(KeyPtr keys, int n, int tid) {
   int logN = 0;
   while ((1 << logN) < n) logN++;
@@ -24,7 +24,7 @@ __device__ __forceinline__ void bitonic_sort_block(KeyPtr keys, int n, int tid) 
   for (int lk = 1; lk <= logN; lk++) {
     const int k = 1 << lk, half = k >> 1;
     stage_sync(k > 64 || prevB > 64);
-    for (int c = tid; c < halfN; c += kThreads) {        // flip step
+    for (int c = tid; c < halfN; c += NT) {               // flip step
       const int b = c >> (lk - 1), off = c & (half - 1);
       const int i = (b << lk) + off, l = (b << lk) + (k - 1 - off);
       if (l < n) {
@@ -36,7 +36,7 @@ __device__ __forceinline__ void bitonic_sort_block(KeyPtr keys, int n, int tid) 
     for (int lj = lk - 2; lj >= 0; lj--) {
       const int j = 1 << lj, B = j << 1;
       stage_sync(B > 64 || prevB > 64);
-      for (int c = tid; c < halfN; c += kThreads) {
+      for (int c = tid; c < halfN; c += NT) {
         const int b = c >> lj, off = c & (j - 1);
         const int i = (b << (lj + 1)) + off, l = i + j;
         if (l < n) {
@@ -52,22 +52,25 @@ __device__ __forceinline__ void bitonic_sort_block(KeyPtr keys, int n, int tid) 
 
 // Fully unrolled network for N = 2^LOGN <= 512 keys: one compare-exchange per thread and stage, all
 // shifts/masks compile-time constants (the generic loop spent ~64 instructions per stage, ncu r1b).
-template <int LOGN>
+template <int LOGN, int NT = kThreads>
 __device__ __forceinline__ void bitonic_sort_fixed(unsigned long long* keys, int n, int tid) {
   constexpr int HALF = (1 << LOGN) >> 1;
-  static_assert(HALF <= kThreads, "one compare-exchange per thread");
-  const bool has_ce = tid < HALF;
+  constexpr int PER = (HALF + NT - 1) / NT;          // compare-exchanges per thread and stage (1 at NT = 256, up to 2 at NT = 128)
   int prevB = 1 << 30;
 #pragma unroll
   for (int lk = 1; lk <= LOGN; lk++) {
     const int k = 1 << lk, half = k >> 1;
     stage_sync(k > 64 || prevB > 64);
-    if (has_ce) {
-      const int b = tid >> (lk - 1), off = tid & (half - 1);
-      const int i = (b << lk) + off, l = (b << lk) + (k - 1 - off);
-      if (l < n) {
-        const unsigned long long ki = keys[i], kl = keys[l];
-        if (ki > kl) { keys[i] = kl; keys[l] = ki; }
+#pragma unroll
+    for (int m = 0; m < PER; m++) {
+      const int c = tid + m * NT;
+      if (c < HALF) {
+        const int b = c >> (lk - 1), off = c & (half - 1);
+        const int i = (b << lk) + off, l = (b << lk) + (k - 1 - off);
+        if (l < n) {
+          const unsigned long long ki = keys[i], kl = keys[l];
+          if (ki > kl) { keys[i] = kl; keys[l] = ki; }
+        }
       }
     }
     prevB = k;
@@ -75,12 +78,16 @@ __device__ __forceinline__ void bitonic_sort_fixed(unsigned long long* keys, int
     for (int lj = lk - 2; lj >= 0; lj--) {
       const int j = 1 << lj, B = j << 1;
       stage_sync(B > 64 || prevB > 64);
-      if (has_ce) {
-        const int b = tid >> lj, off = tid & (j - 1);
-        const int i = (b << (lj + 1)) + off, l = i + j;
-        if (l < n) {
-          const unsigned long long ki = keys[i], kl = keys[l];
-          if (ki > kl) { keys[i] = kl; keys[l] = ki; }
+#pragma unroll
+      for (int m = 0; m < PER; m++) {
+        const int c = tid + m * NT;
+        if (c < HALF) {
+          const int b = c >> lj, off = c & (j - 1);
+          const int i = (b << (lj + 1)) + off, l = i + j;
+          if (l < n) {
+            const unsigned long long ki = keys[i], kl = keys[l];
+            if (ki > kl) { keys[i] = kl; keys[l] = ki; }
+          }
         }
       }
       prevB = B;

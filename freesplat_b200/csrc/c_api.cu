@@ -78,7 +78,7 @@ int fs_raster_forward(const FsRasterFwdArgs* a, void* stream) {
   FS_REQUIRE((long long)tiles_x(a->W) * tiles_y(a->H) * a->V < (1ll << 31), "too many tiles");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int rc;
-  const int stages = a->stages ? a->stages : (FS_STAGE_PREPROCESS | FS_STAGE_BINNING | FS_STAGE_RENDER);
+  const int stages = (a->stages & 7) ? a->stages : (a->stages | FS_STAGE_PREPROCESS | FS_STAGE_BINNING | FS_STAGE_RENDER);
   if ((stages & FS_STAGE_PREPROCESS) && (rc = launch_preprocess(*a, s))) return rc;
   if ((stages & FS_STAGE_BINNING) && (rc = launch_binning(*a, s))) return rc;
   if ((stages & FS_STAGE_RENDER) && (rc = launch_render_fwd(*a, s))) return rc;
@@ -183,6 +183,24 @@ int fs_ptf_gru_update(int32_t M, int32_t F, const float* A1, const float* r_lin,
 int fs_ptf_gru_output(int32_t M, int32_t F, const float* A1, const float* z_lin, const float* q_lin, float* out, void* stream) {
   FS_REQUIRE(M >= 0 && F >= 1 && (M == 0 || (A1 && z_lin && q_lin && out)), "bad arguments");
   return launch_ptf_gru_output(M, F, A1, z_lin, q_lin, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_ptf_gru_output_backward(int32_t M, int32_t F, const float* A1, const float* z_lin, const float* q_lin, const float* g_out, float* dz_lin,
+                               float* dq_lin, float* dA1, void* stream) {
+  FS_REQUIRE(M >= 0 && F >= 1 && (M == 0 || (A1 && z_lin && q_lin && g_out && dz_lin && dq_lin && dA1)), "bad arguments");
+  return launch_ptf_gru_output_bwd(M, F, A1, z_lin, q_lin, g_out, dz_lin, dq_lin, dA1, reinterpret_cast<cudaStream_t>(stream));
+}
+int fs_ptf_gru_update_backward(int32_t M, int32_t F, const float* A1, const float* r_lin, const float* dU, float* dr_lin, float* dA1, void* stream) {
+  FS_REQUIRE(M >= 0 && F >= 1 && (M == 0 || (A1 && r_lin && dU && dr_lin && dA1)), "bad arguments");
+  return launch_ptf_gru_update_bwd(M, F, A1, r_lin, dU, dr_lin, dA1, reinterpret_cast<cudaStream_t>(stream));
+}
+int fs_ptf_gru_inputs_backward(int32_t M, int32_t F, const int32_t* pair_j, const int32_t* pair_p, const float* dens, const float* wemb,
+                               const float* v_dens, const float* v_wemb, const float* dA1, float* d_feats, float* d_dens, float* d_wemb,
+                               float* dv_feats, float* dv_dens, float* dv_wemb, void* stream) {
+  FS_REQUIRE(M >= 0 && F >= 1 && (M == 0 || (pair_j && pair_p && dens && wemb && v_dens && v_wemb && dA1 && d_feats && d_dens && d_wemb &&
+                                           dv_feats && dv_dens && dv_wemb)), "bad arguments");
+  return launch_ptf_gru_inputs_bwd(M, F, pair_j, pair_p, dens, wemb, v_dens, v_wemb, dA1, d_feats, d_dens, d_wemb, dv_feats, dv_dens, dv_wemb,
+                                   reinterpret_cast<cudaStream_t>(stream));
 }
 
 int fs_gaussian_head(const FsAdapterArgs* a, void* stream) {

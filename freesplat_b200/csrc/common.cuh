@@ -48,6 +48,13 @@ int launch_ptf_gru_inputs(int M, int F, const int* pj, const int* pp, const floa
 int launch_ptf_gru_update(int M, int F, const float* A1, const float* r_lin, float* U, cudaStream_t s);
 int launch_ptf_gru_output(int M, int F, const float* A1, const float* z_lin, const float* q_lin, float* out, cudaStream_t s);
 
+int launch_ptf_gru_output_bwd(int M, int F, const float* A1, const float* z_lin, const float* q_lin, const float* g_out, float* dz_lin,
+                              float* dq_lin, float* dA1, cudaStream_t s);
+int launch_ptf_gru_update_bwd(int M, int F, const float* A1, const float* r_lin, const float* dU, float* dr_lin, float* dA1, cudaStream_t s);
+int launch_ptf_gru_inputs_bwd(int M, int F, const int* pj, const int* pp, const float* dens, const float* wemb, const float* v_dens,
+                              const float* v_wemb, const float* dA1, float* d_feats, float* d_dens, float* d_wemb, float* dv_feats,
+                              float* dv_dens, float* dv_wemb, cudaStream_t s);
+
 __host__ __device__ inline int tiles_x(int W) { return (W + FS_TILE - 1) / FS_TILE; }
 __host__ __device__ inline int tiles_y(int H) { return (H + FS_TILE - 1) / FS_TILE; }
 

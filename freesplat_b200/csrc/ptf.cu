@@ -465,6 +465,97 @@ __global__ void __launch_bounds__(256) ptf_gru_output_kernel(int M, int F, const
   out[i] = (1.0f - z) * h + z * tanhf(q_lin[i]);
 }
 
+// ---- backward of the three glue kernels (training: the Linear layers in between stay GEMMs of the caller) ----
+// (1) out = (1-z) h + z q:   dz_lin = g (q - h) z (1 - z) ;  dq_lin = g z (1 - q^2) ;  dA1[:, :F] = g (1 - z)   (direct path to h)
+__global__ void __launch_bounds__(256) ptf_gru_output_bwd_kernel(int M, int F, const float* __restrict__ A1, const float* __restrict__ z_lin,
+                                                                 const float* __restrict__ q_lin, const float* __restrict__ g_out,
+                                                                 float* __restrict__ dz_lin, float* __restrict__ dq_lin, float* __restrict__ dA1) {
+  const size_t total = (size_t)M * F;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const size_t m = i / F; const int c = (int)(i - m * F);
+  const int ld1 = 2 * F + 48;
+  const float z = 1.0f / (1.0f + expf(-z_lin[i])), q = tanhf(q_lin[i]), h = A1[m * ld1 + c], g = g_out[i];
+  dz_lin[i] = g * (q - h) * z * (1.0f - z);
+  dq_lin[i] = g * z * (1.0f - q * q);
+  dA1[m * ld1 + c] = g * (1.0f - z);
+}
+
+// (2) U = [sigmoid(r_lin) h | x | e_in]:  dr_lin = dU[:, :F] h r (1 - r) ;  dA1[:, :F] += dU[:, :F] r ;  dA1[:, F:F+24] = 0 (e_h enters
+//     only through the first layers) ;  dA1[:, F+24:] = dU[:, F:]
+__global__ void __launch_bounds__(256) ptf_gru_update_bwd_kernel(int M, int F, const float* __restrict__ A1, const float* __restrict__ r_lin,
+                                                                 const float* __restrict__ dU, float* __restrict__ dr_lin, float* __restrict__ dA1) {
+  const int ld1 = 2 * F + 48, ldu = 2 * F + 24;
+  const size_t total = (size_t)M * ld1;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const size_t m = i / ld1; const int c = (int)(i - m * ld1);
+  if (c < F) {
+    const float r = 1.0f / (1.0f + expf(-r_lin[m * F + c])), h = A1[i], du = dU[m * ldu + c];
+    dr_lin[m * F + c] = du * h * r * (1.0f - r);
+    dA1[i] += du * r;
+  } else if (c < F + 24) {
+    dA1[i] = 0.f;
+  } else {
+    dA1[i] = dU[m * ldu + (c - 24)];
+  }
+}
+
+// (3) gathers / positional encodings:  d feats[j] = dA1[:, :F] (every global is matched at most once: plain rows) ; view-side
+//     rows and scalars accumulate with atomics (z-buffer ties: several globals per pixel) ;
+//     PE(x) = (sin 2^f x, cos 2^f x)_f  ->  dx = sum_f 2^f (cos(2^f x) d_sin_f - sin(2^f x) d_cos_f)
+__global__ void __launch_bounds__(256) ptf_gru_inputs_bwd_kernel(int M, int F, const int* __restrict__ pair_j, const int* __restrict__ pair_p,
+                                                                 const float* __restrict__ dens, const float* __restrict__ wemb,
+                                                                 const float* __restrict__ v_dens, const float* __restrict__ v_wemb,
+                                                                 const float* __restrict__ dA1, float* __restrict__ d_feats,
+                                                                 float* __restrict__ d_dens, float* __restrict__ d_wemb,
+                                                                 float* __restrict__ dv_feats, float* __restrict__ dv_dens,
+                                                                 float* __restrict__ dv_wemb) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);      // one warp per pair
+  if (m >= M) return;
+  const int j = pair_j[m], p = pair_p[m];
+  const int ld = 2 * F + 48;
+  const float* row = dA1 + (size_t)m * ld;
+  for (int e = lane; e < F; e += 32) {
+    d_feats[(size_t)j * F + e] = row[e];
+    atomicAdd(dv_feats + (size_t)p * F + e, row[F + 24 + e]);
+  }
+  if (lane < 4) {
+    const float x = lane == 0 ? v_dens[p] : lane == 1 ? wemb[j] : lane == 2 ? dens[j] : v_wemb[p];
+    const float* g = row + (lane < 2 ? F + 12 * lane : 2 * F + 24 + 12 * (lane - 2));
+    float acc = 0.f, s = x, sc = 1.0f;
+#pragma unroll
+    for (int f = 0; f < 6; f++) { acc += sc * (cosf(s) * g[2 * f] - sinf(s) * g[2 * f + 1]); s = s * 2.0f; sc = sc * 2.0f; }
+    if (lane == 0) atomicAdd(dv_dens + p, acc);
+    else if (lane == 1) d_wemb[j] = acc;
+    else if (lane == 2) d_dens[j] = acc;
+    else atomicAdd(dv_wemb + p, acc);
+  }
+}
+
+int launch_ptf_gru_output_bwd(int M, int F, const float* A1, const float* z_lin, const float* q_lin, const float* g_out, float* dz_lin,
+                              float* dq_lin, float* dA1, cudaStream_t s) {
+  if (M <= 0) return FS_OK;
+  const size_t total = (size_t)M * F;
+  ptf_gru_output_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(M, F, A1, z_lin, q_lin, g_out, dz_lin, dq_lin, dA1);
+  return check_cuda(cudaGetLastError(), "ptf_gru_output_bwd_kernel");
+}
+int launch_ptf_gru_update_bwd(int M, int F, const float* A1, const float* r_lin, const float* dU, float* dr_lin, float* dA1, cudaStream_t s) {
+  if (M <= 0) return FS_OK;
+  const size_t total = (size_t)M * (2 * F + 48);
+  ptf_gru_update_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(M, F, A1, r_lin, dU, dr_lin, dA1);
+  return check_cuda(cudaGetLastError(), "ptf_gru_update_bwd_kernel");
+}
+int launch_ptf_gru_inputs_bwd(int M, int F, const int* pj, const int* pp, const float* dens, const float* wemb, const float* v_dens,
+                              const float* v_wemb, const float* dA1, float* d_feats, float* d_dens, float* d_wemb, float* dv_feats,
+                              float* dv_dens, float* dv_wemb, cudaStream_t s) {
+  if (M <= 0) return FS_OK;
+  ptf_gru_inputs_bwd_kernel<<<(M + 7) / 8, 256, 0, s>>>(M, F, pj, pp, dens, wemb, v_dens, v_wemb, dA1, d_feats, d_dens, d_wemb, dv_feats,
+                                                         dv_dens, dv_wemb);
+  return check_cuda(cudaGetLastError(), "ptf_gru_inputs_bwd_kernel");
+}
+
 int launch_ptf_gru_inputs(int M, int F, const int* pj, const int* pp, const float* feats, const float* dens, const float* wemb,
                           const float* v_feats, const float* v_dens, const float* v_wemb, float* A1, cudaStream_t s) {
   if (M <= 0) return FS_OK;

@@ -14,8 +14,6 @@
 // Per pixel and instance the arithmetic is the canonical order of oracle/raster_oracle.c:
 //   t = fma(cb, dy, ca*dx) ; power = fma(cc*dy, dy, t*dx) ; alpha = min(.99, o*exp(power)).
 // exp() is MUFU.EX2 (ex2.approx.ftz) of power*log2(e): |rel err| < 1e-6.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "raster_sort.cuh"
 
@@ -521,16 +519,9 @@ __global__ void __launch_bounds__(kThreads) render_bwd_kernel(
   }
 }
 
-// FS_RENDER_VARIANT=1 selects the one-pixel-per-lane kernel (A/B measurements); default: two pixels per lane, packed fp32
-static int render_variant() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FS_RENDER_VARIANT"); v = (e && e[0] == '1') ? 1 : 2; }
-  return v;
-}
-
 int launch_render_fwd(const FsRasterFwdArgs& a, cudaStream_t s) {
   const int gx = tiles_x(a.W), gy = tiles_y(a.H);
-  if (render_variant() == 2) {
+  if (a.stages & FS_STAGE_RENDER_PACKED) {      // two pixels per lane on the packed fp32 pipe (measured 136 vs 129 us: not the default)
     render_fwd2_kernel<<<gx * gy * a.V, kThreads2, kSortSmemKeys2 * 8, s>>>(
         reinterpret_cast<const uint2*>(a.ranges), a.tile_count /* holds the tile order after binning */,
         reinterpret_cast<unsigned long long*>(a.keybuf), a.point_list, reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P,

@@ -150,6 +150,86 @@ def _gru_fused(gru, M, F, pair_j, pair_p, state, view_feats, view_dens, view_wem
     return out
 
 
+class _GruTrain(torch.autograd.Function):
+    """GRU.forward (networks.py:201-214) of the matched pairs for the TRAINING fold.
+
+    forward : the fused tensor-core kernel (fs_ptf_gru, 3xTF32) -- nothing but the inputs is kept for backward;
+    backward: recompute + chain rule by hand: the element-wise work (gathers, positional encodings and their derivatives,
+              gates, scatter of the input gradients incl. atomics for tied pixels) runs in six glue kernels of
+              libfreesplat_b200.so (three forward ones re-used, fs_ptf_gru_{output,update,inputs}_backward), the 18 matrix
+              products in between (6 recomputed layers, 6 data gradients, 6 weight gradients) are plain fp32 GEMMs.
+    Replaces ~60 eager element-wise torch launches per fold step (13.9 -> see profiles/ ms for the 3-view fold)."""
+
+    @staticmethod
+    def forward(ctx, feats, dens, wemb, v_feats, v_dens, v_wemb, pair_j, pair_p, M, gru_tc, *params):
+        dev = feats.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        state = (feats.contiguous(), None, dens.contiguous(), wemb.contiguous())
+        with torch.cuda.device(dev):
+            out = gru_tc(M, pair_j, pair_p, state, v_feats.contiguous(), v_dens.contiguous(), v_wemb.contiguous(), stream)
+        ctx.M = M
+        ctx.sizes = (feats.shape[0], v_feats.shape[0])
+        ctx.save_for_backward(state[0], state[2], state[3], v_feats, v_dens, v_wemb, pair_j[:M].clone(), pair_p[:M].clone(), *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        feats, dens, wemb, v_feats, v_dens, v_wemb, pj, pp = ctx.saved_tensors[:8]
+        (Wr0, br0, Wr2, br2, Wz0, bz0, Wz2, bz2, Wn0, bn0, Wn2, bn2) = ctx.saved_tensors[8:]
+        M, F = ctx.M, feats.shape[1]
+        N, HW = ctx.sizes
+        dev = feats.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        g = g.contiguous()
+        with torch.cuda.device(dev), torch.no_grad():
+            # ---- recompute the forward activations ----
+            A1 = e(M, 2 * F + 48)
+            check(L.fs_ptf_gru_inputs(C.c_int32(M), C.c_int32(F), vp(pj), vp(pp), vp(feats), vp(dens), vp(wemb), vp(v_feats), vp(v_dens),
+                                      vp(v_wemb), vp(A1), st), "fs_ptf_gru_inputs")
+            Hr = torch.addmm(br0, A1, Wr0.t()).relu_(); Hz = torch.addmm(bz0, A1, Wz0.t()).relu_()
+            r_lin = torch.addmm(br2, Hr, Wr2.t()); z_lin = torch.addmm(bz2, Hz, Wz2.t())
+            U = e(M, 2 * F + 24)
+            check(L.fs_ptf_gru_update(C.c_int32(M), C.c_int32(F), vp(A1), vp(r_lin), vp(U), st), "fs_ptf_gru_update")
+            Hn = torch.addmm(bn0, U, Wn0.t()).relu_()
+            q_lin = torch.addmm(bn2, Hn, Wn2.t())
+            # ---- backward ----
+            dz_lin, dq_lin, dA1 = e(M, F), e(M, F), e(M, 2 * F + 48)
+            check(L.fs_ptf_gru_output_backward(C.c_int32(M), C.c_int32(F), vp(A1), vp(z_lin), vp(q_lin), vp(g), vp(dz_lin), vp(dq_lin),
+                                               vp(dA1), st), "fs_ptf_gru_output_backward")
+            gWn2 = dq_lin.t() @ Hn; gbn2 = dq_lin.sum(0)
+            dHn = (dq_lin @ Wn2).mul_(Hn > 0)
+            gWn0 = dHn.t() @ U; gbn0 = dHn.sum(0)
+            dU = dHn @ Wn0
+            dr_lin = e(M, F)
+            check(L.fs_ptf_gru_update_backward(C.c_int32(M), C.c_int32(F), vp(A1), vp(r_lin), vp(dU), vp(dr_lin), vp(dA1), st),
+                  "fs_ptf_gru_update_backward")
+            gWz2 = dz_lin.t() @ Hz; gbz2 = dz_lin.sum(0)
+            dHz = (dz_lin @ Wz2).mul_(Hz > 0)
+            gWz0 = dHz.t() @ A1; gbz0 = dHz.sum(0)
+            dA1.addmm_(dHz, Wz0)
+            gWr2 = dr_lin.t() @ Hr; gbr2 = dr_lin.sum(0)
+            dHr = (dr_lin @ Wr2).mul_(Hr > 0)
+            gWr0 = dHr.t() @ A1; gbr0 = dHr.sum(0)
+            dA1.addmm_(dHr, Wr0)
+            d_feats, d_dens, d_wemb = z(N, F), z(N), z(N)
+            dv_feats, dv_dens, dv_wemb = z(HW, F), z(HW), z(HW)
+            check(L.fs_ptf_gru_inputs_backward(C.c_int32(M), C.c_int32(F), vp(pj), vp(pp), vp(dens), vp(wemb), vp(v_dens), vp(v_wemb), vp(dA1),
+                                               vp(d_feats), vp(d_dens), vp(d_wemb), vp(dv_feats), vp(dv_dens), vp(dv_wemb), st),
+                  "fs_ptf_gru_inputs_backward")
+        return (d_feats, d_dens, d_wemb, dv_feats, dv_dens, dv_wemb, None, None, None, None,
+                gWr0, gbr0, gWr2, gbr2, gWz0, gbz0, gWz2, gbz2, gWn0, gbn0, gWn2, gbn2)
+
+
+def _gru_train(gru, gru_tc, M, pair_j, pair_p, state, v_feats, v_dens, v_wemb):
+    p = (gru.mlp_r[0].weight, gru.mlp_r[0].bias, gru.mlp_r[2].weight, gru.mlp_r[2].bias, gru.mlp_z[0].weight, gru.mlp_z[0].bias,
+         gru.mlp_z[2].weight, gru.mlp_z[2].bias, gru.mlp_n[0].weight, gru.mlp_n[0].bias, gru.mlp_n[2].weight, gru.mlp_n[2].bias)
+    return _GruTrain.apply(state[0], state[2], state[3], v_feats, v_dens, v_wemb, pair_j, pair_p, M, gru_tc, *p)
+
+
 def _ptf_args(h, w, F, n_upper, depth_thres, state, cin, view, scratch, counts_out, out=None, gru_out=None, maps=(None, None)):
     feats, coords, dens, wemb, ext, depth = state
     v_feats, v_coords, v_dens, v_wemb, v_depth, v_ext, E_inv, K_px = view
@@ -289,7 +369,8 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
     N = HW
     debug = []
     use_tc = fused_gru and GRU_MODE == "tc" and _gru_tc_ok(gru, F)
-    gru_tc = _GruTc(gru, dev) if use_tc else None
+    train_tc = need_grad and GRU_MODE == "tc" and _gru_has_reference_structure(gru) and _gru_tc_ok(gru, F)
+    gru_tc = _GruTc(gru, dev) if (use_tc or train_tc) else None
     # inference with the tensor-core GRU: the whole fold is enqueued without reading a counter back (grids are sized by
     # upper bounds, the kernels take N / M from the device counters); ONE host read at the end returns the final size
     sync_free = use_tc and (not need_grad) and timings is None and not return_debug and SYNC_FREE
@@ -332,7 +413,10 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
                 ev[1].record()
             M, N_out = c[2], c[4]
             gru_out = None
-            if M > 0 and use_tc:
+            if M > 0 and train_tc:
+                # training: tensor-core forward, hand-derived backward (glue kernels + GEMMs), see _GruTrain
+                gru_out = _gru_train(gru, gru_tc, M, pair_j, pair_p, state, feats[i], dens[i], wemb[i])
+            elif M > 0 and use_tc:
                 gru_out = gru_tc(M, pair_j, pair_p, det, feats[i], dens[i], wemb[i], stream)
             elif M > 0 and fused_gru:
                 gru_out = _gru_fused(gru, M, F, pair_j, pair_p, det, feats[i], dens[i], wemb[i], stream)

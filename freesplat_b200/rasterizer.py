@@ -24,6 +24,8 @@ from ._lib import FsRasterBwdArgs, FsRasterFwdArgs, check, ptr
 
 VIEW_FLOATS = 48
 REC_FLOATS = 12
+# FS_STAGE_RENDER_PACKED: blend with the two-pixels-per-lane packed-fp32 kernel (bit-identical results; A/B switch)
+RENDER_PACKED = os.environ.get("FREESPLAT_B200_RENDER_PACKED", "0") == "1"
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -195,7 +197,7 @@ def _fwd_args(st: RasterState, means3D, opacities, views, shs, colors_precomp, s
     tile_count, tile_cursor = st.tile_buf[:nt], st.tile_buf[nt:]
     return FsRasterFwdArgs(
         P=st.P, V=st.V, H=st.H, W=st.W, sh_degree=st.sh_degree, M=st.M, scale_modifier=st.scale_modifier,
-        prefiltered=int(prefiltered), stages=0, sh_layout=st.sh_layout, cov_stride=st.cov_stride, capacity=st.capacity,
+        prefiltered=int(prefiltered), stages=8 if RENDER_PACKED else 0, sh_layout=st.sh_layout, cov_stride=st.cov_stride, capacity=st.capacity,
         means3D=ptr(means3D), shs=ptr(shs), colors_precomp=ptr(colors_precomp), opacities=ptr(opacities),
         scales=ptr(scales), rotations=ptr(rotations), cov3D_precomp=ptr(cov3D_precomp), views=ptr(views),
         out_color=ptr(st.color), out_depth=ptr(st.depth), final_T=ptr(st.final_T), n_contrib=ptr(st.n_contrib),
@@ -269,7 +271,7 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
                 # stage_events: list of 4 torch.cuda.Event recorded around preprocess | binning | render
                 for k, bit in enumerate((1, 2, 4)):
                     stage_events[k].record()
-                    a.stages = bit
+                    a.stages = bit | (8 if RENDER_PACKED else 0)
                     check(L.fs_raster_forward(C.byref(a), C.c_void_p(stream)), "fs_raster_forward")
                 stage_events[3].record()
             if check_overflow != "sync":

@@ -110,6 +110,8 @@ typedef struct FsRasterFwdArgs {
 #define FS_STAGE_PREPROCESS 1  /* per-Gaussian projection + tile counting            */
 #define FS_STAGE_BINNING 2     /* tile scan (+ tile order), scatter                  */
 #define FS_STAGE_RENDER 4      /* per-tile depth sort + alpha blend (one kernel)     */
+#define FS_STAGE_RENDER_PACKED 8 /* modifier: render with render_fwd2_kernel (two pixels per lane, FFMA2 / FMUL2 packed fp32,
+                                    half-warp-independent instance lists); bit-identical results, see DESIGN.md 4           */
 
 typedef struct FsRasterBwdArgs {
   int32_t P, V, H, W, sh_degree, M;
@@ -270,6 +272,18 @@ int fs_ptf_gru_inputs(int32_t M, int32_t F, const int32_t* pair_j, const int32_t
                       const float* wemb, const float* v_feats, const float* v_dens, const float* v_wemb, float* A1, void* stream);
 int fs_ptf_gru_update(int32_t M, int32_t F, const float* A1, const float* r_lin, float* U, void* stream);
 int fs_ptf_gru_output(int32_t M, int32_t F, const float* A1, const float* z_lin, const float* q_lin, float* out, void* stream);
+
+/* Backward of the three glue steps (training path: forward = fs_ptf_gru on the tensor cores, backward = recompute with
+ * these kernels around the caller's GEMMs).  dA1 [M,2F+48] is built up across the calls: output_backward writes its [:, :F]
+ * (direct path to the hidden latent), update_backward adds to [:, :F] and writes the rest, the caller adds the first layers'
+ * products, inputs_backward scatters it: d_feats / d_dens / d_wemb rows of the matched globals are plain stores (the caller
+ * zero-fills the buffers), dv_* of view i accumulate with atomics.                                                      */
+int fs_ptf_gru_output_backward(int32_t M, int32_t F, const float* A1, const float* z_lin, const float* q_lin, const float* g_out, float* dz_lin,
+                               float* dq_lin, float* dA1, void* stream);
+int fs_ptf_gru_update_backward(int32_t M, int32_t F, const float* A1, const float* r_lin, const float* dU, float* dr_lin, float* dA1, void* stream);
+int fs_ptf_gru_inputs_backward(int32_t M, int32_t F, const int32_t* pair_j, const int32_t* pair_p, const float* dens, const float* wemb,
+                               const float* v_dens, const float* v_wemb, const float* dA1, float* d_feats, float* d_dens, float* d_wemb,
+                               float* dv_feats, float* dv_dens, float* dv_wemb, void* stream);
 
 /* The whole GRU (networks.py:188-214, latent width 64, 24-wide weight embeddings) for the M matched pairs on the
  * tensor cores (tcgen05, 3xTF32): gathers, positional encodings, the six Linear layers and the gates in one kernel.

@@ -52,6 +52,24 @@ def test_crowded_tile_global_sort_path():
     _check(sc)
 
 
+def test_packed_two_pixel_render_kernel_is_bit_identical(monkeypatch):
+    """FS_STAGE_RENDER_PACKED (render_fwd2_kernel: two pixels per lane, FFMA2 / FMUL2, half-warp-independent instance lists)
+    must reproduce the default kernel bit for bit: images, final_T, n_contrib, sorted keys; incl. a crowded tile (> 2048 keys:
+    its global-memory sort path) and a ragged image."""
+    from freesplat_b200 import rasterizer
+    for sc in (synth.pixel_aligned_scene(seed=1, h=120, w=160, n_context=2, n_target=3, keep=None),
+               synth.random_scene(seed=4, h=64, w=64, P=30000, sigma_px=(0.5, 2.0)), synth.random_scene(seed=3, h=100, w=77, P=3000)):
+        monkeypatch.setattr(rasterizer, "RENDER_PACKED", False)
+        a, _ = rc.run_cuda(sc, bg=(0.1, 0.2, 0.3))
+        monkeypatch.setattr(rasterizer, "RENDER_PACKED", True)
+        b, _ = rc.run_cuda(sc, bg=(0.1, 0.2, 0.3))
+        R = a.num_rendered()
+        assert R == b.num_rendered() and R > 0
+        for k in ("color", "depth", "final_T", "n_contrib", "ranges"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), k
+        assert torch.equal(a.point_list[:R], b.point_list[:R]) and torch.equal(a.keybuf[:R], b.keybuf[:R])
+
+
 def test_capacity_overflow_retry():
     sc = synth.random_scene(seed=5, h=128, w=128, P=5000)
     st, _ = rc.run_cuda(sc, capacity=100)       # far too small: must re-run with the reported R

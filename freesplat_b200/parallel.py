@@ -144,8 +144,9 @@ class ViewExchange:
     (encoder_freesplat.py:443-519), so `ptf.fuse_views(..., view_ready=ready_events)` folds view v while views v+1.. are
     still in flight over NVLink: the exchange costs its first two views, not all ten."""
 
-    def __init__(self, num_views: int, HW: int, F: int, device, group=None):
+    def __init__(self, num_views: int, HW: int, F: int, device, group=None, two_phase: bool = True):
         self.V, self.HW, self.F, self.dev, self.group = num_views, HW, F, device, group
+        self.two_phase = two_phase
         self.block = torch.empty((num_views, HW * (F + 6)), dtype=torch.float32, device=device)
         self.ready_events = [torch.cuda.Event() for _ in range(num_views)]
         self.stream = torch.cuda.Stream(device) if (isinstance(device, torch.device) and device.type == "cuda") or \
@@ -182,10 +183,29 @@ class ViewExchange:
         if cuda:
             self.stream.wait_stream(torch.cuda.current_stream(self.dev))
         ctx = torch.cuda.stream(self.stream) if cuda else _null()
+        S = self.block.shape[1]
+        two_phase = self.two_phase and cuda and S % world == 0
         with ctx:
             for v in range(self.V):
-                src = dist.get_global_rank(self.group, owner_of(v, world)) if self.group is not None else owner_of(v, world)
-                w = dist.broadcast(self.block[v], src=src, group=self.group, async_op=True)
+                owner = owner_of(v, world)
+                src = dist.get_global_rank(self.group, owner) if self.group is not None else owner
+                if two_phase:
+                    # scatter + all-gather instead of a broadcast: the owner sends each rank 1/world of the block, then every
+                    # rank forwards its slice to all others at once -- all NVLink ports of all GPUs carry the view (a ring
+                    # broadcast of 86 MB kept one port per GPU busy and took ~0.6 ms at 8 ranks; this takes the time of
+                    # S/world out of the owner plus one all-gather round)
+                    sl = self.block[v].view(world, S // world)
+                    mine_sl = sl[rank]
+                    if rank != owner:
+                        dist.recv(mine_sl, src=src, group=self.group)
+                    else:
+                        reqs = [dist.isend(sl[r], dst=(dist.get_global_rank(self.group, r) if self.group is not None else r),
+                                           group=self.group) for r in range(world) if r != owner]
+                        for q in reqs:
+                            q.wait()
+                    w = dist.all_gather_into_tensor(self.block[v], mine_sl, group=self.group, async_op=True)
+                else:
+                    w = dist.broadcast(self.block[v], src=src, group=self.group, async_op=True)
                 w.wait()                                  # the side stream (not the host) waits for NCCL
                 if cuda:
                     self.ready_events[v].record(self.stream)

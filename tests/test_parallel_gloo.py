@@ -14,6 +14,34 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+def _spawn(target, world, extra=(), attempts=3):
+    """Runs `target(rank, world, port, *extra, q)` in `world` processes; a failed rendezvous (port taken between probing and
+    binding on a busy host) is retried on a fresh port."""
+    last = None
+    for _ in range(attempts):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        ps = [ctx.Process(target=target, args=(r, world, port, *extra, q)) for r in range(world)]
+        for p in ps:
+            p.start()
+        try:
+            res = [q.get(timeout=180) for _ in ps]
+        except Exception as exc:             # queue.Empty: a worker died or hung
+            last = exc
+            for p in ps:
+                p.kill()
+            continue
+        ok = True
+        for p in ps:
+            p.join(timeout=60)
+            ok = ok and p.exitcode == 0
+        if ok:
+            return res
+        last = RuntimeError("worker exit codes: %s" % [p.exitcode for p in ps])
+    raise last
+
+
 def _worker(rank, world, port, num_views, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -46,17 +74,7 @@ def _worker(rank, world, port, num_views, q):
 
 
 def _run(num_views, world=2):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    ps = [ctx.Process(target=_worker, args=(r, world, port, num_views, q)) for r in range(world)]
-    for p in ps:
-        p.start()
-    res = [q.get(timeout=120) for _ in ps]
-    for p in ps:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    return sorted(res)
+    return sorted(_spawn(_worker, world, (num_views,)))
 
 
 def test_shard_partition_is_exact():
@@ -115,16 +133,7 @@ def _grad_worker(rank, world, port, q):
 
 
 def test_sharded_render_sums_gaussian_gradients_over_ranks():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    ps = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in ps:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in ps], key=lambda r: r[0])
-    for p in ps:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = sorted(_spawn(_grad_worker, 2), key=lambda r: r[0])
     assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3]
     # single-process reference: all views on one rank
     g = torch.Generator().manual_seed(0)
@@ -163,16 +172,7 @@ def _cv_worker(rank, world, port, q):
 
 
 def test_sharded_cost_volume_matches_single_rank_forward_and_backward():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    ps = [ctx.Process(target=_cv_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in ps:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in ps], key=lambda r: r[0])
-    for p in ps:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = sorted(_spawn(_cv_worker, 2), key=lambda r: r[0])
     V, C, Hf, Wf = 5, 4, 3, 6
     g = torch.Generator().manual_seed(1)
     feats = torch.randn((V, C, Hf, Wf), generator=g).requires_grad_(True)

@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
   const int nblk = min(kThreads, a.P - block_base);
   const int M3 = a.M * 3;
   const bool use_sh = a.shs && a.dL_dshs;
+  // fused reduce-scatter, vector path: full block, one owner rank, in-place layouts, staging large enough (13 floats per row)
+  const bool vec_peer = a.peer_delta != nullptr && use_sh && nblk == kThreads && (a.shard_rows % kThreads) == 0 && a.cov_stride == 9 &&
+                        a.dL_dcov3D != nullptr && sh_stride >= 13 && ((nblk * M3) & 3) == 0;
   if (use_sh) {
     const float* src = a.shs + (size_t)block_base * M3;
     const int total = nblk * M3;
@@ -361,7 +364,16 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
     }
     g_mean[0] += dm[0] * ss; g_mean[1] += dm[1] * ss; g_mean[2] += dm[2] * ss;
   }
-  if (a.peer_delta != nullptr) {
+  if (a.peer_delta != nullptr && vec_peer) {
+    // fused reduce-scatter, vector path: the block's rows are parked in shared memory (the SH input staging is dead by now)
+    // and leave below as coalesced 16-byte reductions
+    __syncthreads();          // every thread is past its last read of the SH staging (vec_peer: the block is full, so all 256 get here)
+    float* st = s_sh;
+    st[3 * tid] = g_mean[0]; st[3 * tid + 1] = g_mean[1]; st[3 * tid + 2] = g_mean[2];
+    float* sc = st + 3 * kThreads + 9 * tid;
+    sc[0] = g_cov[0]; sc[1] = g_cov[1]; sc[2] = g_cov[2]; sc[3] = 0.f; sc[4] = g_cov[3]; sc[5] = g_cov[4]; sc[6] = 0.f; sc[7] = 0.f; sc[8] = g_cov[5];
+    st[12 * kThreads + tid] = g_op;
+  } else if (a.peer_delta != nullptr) {
     // fused reduce-scatter: this rank's partial sums go straight into the owner rank's buffers over NVLink (fire-and-forget
     // reductions on peer-mapped memory; the buffers were zeroed on every rank and a cross-rank barrier follows the kernel)
     const long long delta = a.peer_delta[min(i / a.shard_rows, a.world - 1)];
@@ -428,6 +440,28 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(FsRasterBwdArg
     const int qstep = kThreads / M3, rstep = kThreads - qstep * M3;
     int g = tid / M3, c = tid - g * M3;
     const bool fused = a.peer_delta != nullptr;
+    if (vec_peer) {
+      // one owner for the whole block (shard_rows is a multiple of the block size): 16-byte reductions, 32 lanes -> 512
+      // contiguous bytes per instruction, for all four gradient tensors of the block's 256 Gaussians
+      const long long delta = a.peer_delta[min(block_base / a.shard_rows, a.world - 1)];
+      auto red4 = [&](float* p, float v0, float v1, float v2, float v3) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<char*>(p) + delta), "f"(v0), "f"(v1), "f"(v2), "f"(v3)
+                     : "memory");
+      };
+      for (int k4 = tid; k4 < total / 4; k4 += kThreads) {             // SH rows: 256 x M3 floats, gathered from the padded staging
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const int k = 4 * k4 + e, gg = k / M3; v[e] = s_gsh[gg * sh_stride + (k - gg * M3)]; }
+        red4(dst + 4 * k4, v[0], v[1], v[2], v[3]);
+      }
+      const float4* st4 = reinterpret_cast<const float4*>(s_sh);
+      float* dm = a.dL_dmeans3D + 3 * (size_t)block_base;
+      for (int k4 = tid; k4 < 3 * kThreads / 4; k4 += kThreads) { const float4 q = st4[k4]; red4(dm + 4 * k4, q.x, q.y, q.z, q.w); }
+      float* dc = a.dL_dcov3D + 9 * (size_t)block_base;
+      for (int k4 = tid; k4 < 9 * kThreads / 4; k4 += kThreads) { const float4 q = st4[3 * kThreads / 4 + k4]; red4(dc + 4 * k4, q.x, q.y, q.z, q.w); }
+      float* dop = a.dL_dopacities + block_base;
+      for (int k4 = tid; k4 < kThreads / 4; k4 += kThreads) { const float4 q = st4[12 * kThreads / 4 + k4]; red4(dop + 4 * k4, q.x, q.y, q.z, q.w); }
+    } else
     for (int k = tid; k < total; k += kThreads) {
       const float v = s_gsh[g * sh_stride + c];
       if (fused) {

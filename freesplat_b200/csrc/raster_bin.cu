@@ -20,91 +20,17 @@
 // HBM traffic per instance: 8 B scatter + 8 B read + 8 B + 4 B write, against ~6*24 B upstream.
 #include "common.cuh"
 #include "raster_math.cuh"
+#include "raster_scan.cuh"
 
 namespace fs {
 
 // ---- 2. scan over tile counters -------------------------------------------------------------
-// `count` is consumed by the scan and then OVERWRITTEN with the tile processing order (heaviest bucket first).
-__device__ __forceinline__ int order_bucket(uint32_t c) { return 31 - (int)min(31u, c >> 6); }
-
+// The scan itself lives in raster_scan.cuh (tile_scan_block<NT>): it is run by the LAST CTA of preprocess_kernel to finish
+// its tile counting (raster_pre.cu: one launch and ~9 us less per step), and by this stand-alone kernel when a call has no
+// Gaussians or runs the binning stage on its own.
 __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ count, uint32_t* __restrict__ ranges,
                                                          uint32_t* __restrict__ status, int n, long long capacity) {
-  __shared__ unsigned long long warp_sums[32];
-  __shared__ unsigned long long carry_s;
-  __shared__ uint32_t hist[32], bbase[32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry_s = 0ull;
-  if (tid < 32) hist[tid] = 0u;
-  __syncthreads();
-  const unsigned long long cap = (unsigned long long)capacity;
-  // four consecutive counters per thread: 640x480 x 3 views (3600 tiles) is ONE pass of the block
-  for (int base = 0; base < n; base += 4096) {
-    const int k0 = base + 4 * tid;
-    uint32_t c[4];
-#pragma unroll
-    for (int e = 0; e < 4; e++) c[e] = (k0 + e < n) ? count[k0 + e] : 0u;
-    const unsigned long long s4 = (unsigned long long)c[0] + c[1] + c[2] + c[3];
-    unsigned long long incl = s4;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      unsigned long long w = warp_sums[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += t;
-      }
-      warp_sums[lane] = w;  // inclusive over warps
-    }
-    __syncthreads();
-    const unsigned long long carry = carry_s;
-    const unsigned long long warp_excl = warp ? warp_sums[warp - 1] : 0ull;
-    unsigned long long st = carry + warp_excl + incl - s4;
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const unsigned long long end = st + c[e];
-      if (k0 + e < n) {
-        // clamp so that a too-small workspace can never be overrun (the call reports overflow)
-        ranges[2 * (k0 + e)] = (uint32_t)(st < cap ? st : cap);
-        ranges[2 * (k0 + e) + 1] = (uint32_t)(end < cap ? end : cap);
-        atomicAdd(&hist[order_bucket((uint32_t)((end < cap ? end : cap) - (st < cap ? st : cap)))], 1u);
-      }
-      st = end;
-    }
-    __syncthreads();
-    if (tid == 1023) carry_s = st;
-    __syncthreads();
-  }
-  if (tid == 0) {
-    const unsigned long long R = carry_s;
-    status[0] = (uint32_t)(R & 0xffffffffull);
-    status[1] = (uint32_t)(R >> 32);
-    status[2] = (R > cap || R > 0xffffffffull) ? 1u : 0u;
-    status[3] = 0u;
-  }
-  // ---- tile order: counting sort of the tiles by population bucket, heaviest first (order inside a bucket is
-  //      arbitrary: it only decides which CTA starts earlier).  `count` is dead by now and receives the order. ----
-  if (warp == 0) {
-    const uint32_t h = hist[lane];
-    uint32_t incl = h;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    bbase[lane] = incl - h;
-    hist[lane] = 0u;
-  }
-  __syncthreads();
-  for (int k = tid; k < n; k += 1024) {
-    const int b = order_bucket(ranges[2 * k + 1] - ranges[2 * k]);
-    count[bbase[b] + atomicAdd(&hist[b], 1u)] = (uint32_t)k;
-  }
+  tile_scan_block<1024>(count, ranges, status, n, capacity);
 }
 
 // ---- 3. scatter instances into their tile ranges --------------------------------------------
@@ -152,8 +78,11 @@ int launch_binning(const FsRasterFwdArgs& a, cudaStream_t s) {
   const int gx = tiles_x(a.W), gy = tiles_y(a.H);
   const int nt = a.V * gx * gy;
   int rc;
-  tile_scan_kernel<<<1, 1024, 0, s>>>(a.tile_count, a.ranges, a.status, nt, (long long)a.capacity);
-  if ((rc = check_cuda(cudaGetLastError(), "tile_scan_kernel"))) return rc;
+  // the scan normally ran inside preprocess (last CTA); stand-alone only if that stage was not part of this call sequence
+  if (!scan_fused_into_preprocess(a)) {
+    tile_scan_kernel<<<1, 1024, 0, s>>>(a.tile_count, a.ranges, a.status, nt, (long long)a.capacity);
+    if ((rc = check_cuda(cudaGetLastError(), "tile_scan_kernel"))) return rc;
+  }
   if (a.P > 0) {
     dim3 grid((a.P + kThreads - 1) / kThreads, a.V);
     scatter_kernel<<<grid, kThreads, 0, s>>>(a, gx, gy);

@@ -12,6 +12,7 @@
 //   write 48 (record) + 24 (cov used) + 4 (radius) + 4 (tiles) + 1 (clamp) = 81 B
 #include "common.cuh"
 #include "raster_math.cuh"
+#include "raster_scan.cuh"
 
 namespace fs {
 
@@ -23,7 +24,7 @@ namespace fs {
 // DEG = active SH degree (compile time: the 3*(DEG+1)^2 coefficient loads become straight-line shared-memory
 // reads with immediate offsets; the generic loop cost ~300 instructions of predicates / address math per view).
 template <int DEG>
-__global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy, int sh_stride) {
+__global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs a, int gx, int gy, int sh_stride, int fused_scan) {
   extern __shared__ float4 smem4[];
   float* s_sh = reinterpret_cast<float*>(smem4);
   const int tid = threadIdx.x;
@@ -147,6 +148,20 @@ __global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs
     if (active) {
       float4* __restrict__ dst = reinterpret_cast<float4*>(a.rec) + 3 * vi;
       dst[0] = r0; dst[1] = r1; dst[2] = r2;
+    }
+  }
+  // ---- the LAST CTA to finish turns the tile counters into ranges (R2 + R5): no separate one-block launch.  Every CTA makes its
+  //      counter updates visible (fence), takes a ticket from status[3] (zeroed with the counters by the call's memset); the CTA
+  //      that draws the last ticket scans (ld.global.cg reads) and resets the ticket. ----
+  if (fused_scan) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.status + 3, 1u) == gridDim.x - 1u) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      tile_scan_block<kThreads>(a.tile_count, a.ranges, a.status, a.V * gx * gy, (long long)a.capacity);
     }
   }
 }
@@ -556,7 +571,10 @@ int launch_preprocess(const FsRasterFwdArgs& a, cudaStream_t s) {
   const int gx = tiles_x(a.W), gy = tiles_y(a.H);
   const size_t nt = (size_t)a.V * gx * gy;
   int rc;
-  if (a.tile_cursor == a.tile_count + nt) {          // adjacent scratch (the Python wrapper allocates it that way): one memset
+  const bool fused = scan_fused_into_preprocess(a);
+  if (fused) {                                       // [counters | cursors | status]: one memset, status[3] = ticket of the fused scan
+    if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, (2 * nt + 4) * 4, s), "memset tile counters"))) return rc;
+  } else if (a.tile_cursor == a.tile_count + nt) {   // adjacent scratch (the Python wrapper allocates it that way): one memset
     if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, 2 * nt * 4, s), "memset tile counters"))) return rc;
   } else {
     if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, nt * 4, s), "memset tile_count"))) return rc;
@@ -565,13 +583,13 @@ int launch_preprocess(const FsRasterFwdArgs& a, cudaStream_t s) {
   if (a.P > 0) {
     const int sh_stride = (a.M * 3) | 1;
     const size_t smem = a.shs ? (size_t)kThreads * sh_stride * sizeof(float) : 0;
-    void (*kern)(FsRasterFwdArgs, int, int, int) =
+    void (*kern)(FsRasterFwdArgs, int, int, int, int) =
         a.sh_degree == 0 ? preprocess_kernel<0> : a.sh_degree == 1 ? preprocess_kernel<1> : a.sh_degree == 2 ? preprocess_kernel<2> : preprocess_kernel<3>;
     if (smem > 48 * 1024) {
       if ((rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                            "cudaFuncSetAttribute(preprocess_kernel)"))) return rc;
     }
-    kern<<<(a.P + kThreads - 1) / kThreads, kThreads, smem, s>>>(a, gx, gy, sh_stride);
+    kern<<<(a.P + kThreads - 1) / kThreads, kThreads, smem, s>>>(a, gx, gy, sh_stride, fused ? 1 : 0);
     if ((rc = check_cuda(cudaGetLastError(), "preprocess_kernel"))) return rc;
   }
   return FS_OK;

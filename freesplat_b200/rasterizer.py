@@ -183,18 +183,19 @@ def _alloc_state(dev, P, V, H, W, M, sh_degree, scale_modifier, capacity, sh_lay
     # only the parity tests ask for these (the hot path neither writes nor reads them)
     st.cov3D = e(V, P, 6) if debug_buffers else None
     st.tiles_touched = e(V, P, dtype=torch.int32) if debug_buffers else None
-    st.tile_buf = e(2 * nt, dtype=torch.int32)          # [counters | cursors]: adjacent, zeroed by ONE memset in the call
+    # [counters | cursors | status]: adjacent -> ONE memset per call, and the tile scan runs in the last preprocess CTA
+    st.tile_buf = e(2 * nt + 4, dtype=torch.int32)
     st.ranges = e(nt, 2, dtype=torch.int32)
     st.keybuf = e(max(capacity, 1), dtype=torch.int64)
     st.point_list = e(max(capacity, 1), dtype=torch.int32)
-    st.status = e(4, dtype=torch.int32)
+    st.status = st.tile_buf[2 * nt:]
     return st
 
 
 def _fwd_args(st: RasterState, means3D, opacities, views, shs, colors_precomp, scales, rotations, cov3D_precomp,
               prefiltered=False) -> FsRasterFwdArgs:
-    nt = st.tile_buf.numel() // 2
-    tile_count, tile_cursor = st.tile_buf[:nt], st.tile_buf[nt:]
+    nt = (st.tile_buf.numel() - 4) // 2
+    tile_count, tile_cursor = st.tile_buf[:nt], st.tile_buf[nt:2 * nt]
     return FsRasterFwdArgs(
         P=st.P, V=st.V, H=st.H, W=st.W, sh_degree=st.sh_degree, M=st.M, scale_modifier=st.scale_modifier,
         prefiltered=int(prefiltered), stages=8 if RENDER_PACKED else 0, sh_layout=st.sh_layout, cov_stride=st.cov_stride, capacity=st.capacity,
@@ -386,7 +387,7 @@ class RasterPlan:
         return self
 
     def launches_per_run(self) -> int:
-        return 4 + int(self.cameras is not None)        # preprocess, tile scan, scatter, sort + render (+ camera records)
+        return 3 + int(self.cameras is not None)        # preprocess (+ tile scan in its last CTA), scatter, sort + render (+ camera records)
 
     def check(self):
         """(R, overflowed) of the last run: ONE host read (waits for the stream)."""

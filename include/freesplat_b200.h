@@ -104,7 +104,9 @@ typedef struct FsRasterFwdArgs {
   uint64_t* keybuf;      /* [capacity]  (depth_bits<<32 | gaussian) per instance,
                             sorted ascending inside each tile range on return    */
   uint32_t* point_list;  /* [capacity]  Gaussian index per sorted instance       */
-  uint32_t* status;      /* [4] {R_lo, R_hi, overflow(R>capacity), reserved}     */
+  uint32_t* status;      /* [4] {R_lo, R_hi, overflow(R>capacity), reserved}.  If tile_count, tile_cursor and status are
+                            ONE buffer [counters | cursors | status] the tile scan runs inside the preprocess kernel
+                            (its last CTA; status[3] is the ticket): one launch fewer per step                         */
 } FsRasterFwdArgs;
 
 #define FS_STAGE_PREPROCESS 1  /* per-Gaussian projection + tile counting            */

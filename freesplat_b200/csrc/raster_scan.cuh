@@ -1,6 +1,7 @@
 // raster_scan.cuh -- exclusive scan of the V*tiles tile counters -> `ranges` (this IS identifyTileRanges), the instance total R
 // and the overflow flag in `status`, plus a counting sort of the tiles into 32 population buckets (heaviest-first processing
-// order for the render kernel, written over the consumed counters).  One block of NT threads, 4 counters per thread and pass.
+// order for the render kernel, written over the consumed counters).  One block of NT threads, 4096 / NT consecutive counters per
+// thread and pass: 640x480 x 3 views (3600 tiles) is ONE pass for 1024 and for 256 threads alike.
 #pragma once
 #include "common.cuh"
 
@@ -17,17 +18,20 @@ __device__ __noinline__ void tile_scan_block(uint32_t* __restrict__ count, uint3
   __shared__ unsigned long long carry_s;
   __shared__ uint32_t hist[32], bbase[32];
   constexpr int NW = NT / 32;
+  constexpr int IT = 4096 / NT;                      // counters per thread and pass
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry_s = 0ull;
   if (tid < 32) hist[tid] = 0u;
   __syncthreads();
   const unsigned long long cap = (unsigned long long)capacity;
-  for (int base = 0; base < n; base += 4 * NT) {
-    const int k0 = base + 4 * tid;
-    uint32_t c[4];
+  for (int base = 0; base < n; base += IT * NT) {
+    const int k0 = base + IT * tid;
+    uint32_t c[IT];
 #pragma unroll
-    for (int e = 0; e < 4; e++) c[e] = (k0 + e < n) ? __ldcg(count + k0 + e) : 0u;
-    const unsigned long long s4 = (unsigned long long)c[0] + c[1] + c[2] + c[3];
+    for (int e = 0; e < IT; e++) c[e] = (k0 + e < n) ? __ldcg(count + k0 + e) : 0u;
+    unsigned long long s4 = 0ull;
+#pragma unroll
+    for (int e = 0; e < IT; e++) s4 += c[e];
     unsigned long long incl = s4;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -50,7 +54,7 @@ __device__ __noinline__ void tile_scan_block(uint32_t* __restrict__ count, uint3
     const unsigned long long warp_excl = warp ? warp_sums[warp - 1] : 0ull;
     unsigned long long st = carry + warp_excl + incl - s4;
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
+    for (int e = 0; e < IT; e++) {
       const unsigned long long end = st + c[e];
       if (k0 + e < n) {
         // clamp so that a too-small workspace can never be overrun (the call reports overflow)

@@ -26,6 +26,10 @@ VIEW_FLOATS = 48
 REC_FLOATS = 12
 # FS_STAGE_RENDER_PACKED: blend with the two-pixels-per-lane packed-fp32 kernel (bit-identical results; A/B switch)
 RENDER_PACKED = os.environ.get("FREESPLAT_B200_RENDER_PACKED", "0") == "1"
+# tile scan inside the last preprocess CTA instead of its own one-block launch: built and bit-identical, but measured SLOWER
+# (preprocess 47 -> 61 us against 9 us saved in the binning stage: a 256-thread CTA scans 3600 counters in ~14 us at the tail of
+# the kernel, the 1024-thread launch in ~6 us + launch latency that the CUDA graph already hides) -> off by default
+FUSED_SCAN = os.environ.get("FREESPLAT_B200_FUSED_SCAN", "0") == "1"
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -188,7 +192,8 @@ def _alloc_state(dev, P, V, H, W, M, sh_degree, scale_modifier, capacity, sh_lay
     st.ranges = e(nt, 2, dtype=torch.int32)
     st.keybuf = e(max(capacity, 1), dtype=torch.int64)
     st.point_list = e(max(capacity, 1), dtype=torch.int32)
-    st.status = st.tile_buf[2 * nt:]
+    # FREESPLAT_B200_FUSED_SCAN=0: a separate status buffer -> the stand-alone one-block scan kernel runs (A/B measurements)
+    st.status = st.tile_buf[2 * nt:] if FUSED_SCAN else e(4, dtype=torch.int32)
     return st
 
 
@@ -387,7 +392,8 @@ class RasterPlan:
         return self
 
     def launches_per_run(self) -> int:
-        return 3 + int(self.cameras is not None)        # preprocess (+ tile scan in its last CTA), scatter, sort + render (+ camera records)
+        # preprocess, tile scan (its own launch unless FUSED_SCAN), scatter, sort + render (+ camera records)
+        return (3 if FUSED_SCAN else 4) + int(self.cameras is not None)
 
     def check(self):
         """(R, overflowed) of the last run: ONE host read (waits for the stream)."""

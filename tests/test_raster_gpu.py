@@ -70,6 +70,24 @@ def test_packed_two_pixel_render_kernel_is_bit_identical(monkeypatch):
         assert torch.equal(a.point_list[:R], b.point_list[:R]) and torch.equal(a.keybuf[:R], b.keybuf[:R])
 
 
+def test_scan_fused_into_preprocess_is_bit_identical(monkeypatch):
+    """[counters | cursors | status] in one buffer -> the tile scan runs in the last preprocess CTA (ticket in status[3]);
+    a separate status buffer -> the stand-alone scan kernel.  Same ranges, lists and images; 18 views x 300 tiles covers the
+    multi-pass case of the 256-thread scan."""
+    from freesplat_b200 import rasterizer
+    for sc in (synth.pixel_aligned_scene(seed=1, h=120, w=160, n_context=2, n_target=3, keep=None),
+               synth.pixel_aligned_scene(seed=2, h=240, w=320, n_context=2, n_target=18, keep=20000)):
+        out = []
+        for fused in (False, True):
+            monkeypatch.setattr(rasterizer, "FUSED_SCAN", fused)
+            st, _ = rc.run_cuda(sc)
+            R = st.num_rendered()
+            out.append((R, st.ranges.clone(), st.point_list[:R].clone(), st.color.clone(), st.n_contrib.clone()))
+        assert out[0][0] == out[1][0] > 0
+        for a, b in zip(out[0][1:], out[1][1:]):
+            assert torch.equal(a, b)
+
+
 def test_capacity_overflow_retry():
     sc = synth.random_scene(seed=5, h=128, w=128, P=5000)
     st, _ = rc.run_cuda(sc, capacity=100)       # far too small: must re-run with the reported R

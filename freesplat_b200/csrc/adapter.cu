@@ -313,6 +313,34 @@ __global__ void __launch_bounds__(256) ply_vertices_kernel(FsPlyArgs a) {
   for (int k = threadIdx.x; k < cnt; k += 256) dst[k] = rows[k];
 }
 
+// Evaluation image dump (src/misc/image_io.py:36-53 `prep_image`, called by `save_image` from
+// model_wrapper.py:382-416): float images in [0,1] -> uint8 HWC, batch concatenated along the width ("b c h w -> c h (b w)"),
+// single-channel images repeated to 3 channels, value = uint8(clip(x, 0, 1) * 255) (truncation, as torch's .type(torch.uint8)).
+// One pass on the device: the D2H copy that follows moves 1 byte per sample instead of 4.
+__global__ void __launch_bounds__(256) image_u8_kernel(int B, int C, int H, int W, const float* __restrict__ img, uint8_t* __restrict__ out) {
+  const int Co = C == 1 ? 3 : C;
+  const size_t total = (size_t)H * B * W;
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;       // output pixel (y, b*W + x)
+  if (i >= total) return;
+  const int y = (int)(i / ((size_t)B * W));
+  const int bx = (int)(i - (size_t)y * B * W);
+  const int b = bx / W, x = bx - b * W;
+  const float* src = img + ((size_t)b * C * H + y) * W + x;
+  uint8_t* dst = out + i * Co;
+  for (int c = 0; c < Co; c++) {
+    const float v = src[(size_t)(C == 1 ? 0 : c) * H * W];
+    const float q = fminf(fmaxf(v, 0.f), 1.f) * 255.f;
+    dst[c] = (uint8_t)q;
+  }
+}
+
+int launch_image_u8(int B, int C, int H, int W, const float* img, uint8_t* out, cudaStream_t s) {
+  const size_t total = (size_t)H * B * W;
+  if (total == 0) return FS_OK;
+  image_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(B, C, H, W, img, out);
+  return check_cuda(cudaGetLastError(), "image_u8_kernel");
+}
+
 int launch_ply_vertices(const FsPlyArgs& a, cudaStream_t s) {
   if (a.N <= 0) return FS_OK;
   ply_vertices_kernel<<<(a.N + 255) / 256, 256, 0, s>>>(a);

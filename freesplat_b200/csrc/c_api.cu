@@ -223,6 +223,12 @@ int fs_depth_head_backward(const FsDepthHeadBwdArgs* a, void* stream) {
   return launch_depth_head_bwd(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int fs_image_u8(int32_t B, int32_t C, int32_t H, int32_t W, const float* images, uint8_t* out, void* stream) {
+  FS_REQUIRE(B >= 0 && H >= 0 && W >= 0 && (C == 1 || C == 3 || C == 4), "bad sizes (1, 3 or 4 channels)");
+  FS_REQUIRE((long long)B * H * W == 0 || (images && out), "NULL buffer");
+  return launch_image_u8(B, C, H, W, images, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int fs_ply_vertices(const FsPlyArgs* a, void* stream) {
   FS_REQUIRE(a != nullptr && a->N >= 0 && a->d_sh >= 1, "bad sizes");
   FS_REQUIRE(a->N == 0 || (a->means && a->scales && a->rotations && a->harmonics && a->opacities && a->table), "NULL buffer");

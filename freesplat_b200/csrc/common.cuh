@@ -38,6 +38,7 @@ int launch_gaussian_head(const FsAdapterArgs& a, cudaStream_t s);   // adapter.c
 int launch_backproject(const FsBackprojectArgs& a, cudaStream_t s);   // adapter.cu
 int launch_backproject_bwd(const FsBackprojectArgs& a, const float* g_means, float* d_depth, cudaStream_t s);   // adapter.cu
 int launch_ply_vertices(const FsPlyArgs& a, cudaStream_t s);          // adapter.cu
+int launch_image_u8(int B, int C, int H, int W, const float* img, uint8_t* out, cudaStream_t s);   // adapter.cu
 int launch_depth_head(const FsDepthHeadArgs& a, cudaStream_t s);    // depth_head.cu
 int launch_depth_head_bwd(const FsDepthHeadBwdArgs& a, cudaStream_t s);   // depth_head.cu
 int launch_gaussian_head_bwd(const FsAdapterBwdArgs& a, cudaStream_t s);  // adapter.cu

@@ -365,6 +365,10 @@ typedef struct FsPlyArgs {
 } FsPlyArgs;
 int fs_ply_vertices(const FsPlyArgs* args, void* stream);
 
+/* Evaluation image dump (src/misc/image_io.py:36-53 prep_image, used by save_image at model_wrapper.py:382-416): images
+ * [B,C,H,W] float (C = 1, 3 or 4) -> uint8 [H, B*W, C'] (C' = 3 for C = 1), uint8(clip(x,0,1)*255), batch side by side.   */
+int fs_image_u8(int32_t B, int32_t C, int32_t H, int32_t W, const float* images, uint8_t* out, void* stream);
+
 /* ------------------------------------------------------------ depth back-projection */
 /* GaussianAdapter.forward(fusion=True) (gaussian_adapter.py:175-189 -> Create_from_depth_map.project :48-68): world
  * coordinates of every pixel of the V context views from their depth maps, one launch.                          */

@@ -52,7 +52,7 @@ EXPORTS = [
     "fs_raster_forward", "fs_raster_backward", "fs_mark_visible", "fs_camera_records",
     "fs_cost_volume_forward", "fs_cost_volume_backward",
     "fs_ptf_match", "fs_ptf_merge", "fs_ptf_gru_inputs", "fs_ptf_gru_update", "fs_ptf_gru_output",
-    "fs_ptf_view_setup", "fs_ptf_merge_backward", "fs_ptf_gru_output_backward", "fs_ptf_gru_update_backward", "fs_ptf_gru_inputs_backward", "fs_gaussian_head_backward", "fs_depth_head_backward", "fs_backproject_backward", "fs_graph_capture_begin", "fs_graph_capture_end", "fs_graph_launch", "fs_graph_destroy",
+    "fs_ptf_view_setup", "fs_ptf_pool_update", "fs_ptf_pool_order", "fs_ptf_pool_gather", "fs_ptf_merge_backward", "fs_ptf_gru_output_backward", "fs_ptf_gru_update_backward", "fs_ptf_gru_inputs_backward", "fs_gaussian_head_backward", "fs_depth_head_backward", "fs_backproject_backward", "fs_graph_capture_begin", "fs_graph_capture_end", "fs_graph_launch", "fs_graph_destroy",
     "fs_ptf_gru", "fs_ptf_gru_wscratch_bytes", "fs_gaussian_head", "fs_depth_head", "fs_backproject", "fs_ply_vertices", "fs_image_u8",
 ]
 

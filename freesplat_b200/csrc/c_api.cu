@@ -161,6 +161,30 @@ int fs_ptf_merge(const FsPtfArgs* a, void* stream) {
   return launch_ptf_merge(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int fs_ptf_pool_update(const FsPtfArgs* a, void* stream) {
+  if (int rc = check_ptf(a)) return rc;
+  FS_REQUIRE(a->feats && a->dens && a->wemb && a->ext && a->depth && a->v_feats && a->v_coords && a->v_dens && a->v_wemb && a->v_ext,
+             "NULL state buffer");
+  FS_REQUIRE((a->F & 3) == 0 && (a->n_upper == 0 || a->gru_out), "F must be a multiple of 4; gru_out is NULL");
+  return launch_ptf_pool_update(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_ptf_pool_order(int32_t n_upper, const int32_t* counts, const int32_t* phys_in, const uint8_t* match, int32_t* block_scratch,
+                      int32_t* phys_out, void* stream) {
+  FS_REQUIRE(n_upper >= 0 && (n_upper == 0 || (counts && match && block_scratch && phys_out)), "bad arguments");
+  return launch_ptf_pool_order(n_upper, counts, phys_in, match, block_scratch, phys_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fs_ptf_pool_gather(int32_t n_upper, const int32_t* n_dev, const int32_t* phys, int32_t F, const float* feats, const float* coords,
+                       const float* dens, const float* wemb, const float* ext, const float* depth, float* o_feats, float* o_coords,
+                       float* o_dens, float* o_wemb, float* o_ext, float* o_depth, void* stream) {
+  FS_REQUIRE(n_upper >= 0 && F >= 4 && (F & 3) == 0, "bad sizes (F must be a multiple of 4)");
+  FS_REQUIRE(n_upper == 0 || (n_dev && phys && feats && coords && dens && wemb && ext && depth && o_feats && o_coords && o_dens && o_wemb &&
+                              o_ext && o_depth), "NULL buffer");
+  return launch_ptf_pool_gather(n_upper, n_dev, phys, F, feats, coords, dens, wemb, ext, depth, o_feats, o_coords, o_dens, o_wemb, o_ext,
+                                o_depth, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int fs_ptf_merge_backward(const FsPtfMergeBwdArgs* a, void* stream) {
   FS_REQUIRE(a != nullptr && a->H >= 1 && a->W >= 1 && a->F >= 4 && (a->F & 3) == 0 && a->N >= 0 && a->n_keep >= 0 && a->n_match >= 0,
              "bad sizes (F must be a multiple of 4)");

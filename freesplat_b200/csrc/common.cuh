@@ -34,6 +34,11 @@ int launch_ptf_view_setup(int V, int H, int W, const float* ext, const float* K,
 int launch_ptf_match(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
 int launch_ptf_merge(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
 int launch_ptf_merge_bwd(const FsPtfMergeBwdArgs& a, cudaStream_t s);   // ptf.cu
+int launch_ptf_pool_update(const FsPtfArgs& a, cudaStream_t s);   // ptf.cu
+int launch_ptf_pool_order(int n_upper, const int* counts, const int* phys_in, const uint8_t* match, int* blk, int* phys_out, cudaStream_t s);
+int launch_ptf_pool_gather(int n_upper, const int* n_dev, const int* phys, int F, const float* feats, const float* coords, const float* dens,
+                           const float* wemb, const float* ext, const float* depth, float* o_feats, float* o_coords, float* o_dens,
+                           float* o_wemb, float* o_ext, float* o_depth, cudaStream_t s);
 int launch_gaussian_head(const FsAdapterArgs& a, cudaStream_t s);   // adapter.cu
 int launch_backproject(const FsBackprojectArgs& a, cudaStream_t s);   // adapter.cu
 int launch_backproject_bwd(const FsBackprojectArgs& a, const float* g_means, float* d_depth, cudaStream_t s);   // adapter.cu

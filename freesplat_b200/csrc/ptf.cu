@@ -397,6 +397,238 @@ int launch_ptf_merge_bwd(const FsPtfMergeBwdArgs& a, cudaStream_t s) {
   return check_cuda(cudaGetLastError(), "ptf_merge_bwd_kernel");
 }
 
+// =====================================================================================================================
+// Append-only pool (inference fold).  ptf_compact_kernel rewrites the WHOLE state (344 B per Gaussian, read + write) at every
+// fold step although a step only changes the matched rows and adds the unmatched pixels of view i.  Here the state lives in
+// place: row r of the pool never moves; a fused Gaussian is updated where it is, new ones are appended behind the last row.
+// The ORDER contract of the reference ([kept] ++ [fused] ++ [appended], per step) is carried by an index instead of by the
+// data: `phys[k]` = pool row of logical position k.  A step's order update is a stable partition of that index by the step's
+// match flags (N ints instead of 344 N bytes); it depends only on the flags, so the host runs it on a side stream under the
+// following steps.  ONE gather at the end materialises the state in logical order.  Arithmetic per row is unchanged (wmean),
+// so the result is bit-identical to the compacting fold.
+// ---------------------------------------------------------------------------------------------------------------------
+// in-place merge of the matched pairs (pair m: pool row j = pair_j[m], pixel p = pair_p[m]); one warp per pair
+__global__ void __launch_bounds__(256) ptf_pool_fuse_kernel(FsPtfArgs a, float* __restrict__ feats, float* __restrict__ coords,
+                                                            float* __restrict__ dens, float* __restrict__ wemb, float* __restrict__ ext,
+                                                            float* __restrict__ depth) {
+  const int M = a.counts_out[2];
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int j = a.pair_j[m], p = a.pair_p[m];
+  const int F = a.F;
+  const float w0 = dens[j], w1 = a.v_dens[p], ws = w0 + w1;
+  // every lane reads what it needs BEFORE any lane writes (the row is updated in place)
+  float v = 0.f;
+  if (lane < 3) v = wmean(coords[3 * (size_t)j + lane], w0, a.v_coords[3 * (size_t)p + lane], w1, ws);
+  else if (lane == 3) v = wmean(depth[j], w0, a.v_depth[p], w1, ws);
+  else if (lane == 4) v = wemb[j] + a.v_wemb[p];
+  else if (lane >= 8 && lane < 24) v = wmean(ext[16 * (size_t)j + (lane - 8)], w0, a.v_ext[lane - 8], w1, ws);
+  __syncwarp();
+  if (lane < 3) coords[3 * (size_t)j + lane] = v;
+  else if (lane == 3) depth[j] = v;
+  else if (lane == 4) wemb[j] = v;
+  else if (lane == 5) dens[j] = ws;
+  else if (lane >= 8 && lane < 24) ext[16 * (size_t)j + (lane - 8)] = v;
+  for (int e = lane; e < F; e += 32) feats[(size_t)j * F + e] = a.gru_out[(size_t)m * F + e];
+}
+
+// unmatched pixels of view i -> rows N, N+1, ... (raster order); block = kPtfItems pixels
+__global__ void __launch_bounds__(kPtfThreads) ptf_pool_append_kernel(FsPtfArgs a, float* __restrict__ feats, float* __restrict__ coords,
+                                                                      float* __restrict__ dens, float* __restrict__ wemb, float* __restrict__ ext,
+                                                                      float* __restrict__ depth) {
+  constexpr int R = kPtfItems / kPtfThreads;
+  __shared__ int s_warp[R * 8];
+  __shared__ int s_dst[kPtfItems];
+  const int N = a.counts_in[0], HW = a.H * a.W, F = a.F;
+  const int base = blockIdx.x * kPtfItems;
+  if (base >= HW) return;
+  const int off_app = a.block_counts[3 * (size_t)blockIdx.x + 2];
+  int ra[R];
+  block_ranks([&](int r) { const int k = base + r * kPtfThreads + threadIdx.x; return k < HW && a.append[k]; }, ra, s_warp);
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int t = r * kPtfThreads + threadIdx.x, k = base + t;
+    int d = -1;
+    if (k < HW && a.append[k]) {
+      d = N + off_app + ra[r];
+      coords[3 * (size_t)d] = a.v_coords[3 * (size_t)k]; coords[3 * (size_t)d + 1] = a.v_coords[3 * (size_t)k + 1];
+      coords[3 * (size_t)d + 2] = a.v_coords[3 * (size_t)k + 2];
+      dens[d] = a.v_dens[k]; wemb[d] = a.v_wemb[k]; depth[d] = a.v_depth[k];
+      const float4* se = reinterpret_cast<const float4*>(a.v_ext);
+      float4* de = reinterpret_cast<float4*>(ext + 16 * (size_t)d);
+      de[0] = se[0]; de[1] = se[1]; de[2] = se[2]; de[3] = se[3];
+    }
+    s_dst[t] = d;
+  }
+  __syncthreads();
+  const int cpr = F >> 2;
+  const float4* vf4 = reinterpret_cast<const float4*>(a.v_feats);
+  float4* out4 = reinterpret_cast<float4*>(feats);
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < kPtfItems * cpr; idx += kPtfThreads) {
+    const int t = idx / cpr, ch = idx - t * cpr;
+    const int d = s_dst[t];
+    if (d >= 0) out4[(size_t)d * cpr + ch] = vf4[(size_t)(base + t) * cpr + ch];
+  }
+}
+
+// ---- order index: stable partition of phys[0..N) by the step's match flags, then the appended rows ----
+// counts[0] = N (rows before the step), counts[1] = n_keep, counts[3] = n_append
+__global__ void __launch_bounds__(kPtfThreads) ptf_order_count_kernel(const int* __restrict__ counts, const int* __restrict__ phys,
+                                                                      const uint8_t* __restrict__ match, int* __restrict__ blk) {
+  __shared__ int s_cnt;
+  const int N = counts[0];
+  const int base = blockIdx.x * kPtfItems;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < kPtfItems / kPtfThreads; r++) {
+    const int k = base + r * kPtfThreads + threadIdx.x;
+    if (k < N) c += match[phys ? phys[k] : k] ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) blk[blockIdx.x] = s_cnt;
+}
+
+__global__ void __launch_bounds__(1024) ptf_order_scan_kernel(int* __restrict__ blk, int nb) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int k = base + tid;
+    const int c = k < nb ? blk[k] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int endv = carry + (warp ? warp_sums[warp - 1] : 0) + incl;
+    if (k < nb) blk[k] = endv - c;                          // exclusive offset of the block's matched rows
+    __syncthreads();
+    if (tid == 1023) carry = endv;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kPtfThreads) ptf_order_scatter_kernel(const int* __restrict__ counts, const int* __restrict__ phys,
+                                                                        const uint8_t* __restrict__ match, const int* __restrict__ blk,
+                                                                        int* __restrict__ phys_out) {
+  constexpr int R = kPtfItems / kPtfThreads;
+  __shared__ int s_warp[R * 8];
+  const int N = counts[0], n_keep = counts[1], n_app = counts[3];
+  const int base = blockIdx.x * kPtfItems;
+  if (base >= N + n_app) return;
+  int row[R];
+  bool mt[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int k = base + r * kPtfThreads + threadIdx.x;
+    row[r] = k < N ? (phys ? phys[k] : k) : -1;
+    mt[r] = k < N && match[row[r]];
+  }
+  int rm[R];
+  block_ranks([&](int r) { return mt[r]; }, rm, s_warp);
+  const int off_m = base < N ? blk[blockIdx.x] : 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int k = base + r * kPtfThreads + threadIdx.x;
+    if (k < N) {
+      // matched rows before position k (exclusive): off_m + rm[r]; kept rows before it: k - that
+      const int before = off_m + rm[r];
+      phys_out[mt[r] ? n_keep + before : k - before] = row[r];
+    } else if (k < N + n_app) {
+      phys_out[k] = k;                                      // appended rows sit in raster order behind the old ones, pool row = position
+    }
+  }
+}
+
+// final materialisation: logical position k <- pool row phys[k]
+__global__ void __launch_bounds__(kPtfThreads) ptf_pool_gather_kernel(const int* __restrict__ n_dev, const int* __restrict__ phys, int F,
+                                                                      const float* __restrict__ feats, const float* __restrict__ coords,
+                                                                      const float* __restrict__ dens, const float* __restrict__ wemb,
+                                                                      const float* __restrict__ ext, const float* __restrict__ depth,
+                                                                      float* __restrict__ o_feats, float* __restrict__ o_coords,
+                                                                      float* __restrict__ o_dens, float* __restrict__ o_wemb,
+                                                                      float* __restrict__ o_ext, float* __restrict__ o_depth) {
+  __shared__ int s_src[kPtfItems];
+  const int N = n_dev[0];
+  const int base = blockIdx.x * kPtfItems;
+  if (base >= N) return;
+#pragma unroll
+  for (int r = 0; r < kPtfItems / kPtfThreads; r++) {
+    const int t = r * kPtfThreads + threadIdx.x, k = base + t;
+    int src = -1;
+    if (k < N) {
+      src = phys[k];
+      o_coords[3 * (size_t)k] = coords[3 * (size_t)src]; o_coords[3 * (size_t)k + 1] = coords[3 * (size_t)src + 1];
+      o_coords[3 * (size_t)k + 2] = coords[3 * (size_t)src + 2];
+      o_dens[k] = dens[src]; o_wemb[k] = wemb[src]; o_depth[k] = depth[src];
+      const float4* se = reinterpret_cast<const float4*>(ext + 16 * (size_t)src);
+      float4* de = reinterpret_cast<float4*>(o_ext + 16 * (size_t)k);
+      const float4 e0 = se[0], e1 = se[1], e2 = se[2], e3 = se[3];
+      de[0] = e0; de[1] = e1; de[2] = e2; de[3] = e3;
+    }
+    s_src[t] = src;
+  }
+  __syncthreads();
+  const int cpr = F >> 2;
+  const float4* f4 = reinterpret_cast<const float4*>(feats);
+  float4* out4 = reinterpret_cast<float4*>(o_feats);
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < kPtfItems * cpr; idx += kPtfThreads) {
+    const int t = idx / cpr, ch = idx - t * cpr;
+    const int src = s_src[t];
+    if (src >= 0) out4[(size_t)(base + t) * cpr + ch] = f4[(size_t)src * cpr + ch];
+  }
+}
+
+int launch_ptf_pool_update(const FsPtfArgs& a, cudaStream_t s) {
+  // the pool IS the state: a.feats ... a.depth are updated in place (the const of the struct refers to the compacting fold)
+  float* feats = const_cast<float*>(a.feats); float* coords = const_cast<float*>(a.coords); float* dens = const_cast<float*>(a.dens);
+  float* wemb = const_cast<float*>(a.wemb); float* ext = const_cast<float*>(a.ext); float* depth = const_cast<float*>(a.depth);
+  const int HW = a.H * a.W;
+  if (a.n_upper > 0) {
+    ptf_pool_fuse_kernel<<<(a.n_upper + 7) / 8, 256, 0, s>>>(a, feats, coords, dens, wemb, ext, depth);
+    if (int rc = check_cuda(cudaGetLastError(), "ptf_pool_fuse_kernel")) return rc;
+  }
+  ptf_pool_append_kernel<<<(HW + kPtfItems - 1) / kPtfItems, kPtfThreads, 0, s>>>(a, feats, coords, dens, wemb, ext, depth);
+  return check_cuda(cudaGetLastError(), "ptf_pool_append_kernel");
+}
+
+int launch_ptf_pool_order(int n_upper, const int* counts, const int* phys_in, const uint8_t* match, int* blk, int* phys_out, cudaStream_t s) {
+  const int nb = (n_upper + kPtfItems - 1) / kPtfItems;
+  if (nb <= 0) return FS_OK;
+  ptf_order_count_kernel<<<nb, kPtfThreads, 0, s>>>(counts, phys_in, match, blk);
+  if (int rc = check_cuda(cudaGetLastError(), "ptf_order_count_kernel")) return rc;
+  ptf_order_scan_kernel<<<1, 1024, 0, s>>>(blk, nb);
+  if (int rc = check_cuda(cudaGetLastError(), "ptf_order_scan_kernel")) return rc;
+  ptf_order_scatter_kernel<<<nb, kPtfThreads, 0, s>>>(counts, phys_in, match, blk, phys_out);
+  return check_cuda(cudaGetLastError(), "ptf_order_scatter_kernel");
+}
+
+int launch_ptf_pool_gather(int n_upper, const int* n_dev, const int* phys, int F, const float* feats, const float* coords, const float* dens,
+                           const float* wemb, const float* ext, const float* depth, float* o_feats, float* o_coords, float* o_dens,
+                           float* o_wemb, float* o_ext, float* o_depth, cudaStream_t s) {
+  const int nb = (n_upper + kPtfItems - 1) / kPtfItems;
+  if (nb <= 0) return FS_OK;
+  ptf_pool_gather_kernel<<<nb, kPtfThreads, 0, s>>>(n_dev, phys, F, feats, coords, dens, wemb, ext, depth, o_feats, o_coords, o_dens, o_wemb,
+                                                    o_ext, o_depth);
+  return check_cuda(cudaGetLastError(), "ptf_pool_gather_kernel");
+}
+
 __global__ void ptf_fill_kernel(uint32_t* p, uint32_t v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

@@ -303,6 +303,56 @@ class _PtfMerge(torch.autograd.Function):
         return (*d_state, *d_view, d_gru if ctx.has_gru else None, None)
 
 
+# 1: the inference fold keeps the state in an append-only pool (rows never move, an order index carries the reference's output
+#    order, one gather at the end); 0: the compacting fold (fs_ptf_merge rewrites the whole state every step)
+POOL = os.environ.get("FREESPLAT_B200_PTF_POOL", "1") == "1"
+
+
+def _fold_pool(L, gru_tc, feats, coords, dens, wemb, depths, ext16, E_inv, K_px, h, w, F, V, HW, cap, depth_thres, counts, scratch, stream,
+               view_ready, ts, dev):
+    """Sync-free inference fold on the append-only pool (csrc/ptf.cu, "Append-only pool")."""
+    zbuf, pix, zeta, match, append, block_counts, pair_j, pair_p = scratch
+    e = lambda *s_: torch.empty(s_, dtype=torch.float32, device=dev)
+    pool = (e(cap, F), e(cap, 3), e(cap), e(cap), e(cap, 16), e(cap))
+    pool[0][:HW] = feats[0]; pool[1][:HW] = coords[0]; pool[2][:HW] = dens[0]; pool[3][:HW] = wemb[0]
+    pool[4][:HW] = ext16[0]; pool[5][:HW] = depths[0]
+    if V == 1:
+        return (pool[0][:HW], pool[1][:HW], pool[4][:HW].reshape(HW, 4, 4), pool[5][:HW])
+    match_all = torch.empty((V - 1, cap), dtype=torch.uint8, device=dev)       # step i's flags by pool row: the order passes read them later
+    phys = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)]
+    blk = torch.empty((cap + 511) // 512 + 1, dtype=torch.int32, device=dev)
+    gru_buf = e(min(cap, (V - 1) * HW), F)
+    side = torch.cuda.Stream(dev)
+    ev_match = [torch.cuda.Event() for _ in range(V)]
+    with torch.cuda.device(dev):
+        for i in range(1, V):
+            if view_ready is not None:
+                ts.wait_event(view_ready[i])
+            n_up = min(cap, i * HW)
+            sc = (zbuf, pix, zeta, match_all[i - 1], append, block_counts, pair_j, pair_p)
+            view = (feats[i], coords[i], dens[i], wemb[i], depths[i], ext16[i], E_inv[i], K_px[i])
+            a = _ptf_args(h, w, F, n_up, depth_thres, pool, counts[i - 1, 4:5], view, sc, counts[i])
+            check(L.fs_ptf_match(C.byref(a), C.c_void_p(stream)), "fs_ptf_match")
+            ev_match[i].record(ts)
+            gru_tc(n_up, pair_j, pair_p, pool, feats[i], dens[i], wemb[i], stream, out=gru_buf, M_dev=counts[i, 2:3])
+            a.gru_out = ptr(gru_buf)
+            check(L.fs_ptf_pool_update(C.byref(a), C.c_void_p(stream)), "fs_ptf_pool_update")
+            # the order index only needs this step's flags and counters: side stream, under the next steps' kernels
+            side.wait_event(ev_match[i])
+            check(L.fs_ptf_pool_order(C.c_int32(min(cap, (i + 1) * HW)), C.c_void_p(ptr(counts[i])),
+                                      C.c_void_p(ptr(phys[(i - 1) & 1]) if i > 1 else None), C.c_void_p(ptr(match_all[i - 1])),
+                                      C.c_void_p(ptr(blk)), C.c_void_p(ptr(phys[i & 1])), C.c_void_p(side.cuda_stream)), "fs_ptf_pool_order")
+        ts.wait_stream(side)
+        out = (e(cap, F), e(cap, 3), e(cap), e(cap), e(cap, 16), e(cap))
+        check(L.fs_ptf_pool_gather(C.c_int32(cap), C.c_void_p(ptr(counts[V - 1, 4:5])), C.c_void_p(ptr(phys[(V - 1) & 1])), C.c_int32(F),
+                                   *[C.c_void_p(ptr(t)) for t in pool], *[C.c_void_p(ptr(t)) for t in out], C.c_void_p(stream)),
+              "fs_ptf_pool_gather")
+    for t in (match_all, blk, *phys, *pool, gru_buf):
+        t.record_stream(side)
+    N = int(counts[V - 1, 4])
+    return (out[0][:N], out[1][:N], out[4][:N].reshape(N, 4, 4), out[5][:N])
+
+
 def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, image_shape, depth_thres=0.1,
                E_inv=None, return_debug=False, timings=None, view_ready=None):
     """Flat form: feats [V,HW,F], coords [V,HW,3], dens/wemb [V,HW], depths [V,HW], extrinsics [V,4,4] (c2w),
@@ -358,6 +408,15 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
     ts = torch.cuda.current_stream(dev)
     if view_ready is not None:
         ts.wait_event(view_ready[0])
+    use_tc = fused_gru and GRU_MODE == "tc" and _gru_tc_ok(gru, F)
+    train_tc = need_grad and GRU_MODE == "tc" and _gru_has_reference_structure(gru) and _gru_tc_ok(gru, F)
+    gru_tc = _GruTc(gru, dev) if (use_tc or train_tc) else None
+    # inference with the tensor-core GRU: the whole fold is enqueued without reading a counter back (grids are sized by
+    # upper bounds, the kernels take N / M from the device counters); ONE host read at the end returns the final size
+    sync_free = use_tc and (not need_grad) and timings is None and not return_debug and SYNC_FREE
+    if sync_free and POOL:
+        return _fold_pool(L, gru_tc, feats, coords, dens, wemb, depths, ext16, E_inv, K_px, h, w, F, V, HW, cap, depth_thres, counts,
+                          scratch, stream, view_ready, ts, dev)
     if need_grad:
         state = (feats[0], coords[0], dens[0], wemb[0], ext16[0][None].expand(HW, 16).contiguous(), depths[0])
         nxt = None
@@ -368,12 +427,6 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
         state = (cur.feats, cur.coords, cur.dens, cur.wemb, cur.ext, cur.depth)
     N = HW
     debug = []
-    use_tc = fused_gru and GRU_MODE == "tc" and _gru_tc_ok(gru, F)
-    train_tc = need_grad and GRU_MODE == "tc" and _gru_has_reference_structure(gru) and _gru_tc_ok(gru, F)
-    gru_tc = _GruTc(gru, dev) if (use_tc or train_tc) else None
-    # inference with the tensor-core GRU: the whole fold is enqueued without reading a counter back (grids are sized by
-    # upper bounds, the kernels take N / M from the device counters); ONE host read at the end returns the final size
-    sync_free = use_tc and (not need_grad) and timings is None and not return_debug and SYNC_FREE
     if sync_free:
         # matched pairs of step i: M <= N_i <= i * HW (with exact z-buffer ties several globals match one pixel, so HW is
         # NOT a bound); the buffer and the GRU grid take the same upper bound as the state, CTAs beyond M_dev exit at once

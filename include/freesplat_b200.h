@@ -237,6 +237,19 @@ typedef struct FsPtfArgs {
 int fs_ptf_match(const FsPtfArgs* args, void* stream);
 int fs_ptf_merge(const FsPtfArgs* args, void* stream);
 
+/* Append-only pool (inference fold): instead of fs_ptf_merge rewriting the whole state every step, the state arrays of `args`
+ * (feats ... depth, capacity >= N + H*W) are updated IN PLACE: fused Gaussians where they are (pair m: row pair_j[m]), the unmatched
+ * pixels of view i appended at rows N, N+1, ... (raster order).  The reference's order contract ([kept] ++ [fused] ++ [appended]
+ * per step) is tracked by an index: fs_ptf_pool_order turns phys_in (logical position -> pool row of the previous step; NULL =
+ * identity) into phys_out by a stable partition with the step's `match` flags (indexed by pool row) and the step's counters
+ * `counts` = fs_ptf_match's counts_out; fs_ptf_pool_gather materialises the state in logical order once, at the end.        */
+int fs_ptf_pool_update(const FsPtfArgs* args, void* stream);
+int fs_ptf_pool_order(int32_t n_upper, const int32_t* counts, const int32_t* phys_in, const uint8_t* match, int32_t* block_scratch,
+                      int32_t* phys_out, void* stream);
+int fs_ptf_pool_gather(int32_t n_upper, const int32_t* n_dev, const int32_t* phys, int32_t F, const float* feats, const float* coords,
+                       const float* dens, const float* wemb, const float* ext, const float* depth, float* o_feats, float* o_coords,
+                       float* o_dens, float* o_wemb, float* o_ext, float* o_depth, void* stream);
+
 /* Backward of fs_ptf_merge (training; the reference gets it from autograd through its index / cat ops,
  * encoder_freesplat.py:492-519): gradients of the new state -> gradients of the old state, of view i's candidates and of
  * the GRU output rows.  Kept / appended rows are copies; a fused row j (partner pixel p) splits by the density weights

@@ -236,3 +236,24 @@ def test_mid_size_reference_golden_forward_and_backward():
         with open(os.path.join(out_dir, "ptf_mid_golden_report.txt"), "w") as f:
             f.write("\n".join(map(str, report)))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("case", ["ties_golden", "five_views"])
+def test_pool_fold_is_bit_identical_to_compacting_fold(case, monkeypatch):
+    """The append-only pool (in-place fused rows, appended rows, order index, one gather) must return exactly what the compacting
+    fold returns: same length, same ORDER, same bits in every field -- incl. the golden case with exact z-buffer ties."""
+    from freesplat_b200 import ptf
+    if case == "ties_golden":
+        z = np.load([p for p in GOLD if "ties" in p][0])
+        seed = int(z["meta"][0])
+        args = flat_inputs(z)
+    else:
+        seed = 9
+        args = flat_inputs(synth.ptf_inputs(seed, 5, 96, 128))
+    outs = []
+    for pool in (False, True):
+        monkeypatch.setattr(ptf, "POOL", pool)
+        outs.append([t_.cpu().numpy() for t_ in _run(*args, seed)])
+    assert outs[0][0].shape == outs[1][0].shape and outs[0][0].shape[0] > args[0].shape[1]
+    for a_, b_ in zip(outs[0], outs[1]):
+        assert np.array_equal(bits(a_), bits(b_))

@@ -407,30 +407,45 @@ int launch_ptf_merge_bwd(const FsPtfMergeBwdArgs& a, cudaStream_t s) {
 // following steps.  ONE gather at the end materialises the state in logical order.  Arithmetic per row is unchanged (wmean),
 // so the result is bit-identical to the compacting fold.
 // ---------------------------------------------------------------------------------------------------------------------
-// in-place merge of the matched pairs (pair m: pool row j = pair_j[m], pixel p = pair_p[m]); one warp per pair
+// in-place merge of the matched pairs (pair m: pool row j = pair_j[m], pixel p = pair_p[m]).  Grid-stride (M is only known on the
+// device; a grid sized by its upper bound was ~300 waves of empty blocks per step): first one THREAD per pair for the scalar
+// fields (independent loads across the threads; a warp-per-pair version with dependent scalar loads took 0.12 ms per step, as
+// long as the compaction it replaces), then one thread per 16-byte chunk of the fused latents.
 __global__ void __launch_bounds__(256) ptf_pool_fuse_kernel(FsPtfArgs a, float* __restrict__ feats, float* __restrict__ coords,
                                                             float* __restrict__ dens, float* __restrict__ wemb, float* __restrict__ ext,
                                                             float* __restrict__ depth) {
   const int M = a.counts_out[2];
-  const int lane = threadIdx.x & 31;
-  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (m >= M) return;
-  const int j = a.pair_j[m], p = a.pair_p[m];
-  const int F = a.F;
-  const float w0 = dens[j], w1 = a.v_dens[p], ws = w0 + w1;
-  // every lane reads what it needs BEFORE any lane writes (the row is updated in place)
-  float v = 0.f;
-  if (lane < 3) v = wmean(coords[3 * (size_t)j + lane], w0, a.v_coords[3 * (size_t)p + lane], w1, ws);
-  else if (lane == 3) v = wmean(depth[j], w0, a.v_depth[p], w1, ws);
-  else if (lane == 4) v = wemb[j] + a.v_wemb[p];
-  else if (lane >= 8 && lane < 24) v = wmean(ext[16 * (size_t)j + (lane - 8)], w0, a.v_ext[lane - 8], w1, ws);
-  __syncwarp();
-  if (lane < 3) coords[3 * (size_t)j + lane] = v;
-  else if (lane == 3) depth[j] = v;
-  else if (lane == 4) wemb[j] = v;
-  else if (lane == 5) dens[j] = ws;
-  else if (lane >= 8 && lane < 24) ext[16 * (size_t)j + (lane - 8)] = v;
-  for (int e = lane; e < F; e += 32) feats[(size_t)j * F + e] = a.gru_out[(size_t)m * F + e];
+  const int gtid = blockIdx.x * 256 + threadIdx.x, gsize = gridDim.x * 256;
+  for (int m = gtid; m < M; m += gsize) {
+    const int j = a.pair_j[m], p = a.pair_p[m];
+    const float w0 = dens[j], w1 = a.v_dens[p], ws = w0 + w1;
+    float c[3];
+#pragma unroll
+    for (int e = 0; e < 3; e++) c[e] = wmean(coords[3 * (size_t)j + e], w0, a.v_coords[3 * (size_t)p + e], w1, ws);
+    const float z = wmean(depth[j], w0, a.v_depth[p], w1, ws);
+    const float we = wemb[j] + a.v_wemb[p];
+    float4* ej = reinterpret_cast<float4*>(ext + 16 * (size_t)j);
+    const float4* ev = reinterpret_cast<const float4*>(a.v_ext);
+    float4 E[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float4 g = ej[q], v = ev[q];
+      E[q] = make_float4(wmean(g.x, w0, v.x, w1, ws), wmean(g.y, w0, v.y, w1, ws), wmean(g.z, w0, v.z, w1, ws), wmean(g.w, w0, v.w, w1, ws));
+    }
+#pragma unroll
+    for (int e = 0; e < 3; e++) coords[3 * (size_t)j + e] = c[e];
+    depth[j] = z; wemb[j] = we; dens[j] = ws;
+#pragma unroll
+    for (int q = 0; q < 4; q++) ej[q] = E[q];
+  }
+  const int cpr = a.F >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(a.gru_out);
+  float4* f4 = reinterpret_cast<float4*>(feats);
+  const long long total = (long long)M * cpr;
+  for (long long idx = gtid; idx < total; idx += gsize) {
+    const int m = (int)(idx / cpr), ch = (int)(idx - (long long)m * cpr);
+    f4[(size_t)a.pair_j[m] * cpr + ch] = g4[idx];
+  }
 }
 
 // unmatched pixels of view i -> rows N, N+1, ... (raster order); block = kPtfItems pixels
@@ -601,7 +616,8 @@ int launch_ptf_pool_update(const FsPtfArgs& a, cudaStream_t s) {
   float* wemb = const_cast<float*>(a.wemb); float* ext = const_cast<float*>(a.ext); float* depth = const_cast<float*>(a.depth);
   const int HW = a.H * a.W;
   if (a.n_upper > 0) {
-    ptf_pool_fuse_kernel<<<(a.n_upper + 7) / 8, 256, 0, s>>>(a, feats, coords, dens, wemb, ext, depth);
+    const int blocks = min((a.n_upper + 255) / 256, 148 * 8);
+    ptf_pool_fuse_kernel<<<blocks, 256, 0, s>>>(a, feats, coords, dens, wemb, ext, depth);
     if (int rc = check_cuda(cudaGetLastError(), "ptf_pool_fuse_kernel")) return rc;
   }
   ptf_pool_append_kernel<<<(HW + kPtfItems - 1) / kPtfItems, kPtfThreads, 0, s>>>(a, feats, coords, dens, wemb, ext, depth);

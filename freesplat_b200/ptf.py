@@ -305,12 +305,20 @@ class _PtfMerge(torch.autograd.Function):
 
 # 1: the inference fold keeps the state in an append-only pool (rows never move, an order index carries the reference's output
 #    order, one gather at the end); 0: the compacting fold (fs_ptf_merge rewrites the whole state every step)
-POOL = os.environ.get("FREESPLAT_B200_PTF_POOL", "1") == "1"
+#    Measured (B200, 640x480): 10 views 4.36-4.51 ms (pool) vs 4.49-4.61 ms (compacting), 3 views 1.15 vs 1.08 ms: the final gather
+#    and the order passes cost what the smaller per-step traffic saves on short folds -> "auto" uses the pool from 6 views on
+#    (it also halves the state memory: no ping-pong buffers).
+POOL = os.environ.get("FREESPLAT_B200_PTF_POOL", "auto")
+POOL = {"1": True, "0": False}.get(POOL, "auto")
 
 
 def _fold_pool(L, gru_tc, feats, coords, dens, wemb, depths, ext16, E_inv, K_px, h, w, F, V, HW, cap, depth_thres, counts, scratch, stream,
                view_ready, ts, dev):
-    """Sync-free inference fold on the append-only pool (csrc/ptf.cu, "Append-only pool")."""
+    """Sync-free inference fold on the append-only pool (csrc/ptf.cu, "Append-only pool").
+
+    The fold is a few small kernels per view; what the host spends per step decides whether the GPU waits (measured: 6.2 ms of
+    Python for 4.1 ms of kernels when every step re-built its argument structs from tensor views).  The two structs are therefore
+    built ONCE and only the fields that change are patched per step with plain pointer arithmetic."""
     zbuf, pix, zeta, match, append, block_counts, pair_j, pair_p = scratch
     e = lambda *s_: torch.empty(s_, dtype=torch.float32, device=dev)
     pool = (e(cap, F), e(cap, 3), e(cap), e(cap), e(cap, 16), e(cap))
@@ -323,31 +331,53 @@ def _fold_pool(L, gru_tc, feats, coords, dens, wemb, depths, ext16, E_inv, K_px,
     blk = torch.empty((cap + 511) // 512 + 1, dtype=torch.int32, device=dev)
     gru_buf = e(min(cap, (V - 1) * HW), F)
     side = torch.cuda.Stream(dev)
-    ev_match = [torch.cuda.Event() for _ in range(V)]
+    ev = torch.cuda.Event()
+
+    def base_stride(t):                       # per-view pointer = base + i * stride (the views may be strided slices of a block)
+        return t[0].data_ptr(), (t[1].data_ptr() - t[0].data_ptr())
+    pf, pc, pd, pw, pz = (base_stride(t) for t in (feats, coords, dens, wemb, depths))
+    p_ext, p_einv, p_kpx, p_counts, p_match = ext16.data_ptr(), E_inv.data_ptr(), K_px.data_ptr(), counts.data_ptr(), match_all.data_ptr()
+    sc = (zbuf, pix, zeta, match_all[0], append, block_counts, pair_j, pair_p)
+    view0 = (feats[1], coords[1], dens[1], wemb[1], depths[1], ext16[1], E_inv[1], K_px[1])
+    a = _ptf_args(h, w, F, HW, depth_thres, pool, counts[0, 4:5], view0, sc, counts[1])
+    a.gru_out = ptr(gru_buf)
+    Ws = gru_tc.Ws
+    g = FsPtfGruArgs(M=HW, flags=int(gru_tc.prepared), pair_j=ptr(pair_j), pair_p=ptr(pair_p), feats=ptr(pool[0]), dens=ptr(pool[2]),
+                     wemb=ptr(pool[3]), v_feats=pf[0], v_dens=pd[0], v_wemb=pw[0], W_r0=ptr(Ws[0]), W_z0=ptr(Ws[1]), W_r2=ptr(Ws[2]),
+                     W_z2=ptr(Ws[3]), W_n0=ptr(Ws[4]), W_n2=ptr(Ws[5]), biases=ptr(gru_tc.biases), wscratch=ptr(gru_tc.scratch),
+                     out=ptr(gru_buf), M_dev=None)
+    st, sst = C.c_void_p(stream), C.c_void_p(side.cuda_stream)
+    ra, rg = C.byref(a), C.byref(g)
+    phys_ptr = (phys[0].data_ptr(), phys[1].data_ptr())
+    blk_ptr = C.c_void_p(blk.data_ptr())
     with torch.cuda.device(dev):
         for i in range(1, V):
             if view_ready is not None:
                 ts.wait_event(view_ready[i])
             n_up = min(cap, i * HW)
-            sc = (zbuf, pix, zeta, match_all[i - 1], append, block_counts, pair_j, pair_p)
-            view = (feats[i], coords[i], dens[i], wemb[i], depths[i], ext16[i], E_inv[i], K_px[i])
-            a = _ptf_args(h, w, F, n_up, depth_thres, pool, counts[i - 1, 4:5], view, sc, counts[i])
-            check(L.fs_ptf_match(C.byref(a), C.c_void_p(stream)), "fs_ptf_match")
-            ev_match[i].record(ts)
-            gru_tc(n_up, pair_j, pair_p, pool, feats[i], dens[i], wemb[i], stream, out=gru_buf, M_dev=counts[i, 2:3])
-            a.gru_out = ptr(gru_buf)
-            check(L.fs_ptf_pool_update(C.byref(a), C.c_void_p(stream)), "fs_ptf_pool_update")
+            crow = p_counts + 32 * i                                   # counts[i] (8 x int32)
+            a.n_upper = n_up
+            a.counts_in = p_counts + 32 * (i - 1) + 16                 # counts[i-1][4] = N
+            a.counts_out = crow
+            a.match = p_match + cap * (i - 1)
+            a.v_feats = pf[0] + i * pf[1]; a.v_coords = pc[0] + i * pc[1]; a.v_dens = pd[0] + i * pd[1]; a.v_wemb = pw[0] + i * pw[1]
+            a.v_depth = pz[0] + i * pz[1]; a.v_ext = p_ext + 64 * i; a.E_inv = p_einv + 64 * i; a.K_px = p_kpx + 36 * i
+            check(L.fs_ptf_match(ra, st), "fs_ptf_match")
+            ev.record(ts)
+            g.M = n_up; g.flags = int(gru_tc.prepared)
+            g.v_feats = a.v_feats; g.v_dens = a.v_dens; g.v_wemb = a.v_wemb; g.M_dev = crow + 8     # counts[i][2] = pairs
+            check(L.fs_ptf_gru(rg, st), "fs_ptf_gru")
+            gru_tc.prepared = True
+            check(L.fs_ptf_pool_update(ra, st), "fs_ptf_pool_update")
             # the order index only needs this step's flags and counters: side stream, under the next steps' kernels
-            side.wait_event(ev_match[i])
-            check(L.fs_ptf_pool_order(C.c_int32(min(cap, (i + 1) * HW)), C.c_void_p(ptr(counts[i])),
-                                      C.c_void_p(ptr(phys[(i - 1) & 1]) if i > 1 else None), C.c_void_p(ptr(match_all[i - 1])),
-                                      C.c_void_p(ptr(blk)), C.c_void_p(ptr(phys[i & 1])), C.c_void_p(side.cuda_stream)), "fs_ptf_pool_order")
+            side.wait_event(ev)
+            check(L.fs_ptf_pool_order(C.c_int32(min(cap, (i + 1) * HW)), C.c_void_p(crow), C.c_void_p(phys_ptr[(i - 1) & 1] if i > 1 else None),
+                                      C.c_void_p(a.match), blk_ptr, C.c_void_p(phys_ptr[i & 1]), sst), "fs_ptf_pool_order")
         ts.wait_stream(side)
         out = (e(cap, F), e(cap, 3), e(cap), e(cap), e(cap, 16), e(cap))
-        check(L.fs_ptf_pool_gather(C.c_int32(cap), C.c_void_p(ptr(counts[V - 1, 4:5])), C.c_void_p(ptr(phys[(V - 1) & 1])), C.c_int32(F),
-                                   *[C.c_void_p(ptr(t)) for t in pool], *[C.c_void_p(ptr(t)) for t in out], C.c_void_p(stream)),
-              "fs_ptf_pool_gather")
-    for t in (match_all, blk, *phys, *pool, gru_buf):
+        check(L.fs_ptf_pool_gather(C.c_int32(cap), C.c_void_p(p_counts + 32 * (V - 1) + 16), C.c_void_p(phys_ptr[(V - 1) & 1]), C.c_int32(F),
+                                   *[C.c_void_p(ptr(t)) for t in pool], *[C.c_void_p(ptr(t)) for t in out], st), "fs_ptf_pool_gather")
+    for t in (match_all, blk, *phys, *pool, gru_buf, counts):
         t.record_stream(side)
     N = int(counts[V - 1, 4])
     return (out[0][:N], out[1][:N], out[4][:N].reshape(N, 4, 4), out[5][:N])
@@ -414,7 +444,7 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
     # inference with the tensor-core GRU: the whole fold is enqueued without reading a counter back (grids are sized by
     # upper bounds, the kernels take N / M from the device counters); ONE host read at the end returns the final size
     sync_free = use_tc and (not need_grad) and timings is None and not return_debug and SYNC_FREE
-    if sync_free and POOL:
+    if sync_free and (POOL is True or (POOL == "auto" and V >= 6)):
         return _fold_pool(L, gru_tc, feats, coords, dens, wemb, depths, ext16, E_inv, K_px, h, w, F, V, HW, cap, depth_thres, counts,
                           scratch, stream, view_ready, ts, dev)
     if need_grad:

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfreesplat_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 vp = C.c_void_p
 
@@ -53,7 +53,7 @@ EXPORTS = [
     "fs_cost_volume_forward", "fs_cost_volume_backward",
     "fs_ptf_match", "fs_ptf_merge", "fs_ptf_gru_inputs", "fs_ptf_gru_update", "fs_ptf_gru_output",
     "fs_ptf_view_setup", "fs_ptf_pool_update", "fs_ptf_pool_order", "fs_ptf_pool_gather", "fs_ptf_merge_backward", "fs_ptf_gru_output_backward", "fs_ptf_gru_update_backward", "fs_ptf_gru_inputs_backward", "fs_gaussian_head_backward", "fs_depth_head_backward", "fs_backproject_backward", "fs_graph_capture_begin", "fs_graph_capture_end", "fs_graph_launch", "fs_graph_destroy",
-    "fs_ptf_gru", "fs_ptf_gru_wscratch_bytes", "fs_gaussian_head", "fs_depth_head", "fs_backproject", "fs_ply_vertices", "fs_image_u8",
+    "fs_ptf_gru", "fs_ptf_gru_wscratch_bytes", "fs_ptf_gru_bwd_data", "fs_ptf_gru_bwd_weights", "fs_gaussian_head", "fs_depth_head", "fs_backproject", "fs_ply_vertices", "fs_image_u8",
 ]
 
 _lib = None

@@ -24,6 +24,7 @@ SOURCES = [
     ("raster_render.cu", []),
     ("cost_volume.cu", []),
     ("ptf.cu", ["-fmad=false"]),
+    ("ptf_gru_bwd.cu", []),
     ("adapter.cu", []),
     ("depth_head.cu", []),
     ("c_api.cu", []),

@@ -35,6 +35,8 @@ int fs_struct_size(int32_t which) {
     case 2: return (int)sizeof(FsCostVolumeArgs);
     case 3: return (int)sizeof(FsPtfArgs);
     case 4: return (int)sizeof(FsPtfGruArgs);
+    case 12: return (int)sizeof(FsGruBwdDataArgs);
+    case 13: return (int)sizeof(FsGruBwdWeightsArgs);
     case 5: return (int)sizeof(FsAdapterArgs);
     case 6: return (int)sizeof(FsDepthHeadArgs);
     case 7: return (int)sizeof(FsBackprojectArgs);
@@ -287,6 +289,25 @@ int fs_ptf_gru(const FsPtfGruArgs* a, void* stream) {
   return launch_ptf_gru_tc(*a, reinterpret_cast<cudaStream_t>(stream));
 }
 int64_t fs_ptf_gru_wscratch_bytes(void) { return (int64_t)ptf_gru_wscratch_bytes(); }
+
+int fs_ptf_gru_bwd_data(const FsGruBwdDataArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr && a->M >= 0 && a->N >= 4 && a->N <= 192 && a->N % 4 == 0, "bad sizes (N % 4 == 0, 4 <= N <= 192)");
+  FS_REQUIRE(a->mode >= 0 && a->mode <= 2, "mode must be 0 (store), 1 (ReLU mask) or 2 (accumulate)");
+  FS_REQUIRE(a->lda >= 64 && a->lda % 4 == 0 && a->ldc >= a->N && a->ldc % 4 == 0, "bad leading dimensions");
+  FS_REQUIRE(a->M == 0 || (a->A && a->W && a->C), "NULL buffer");
+  FS_REQUIRE(a->mode != 1 || (a->N == 64 && (a->M == 0 || (a->mask && a->ldm >= 64 && a->ldm % 4 == 0))),
+             "mode 1 needs N == 64 and a mask with ldm >= 64, ldm % 4 == 0");
+  return launch_ptf_gru_bwd_data(*a, reinterpret_cast<cudaStream_t>(stream));
+}
+int fs_ptf_gru_bwd_weights(const FsGruBwdWeightsArgs* a, void* stream) {
+  FS_REQUIRE(a != nullptr && a->M >= 0 && a->nx0 >= 1 && a->nx1 >= 0, "bad sizes");
+  FS_REQUIRE(a->ldg % 16 == 0 && a->ldg <= 256 && a->nx0 + a->nx1 < a->ldg, "ldg % 16 == 0, nx0 + nx1 < ldg <= 256");
+  FS_REQUIRE(a->G != nullptr, "G is NULL");
+  FS_REQUIRE(a->M == 0 || (a->Y0 && a->X0 && a->ldy0 >= 64 && a->ldx0 >= a->nx0), "NULL buffer / bad leading dimension");
+  FS_REQUIRE(a->M == 0 || !a->Y1 || a->ldy1 >= 64, "ldy1 < 64");
+  FS_REQUIRE(a->M == 0 || ((a->X1 != nullptr) == (a->nx1 > 0) && (!a->X1 || a->ldx1 >= a->nx1)), "X1 / nx1 mismatch");
+  return launch_ptf_gru_bwd_weights(*a, reinterpret_cast<cudaStream_t>(stream));
+}
 
 // ---- CUDA graphs: a launch sequence of fs_* calls with static arguments, replayed by ONE cudaGraphLaunch ----
 int fs_graph_capture_begin(void** stream_out) {

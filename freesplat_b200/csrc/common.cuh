@@ -48,6 +48,8 @@ int launch_depth_head(const FsDepthHeadArgs& a, cudaStream_t s);    // depth_hea
 int launch_depth_head_bwd(const FsDepthHeadBwdArgs& a, cudaStream_t s);   // depth_head.cu
 int launch_gaussian_head_bwd(const FsAdapterBwdArgs& a, cudaStream_t s);  // adapter.cu
 int launch_ptf_gru_tc(const FsPtfGruArgs& a, cudaStream_t s);
+int launch_ptf_gru_bwd_data(const FsGruBwdDataArgs& a, cudaStream_t s);
+int launch_ptf_gru_bwd_weights(const FsGruBwdWeightsArgs& a, cudaStream_t s);
 size_t ptf_gru_wscratch_bytes();
 int launch_ptf_gru_inputs(int M, int F, const int* pj, const int* pp, const float* feats, const float* dens, const float* wemb,
                           const float* v_feats, const float* v_dens, const float* v_wemb, float* A1, cudaStream_t s);

@@ -14,7 +14,10 @@
 // coordinates feed the index decisions of the following views (bit-exact indices across all steps).
 //
 // HBM-bound: algorithmic bytes per step = 16 N (project) + 8 HW (z-buffer) + 344 N_out + 280 HW.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tc_tf32.cuh"
 
 namespace fs {
 
@@ -913,52 +916,11 @@ int launch_ptf_merge(const FsPtfArgs& a, cudaStream_t s) {
 //   * layer 1 computes r and z hidden layers together (N = 128); TMEM columns: D1 [0,128) -> reused by D3 [0,64), D4 [64,128);
 //     D2r [128,192), D2z [192,256).
 namespace gru {
+using namespace tc;
 
 constexpr int kF = 64, kE = 24, kK1 = 2 * kF + 2 * kE /*176*/, kK3 = 2 * kF + kE /*152*/, kK3p = 160;
-constexpr int kRound = 16;                                   // K columns per round = 2 UMMA k-steps
 constexpr int kR1 = kK1 / kRound /*11*/, kR2 = kF / kRound /*4*/, kR3 = kK3p / kRound /*10*/, kR4 = kF / kRound /*4*/;
 constexpr int kATile = 2 * (128 / 8) * 256;                  // one A round (128 rows x 16 cols): 8 KB per hi / lo
-__host__ __device__ constexpr int bTile(int n) { return 2 * (n / 8) * 256; }     // one B round (n rows x 16 cols)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
-// activation-side tf32 split by TRUNCATION: hi = top 19 bits of x, lo = top 19 bits of (x - hi) (the subtraction is exact).
-// cvt.rna.tf32.f32 is three instructions on sm_100a (FSETP + IADD + LOP3): the rounded split cost 7 instructions per element
-// and ~15 % of the cost-volume / GRU kernels; the truncated one costs 3.  x = hi + lo holds to 2^-20 |x| (2^-22 rounded):
-// the dropped lo*lo term and the split error stay ~1e-6 relative, inside the 1e-4 budget.  Weights keep the rounded split.
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
-}
-__host__ __device__ constexpr uint32_t idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
-__device__ __forceinline__ void mma_tf32(uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(da),
-               "l"(db), "r"(id), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile("{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(bar),
-               "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
-}
-// byte offset of (row, k) inside one operand round (k in 0..15)
-__host__ __device__ inline uint32_t op_off(int row, int k, int rows) {
-  return (uint32_t)((k >> 3) * ((rows / 8) * 256) + (row >> 3) * 256 + ((k >> 2) & 1) * 128 + (row & 7) * 16 + (k & 3) * 4);
-}
 
 // ---- weight preparation: every B round as [hi tile | lo tile] in the canonical layout, rounds concatenated ----
 // order: L1 (N=128: rows 0..63 = mlp_r[0], 64..127 = mlp_z[0]; 11 rounds) | L2r (N=64, 4) | L2z (4) | L3 (N=64, 10, K padded) | L4 (4)
@@ -981,21 +943,19 @@ __global__ void ptf_gru_prep_kernel(const float* Wr0, const float* Wz0, const fl
   if (t < 64 * kK3p) { const int n = t / kK3p, k = t - n * kK3p; put(kOffL3, 64, k / kRound, n, k % kRound, k < kK3 ? Wn0[n * kK3 + k] : 0.f); }
 }
 
+// kT = row tiles of 128 pairs per CTA.  kT = 2 (256 pairs, all 512 TMEM columns, one CTA per SM): every weight round is copied
+// from L2 once and multiplied into BOTH tiles -- half the L2 -> shared weight traffic (352 KB per 128 pairs at kT = 1, ~0.6 GB
+// per fold step) and half the block barriers per pair.
+template <int kT>
 struct __align__(128) Smem {
-  unsigned char A[2][2][kATile];        // [buffer][hi|lo]   (a second A tile for layer 2's z half lives in Az)
-  unsigned char Az[2][2][kATile];
+  unsigned char A[kT][2][2][kATile];    // [tile][buffer][hi|lo]   (a second A tile for layer 2's z half lives in Az)
+  unsigned char Az[kT][2][2][kATile];
   unsigned char B[2][2 * bTile(128)];   // [buffer][hi tile | lo tile]  (layer 2: r round then z round, 64 rows each)
   float b_r0[kF], b_z0[kF], b_r2[kF], b_z2[kF], b_n0[kF], b_n2[kF];
   unsigned long long bar_free[2], bar_done;
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void store_a4(unsigned char* hi, unsigned char* lo, int row, int k0, float v0, float v1, float v2, float v3) {
-  uint4 h, l;
-  split_tf32(v0, h.x, l.x); split_tf32(v1, h.y, l.y); split_tf32(v2, h.z, l.z); split_tf32(v3, h.w, l.w);
-  const uint32_t off = op_off(row, k0, 128);
-  *reinterpret_cast<uint4*>(hi + off) = h; *reinterpret_cast<uint4*>(lo + off) = l;
-}
 // gates through MUFU.EX2 / MUFU.RCP (|rel err| ~ 1e-6 each, far inside the 1e-4 budget of the latents; the library expf +
 // IEEE division + tanhf versions were ~35 % of the kernel's instructions)
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -1006,18 +966,26 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return (1.0f - e) * rcpa(1.0f + e);
 }
 
-__global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* __restrict__ M_dev, const int* __restrict__ pair_j, const int* __restrict__ pair_p,
+template <int kT>
+__global__ void __launch_bounds__(128 * kT) ptf_gru_tc_kernel(int M_host, const int* __restrict__ M_dev, const int* __restrict__ pair_j, const int* __restrict__ pair_p,
                                                          const float* __restrict__ feats, const float* __restrict__ dens,
                                                          const float* __restrict__ wemb, const float* __restrict__ v_feats,
                                                          const float* __restrict__ v_dens, const float* __restrict__ v_wemb,
                                                          const unsigned char* __restrict__ W, const float* __restrict__ biases /*6 x 64*/,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, float* __restrict__ save /*6 x [M_host,64] or NULL*/) {
   extern __shared__ __align__(128) unsigned char gru_smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(gru_smem_raw);
+  Smem<kT>& sm = *reinterpret_cast<Smem<kT>*>(gru_smem_raw);
+  constexpr int kNT = 128 * kT;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = tid >> 7, row = tid & 127;             // this thread's pair = row `row` of row tile `tile`
   const int M = M_dev ? min(*M_dev, M_host) : M_host;        // M_host is only the grid's upper bound when M_dev is given
-  if ((int)blockIdx.x * 128 >= M) return;                  // CTA-uniform, before any barrier / TMEM allocation
-  const int m = blockIdx.x * 128 + tid;
+  if ((int)blockIdx.x * kNT >= M) return;                  // CTA-uniform, before any barrier / TMEM allocation
+  const int m = blockIdx.x * kNT + tid;
+  // training: the six intermediate activations the backward needs, [Hr | Hz | r_lin | z_lin | Hn | q_lin] as six [M,64] matrices
+  // (fs_ptf_gru_backward reads them instead of recomputing the six layers)
+  auto keep = [&](int which, int col, float v0, float v1, float v2, float v3) {
+    *reinterpret_cast<float4*>(save + ((size_t)which * M_host + m) * kF + col) = make_float4(v0, v1, v2, v3);
+  };
   const bool active = m < M;
   if (tid < kF) { sm.b_r0[tid] = biases[tid]; sm.b_z0[tid] = biases[64 + tid]; sm.b_r2[tid] = biases[128 + tid]; sm.b_z2[tid] = biases[192 + tid];
                   sm.b_n0[tid] = biases[256 + tid]; sm.b_n2[tid] = biases[320 + tid]; }
@@ -1028,14 +996,15 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(256u * kT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
-  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  // a warp reaches the 32 TMEM lanes of its quarter (warp % 4); tile t owns columns [256 t, 256 t + 256)
+  const uint32_t t_row = tmem + 256u * (uint32_t)tile + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t bar_free[2] = {smem_u32(&sm.bar_free[0]), smem_u32(&sm.bar_free[1])};
   const uint32_t bar_done = smem_u32(&sm.bar_done);
   uint32_t ph_free[2] = {0u, 0u}, ph_done = 0u;
@@ -1067,7 +1036,7 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
   // round and completes underneath it (ncu r1f: the synchronous LDG -> STS copy was the long-scoreboard stall of this kernel)
   auto copy_b = [&](int buf, const unsigned char* src, int bytes) {
     const uint32_t d0 = smem_u32(sm.B[buf]);
-    for (int k = tid; k < bytes / 16; k += 128)
+    for (int k = tid; k < bytes / 16; k += kNT)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)k * 16u), "l"(src + (size_t)k * 16) : "memory");
   };
   auto publish = [&]() {
@@ -1117,18 +1086,22 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
       float v[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) v[e] = a1_col(c + e);
-      store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, v[0], v[1], v[2], v[3]);
+      store_a4(sm.A[tile][buf][0], sm.A[tile][buf][1], row, 4 * q, v[0], v[1], v[2], v[3]);
     }
     publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t aH = smem_u32(sm.A[buf][0]), aL = smem_u32(sm.A[buf][1]), bH = smem_u32(sm.B[buf]), bL = bH + bTile(128);
+      const uint32_t bH = smem_u32(sm.B[buf]), bL = bH + bTile(128);
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const uint32_t ao = s * (128 / 8) * 256, bo = s * (128 / 8) * 256;
-        mma_tf32(tmem, make_desc(aL + ao), make_desc(bH + bo), idesc(128), (r > 0 || s > 0) ? 1u : 0u);
-        mma_tf32(tmem, make_desc(aH + ao), make_desc(bL + bo), idesc(128), 1u);
-        mma_tf32(tmem, make_desc(aH + ao), make_desc(bH + bo), idesc(128), 1u);
+      for (int t = 0; t < kT; t++) {
+        const uint32_t aH = smem_u32(sm.A[t][buf][0]), aL = smem_u32(sm.A[t][buf][1]), td = tmem + 256u * t;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const uint32_t ao = s * (128 / 8) * 256, bo = s * (128 / 8) * 256;
+          mma_tf32(td, make_desc(aL + ao), make_desc(bH + bo), idesc(128), (r > 0 || s > 0) ? 1u : 0u);
+          mma_tf32(td, make_desc(aH + ao), make_desc(bL + bo), idesc(128), 1u);
+          mma_tf32(td, make_desc(aH + ao), make_desc(bH + bo), idesc(128), 1u);
+        }
       }
       commit(bar_free[buf]);
       if (r == kR1 - 1) commit(bar_done);
@@ -1147,7 +1120,7 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
       const unsigned char* s2 = W + kOffL2z + (size_t)r * 2 * bTile(64);
       const uint32_t d0 = smem_u32(sm.B[buf]);
       const int n16 = 2 * bTile(64) / 16;
-      for (int k = tid; k < n16; k += 128) {
+      for (int k = tid; k < n16; k += kNT) {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)k * 16u), "l"(s1 + (size_t)k * 16) : "memory");
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)(n16 + k) * 16u), "l"(s2 + (size_t)k * 16) : "memory");
       }
@@ -1163,24 +1136,29 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
         a[e] = fmaxf(hr[4 * q + e] + sm.b_r0[r * kRound + 4 * q + e], 0.f);
         b[e] = fmaxf(hz[4 * q + e] + sm.b_z0[r * kRound + 4 * q + e], 0.f);
       }
-      store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, a[0], a[1], a[2], a[3]);
-      store_a4(sm.Az[buf][0], sm.Az[buf][1], tid, 4 * q, b[0], b[1], b[2], b[3]);
+      store_a4(sm.A[tile][buf][0], sm.A[tile][buf][1], row, 4 * q, a[0], a[1], a[2], a[3]);
+      store_a4(sm.Az[tile][buf][0], sm.Az[tile][buf][1], row, 4 * q, b[0], b[1], b[2], b[3]);
+      if (save && active) { keep(0, r * kRound + 4 * q, a[0], a[1], a[2], a[3]); keep(1, r * kRound + 4 * q, b[0], b[1], b[2], b[3]); }
     }
     publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t bR = smem_u32(sm.B[buf]), bZ = bR + 2 * bTile(64);
-      const uint32_t arH = smem_u32(sm.A[buf][0]), arL = smem_u32(sm.A[buf][1]), azH = smem_u32(sm.Az[buf][0]), azL = smem_u32(sm.Az[buf][1]);
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const uint32_t ao = s * (128 / 8) * 256, bo = s * (64 / 8) * 256;
-        const uint32_t acc = (r > 0 || s > 0) ? 1u : 0u;
-        mma_tf32(tmem + 128u, make_desc(arL + ao), make_desc(bR + bo), idesc(64), acc);
-        mma_tf32(tmem + 128u, make_desc(arH + ao), make_desc(bR + bTile(64) + bo), idesc(64), 1u);
-        mma_tf32(tmem + 128u, make_desc(arH + ao), make_desc(bR + bo), idesc(64), 1u);
-        mma_tf32(tmem + 192u, make_desc(azL + ao), make_desc(bZ + bo), idesc(64), acc);
-        mma_tf32(tmem + 192u, make_desc(azH + ao), make_desc(bZ + bTile(64) + bo), idesc(64), 1u);
-        mma_tf32(tmem + 192u, make_desc(azH + ao), make_desc(bZ + bo), idesc(64), 1u);
+      for (int t = 0; t < kT; t++) {
+        const uint32_t arH = smem_u32(sm.A[t][buf][0]), arL = smem_u32(sm.A[t][buf][1]), azH = smem_u32(sm.Az[t][buf][0]),
+                       azL = smem_u32(sm.Az[t][buf][1]), td = tmem + 256u * t;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const uint32_t ao = s * (128 / 8) * 256, bo = s * (64 / 8) * 256;
+          const uint32_t acc = (r > 0 || s > 0) ? 1u : 0u;
+          mma_tf32(td + 128u, make_desc(arL + ao), make_desc(bR + bo), idesc(64), acc);
+          mma_tf32(td + 128u, make_desc(arH + ao), make_desc(bR + bTile(64) + bo), idesc(64), 1u);
+          mma_tf32(td + 128u, make_desc(arH + ao), make_desc(bR + bo), idesc(64), 1u);
+          mma_tf32(td + 192u, make_desc(azL + ao), make_desc(bZ + bo), idesc(64), acc);
+          mma_tf32(td + 192u, make_desc(azH + ao), make_desc(bZ + bTile(64) + bo), idesc(64), 1u);
+          mma_tf32(td + 192u, make_desc(azH + ao), make_desc(bZ + bo), idesc(64), 1u);
+        }
       }
       commit(bar_free[buf]);
       if (r == kR2 - 1) commit(bar_done);
@@ -1208,18 +1186,26 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
         else if (c < kK3) v[e] = e_in[c - 2 * kF];
         else v[e] = 0.f;
       }
-      store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, v[0], v[1], v[2], v[3]);
+      store_a4(sm.A[tile][buf][0], sm.A[tile][buf][1], row, 4 * q, v[0], v[1], v[2], v[3]);
+      if (r < kR2 && save && active) {
+        const int c = r * kRound + 4 * q;
+        keep(2, c, rg[4 * q] + sm.b_r2[c], rg[4 * q + 1] + sm.b_r2[c + 1], rg[4 * q + 2] + sm.b_r2[c + 2], rg[4 * q + 3] + sm.b_r2[c + 3]);
+      }
     }
     publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t aH = smem_u32(sm.A[buf][0]), aL = smem_u32(sm.A[buf][1]), bH = smem_u32(sm.B[buf]), bL = bH + bTile(64);
+      const uint32_t bH = smem_u32(sm.B[buf]), bL = bH + bTile(64);
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const uint32_t ao = s * (128 / 8) * 256, bo = s * (64 / 8) * 256;
-        mma_tf32(tmem, make_desc(aL + ao), make_desc(bH + bo), idesc(64), (r > 0 || s > 0) ? 1u : 0u);
-        mma_tf32(tmem, make_desc(aH + ao), make_desc(bL + bo), idesc(64), 1u);
-        mma_tf32(tmem, make_desc(aH + ao), make_desc(bH + bo), idesc(64), 1u);
+      for (int t = 0; t < kT; t++) {
+        const uint32_t aH = smem_u32(sm.A[t][buf][0]), aL = smem_u32(sm.A[t][buf][1]), td = tmem + 256u * t;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const uint32_t ao = s * (128 / 8) * 256, bo = s * (64 / 8) * 256;
+          mma_tf32(td, make_desc(aL + ao), make_desc(bH + bo), idesc(64), (r > 0 || s > 0) ? 1u : 0u);
+          mma_tf32(td, make_desc(aH + ao), make_desc(bL + bo), idesc(64), 1u);
+          mma_tf32(td, make_desc(aH + ao), make_desc(bH + bo), idesc(64), 1u);
+        }
       }
       commit(bar_free[buf]);
       if (r == kR3 - 1) commit(bar_done);
@@ -1237,20 +1223,27 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
     float hn[16];
     tmem_ld16(t_row + (uint32_t)(r * kRound), hn);
 #pragma unroll
-    for (int q = 0; q < 4; q++)
-      store_a4(sm.A[buf][0], sm.A[buf][1], tid, 4 * q, fmaxf(hn[4 * q] + sm.b_n0[r * kRound + 4 * q], 0.f),
-               fmaxf(hn[4 * q + 1] + sm.b_n0[r * kRound + 4 * q + 1], 0.f), fmaxf(hn[4 * q + 2] + sm.b_n0[r * kRound + 4 * q + 2], 0.f),
-               fmaxf(hn[4 * q + 3] + sm.b_n0[r * kRound + 4 * q + 3], 0.f));
+    for (int q = 0; q < 4; q++) {
+      const int c = r * kRound + 4 * q;
+      const float v0 = fmaxf(hn[4 * q] + sm.b_n0[c], 0.f), v1 = fmaxf(hn[4 * q + 1] + sm.b_n0[c + 1], 0.f),
+                  v2 = fmaxf(hn[4 * q + 2] + sm.b_n0[c + 2], 0.f), v3 = fmaxf(hn[4 * q + 3] + sm.b_n0[c + 3], 0.f);
+      store_a4(sm.A[tile][buf][0], sm.A[tile][buf][1], row, 4 * q, v0, v1, v2, v3);
+      if (save && active) keep(4, c, v0, v1, v2, v3);
+    }
     publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t aH = smem_u32(sm.A[buf][0]), aL = smem_u32(sm.A[buf][1]), bH = smem_u32(sm.B[buf]), bL = bH + bTile(64);
+      const uint32_t bH = smem_u32(sm.B[buf]), bL = bH + bTile(64);
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const uint32_t ao = s * (128 / 8) * 256, bo = s * (64 / 8) * 256;
-        mma_tf32(tmem + 64u, make_desc(aL + ao), make_desc(bH + bo), idesc(64), (r > 0 || s > 0) ? 1u : 0u);
-        mma_tf32(tmem + 64u, make_desc(aH + ao), make_desc(bL + bo), idesc(64), 1u);
-        mma_tf32(tmem + 64u, make_desc(aH + ao), make_desc(bH + bo), idesc(64), 1u);
+      for (int t = 0; t < kT; t++) {
+        const uint32_t aH = smem_u32(sm.A[t][buf][0]), aL = smem_u32(sm.A[t][buf][1]), td = tmem + 256u * t;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const uint32_t ao = s * (128 / 8) * 256, bo = s * (64 / 8) * 256;
+          mma_tf32(td + 64u, make_desc(aL + ao), make_desc(bH + bo), idesc(64), (r > 0 || s > 0) ? 1u : 0u);
+          mma_tf32(td + 64u, make_desc(aH + ao), make_desc(bL + bo), idesc(64), 1u);
+          mma_tf32(td + 64u, make_desc(aH + ao), make_desc(bH + bo), idesc(64), 1u);
+        }
       }
       commit(bar_free[buf]);
       if (r == kR4 - 1) commit(bar_done);
@@ -1277,12 +1270,17 @@ __global__ void __launch_bounds__(128) ptf_gru_tc_kernel(int M_host, const int* 
           o[e] = (1.0f - z) * h[c] + z * tanh_fast(ql[4 * q + e] + sm.b_n2[c]);
         }
         op[q] = make_float4(o[0], o[1], o[2], o[3]);
+        if (save) {
+          const int c = r * kRound + 4 * q;
+          keep(3, c, zl[4 * q] + sm.b_z2[c], zl[4 * q + 1] + sm.b_z2[c + 1], zl[4 * q + 2] + sm.b_z2[c + 2], zl[4 * q + 3] + sm.b_z2[c + 3]);
+          keep(5, c, ql[4 * q] + sm.b_n2[c], ql[4 * q + 1] + sm.b_n2[c + 1], ql[4 * q + 2] + sm.b_n2[c + 2], ql[4 * q + 3] + sm.b_n2[c + 3]);
+        }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u * kT) : "memory");
 }
 
 }  // namespace gru
@@ -1294,11 +1292,24 @@ int launch_ptf_gru_tc(const FsPtfGruArgs& a, cudaStream_t s) {
     gru::ptf_gru_prep_kernel<<<(128 * gru::kK1 + 255) / 256, 256, 0, s>>>(a.W_r0, a.W_z0, a.W_r2, a.W_z2, a.W_n0, a.W_n2, a.wscratch);
     if ((rc = check_cuda(cudaGetLastError(), "ptf_gru_prep_kernel"))) return rc;
   }
-  const size_t smem = sizeof(gru::Smem) + 128;
-  if ((rc = check_cuda(cudaFuncSetAttribute(gru::ptf_gru_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                       "cudaFuncSetAttribute(ptf_gru_tc_kernel)"))) return rc;
-  gru::ptf_gru_tc_kernel<<<(a.M + 127) / 128, 128, smem, s>>>(a.M, a.M_dev, a.pair_j, a.pair_p, a.feats, a.dens, a.wemb, a.v_feats, a.v_dens, a.v_wemb,
-                                                            a.wscratch, a.biases, a.out);
+  // 128 pairs per CTA, two CTAs per SM.  FS_GRU_TILES=2 selects the 256-pair variant (two row tiles share every weight round,
+  // one CTA per SM): bit-identical, but 4 % SLOWER on B200 (4.55 vs 4.37 ms, 10-view fold) -- the kernel is bound by the per-thread
+  // A builds, not by the L2 weight stream, and two independent CTAs overlap those better than one wide one.
+  static int tiles = -1;
+  if (tiles < 0) { const char* e = getenv("FS_GRU_TILES"); tiles = (e && e[0] == '2') ? 2 : 1; }
+  if (tiles == 2) {
+    const size_t smem = sizeof(gru::Smem<2>) + 128;
+    if ((rc = check_cuda(cudaFuncSetAttribute(gru::ptf_gru_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                         "cudaFuncSetAttribute(ptf_gru_tc_kernel<2>)"))) return rc;
+    gru::ptf_gru_tc_kernel<2><<<(a.M + 255) / 256, 256, smem, s>>>(a.M, a.M_dev, a.pair_j, a.pair_p, a.feats, a.dens, a.wemb, a.v_feats, a.v_dens,
+                                                                    a.v_wemb, a.wscratch, a.biases, a.out, a.save);
+  } else {
+    const size_t smem = sizeof(gru::Smem<1>) + 128;
+    if ((rc = check_cuda(cudaFuncSetAttribute(gru::ptf_gru_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                         "cudaFuncSetAttribute(ptf_gru_tc_kernel<1>)"))) return rc;
+    gru::ptf_gru_tc_kernel<1><<<(a.M + 127) / 128, 128, smem, s>>>(a.M, a.M_dev, a.pair_j, a.pair_p, a.feats, a.dens, a.wemb, a.v_feats, a.v_dens,
+                                                                    a.v_wemb, a.wscratch, a.biases, a.out, a.save);
+  }
   return check_cuda(cudaGetLastError(), "ptf_gru_tc_kernel");
 }
 

@@ -78,7 +78,19 @@ class FsPtfGruArgs(C.Structure):
                 ("feats", C.c_void_p), ("dens", C.c_void_p), ("wemb", C.c_void_p),
                 ("v_feats", C.c_void_p), ("v_dens", C.c_void_p), ("v_wemb", C.c_void_p),
                 ("W_r0", C.c_void_p), ("W_z0", C.c_void_p), ("W_r2", C.c_void_p), ("W_z2", C.c_void_p), ("W_n0", C.c_void_p),
-                ("W_n2", C.c_void_p), ("biases", C.c_void_p), ("wscratch", C.c_void_p), ("out", C.c_void_p), ("M_dev", C.c_void_p)]
+                ("W_n2", C.c_void_p), ("biases", C.c_void_p), ("wscratch", C.c_void_p), ("out", C.c_void_p), ("M_dev", C.c_void_p),
+                ("save", C.c_void_p)]
+
+
+class FsGruBwdDataArgs(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("mode", C.c_int32), ("lda", C.c_int32), ("ldc", C.c_int32), ("ldm", C.c_int32),
+                ("A", C.c_void_p), ("W", C.c_void_p), ("mask", C.c_void_p), ("C", C.c_void_p)]
+
+
+class FsGruBwdWeightsArgs(C.Structure):
+    _fields_ = [("M", C.c_int32), ("ldy0", C.c_int32), ("ldy1", C.c_int32), ("ldx0", C.c_int32), ("nx0", C.c_int32), ("ldx1", C.c_int32),
+                ("nx1", C.c_int32), ("ldg", C.c_int32), ("Y0", C.c_void_p), ("Y1", C.c_void_p), ("X0", C.c_void_p), ("X1", C.c_void_p),
+                ("G", C.c_void_p)]
 
 
 # "tc": the whole GRU on the tensor cores (fs_ptf_gru, 3xTF32) ; "cublas": glue kernels + nn.Linear GEMMs
@@ -113,7 +125,7 @@ class _GruTc:
         self.prepared = False
         self.dev = dev
 
-    def __call__(self, M, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream, out=None, M_dev=None):
+    def __call__(self, M, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream, out=None, M_dev=None, save=None):
         L = _lib.lib()
         Ws = self.Ws
         if out is None:
@@ -121,7 +133,7 @@ class _GruTc:
         a = FsPtfGruArgs(M=M, flags=int(self.prepared), pair_j=ptr(pair_j), pair_p=ptr(pair_p), feats=ptr(state[0]), dens=ptr(state[2]),
                          wemb=ptr(state[3]), v_feats=ptr(view_feats), v_dens=ptr(view_dens), v_wemb=ptr(view_wemb),
                          W_r0=ptr(Ws[0]), W_z0=ptr(Ws[1]), W_r2=ptr(Ws[2]), W_z2=ptr(Ws[3]), W_n0=ptr(Ws[4]), W_n2=ptr(Ws[5]),
-                         biases=ptr(self.biases), wscratch=ptr(self.scratch), out=ptr(out), M_dev=ptr(M_dev))
+                         biases=ptr(self.biases), wscratch=ptr(self.scratch), out=ptr(out), M_dev=ptr(M_dev), save=ptr(save))
         check(L.fs_ptf_gru(C.byref(a), C.c_void_p(stream)), "fs_ptf_gru")
         self.prepared = True
         return out
@@ -150,30 +162,108 @@ def _gru_fused(gru, M, F, pair_j, pair_p, state, view_feats, view_dens, view_wem
     return out
 
 
-class _GruTrain(torch.autograd.Function):
-    """GRU.forward (networks.py:201-214) of the matched pairs for the TRAINING fold.
+# "tc": the 12 matrix products of the GRU backward on the tensor cores (fs_ptf_gru_bwd_data / _weights); "cublas": the
+# round-2a path (recompute + 18 torch fp32 GEMMs) kept for A/B runs
+GRU_BWD = os.environ.get("FREESPLAT_B200_PTF_GRU_BWD", "tc")
 
-    forward : the fused tensor-core kernel (fs_ptf_gru, 3xTF32) -- nothing but the inputs is kept for backward;
-    backward: recompute + chain rule by hand: the element-wise work (gathers, positional encodings and their derivatives,
-              gates, scatter of the input gradients incl. atomics for tied pixels) runs in six glue kernels of
-              libfreesplat_b200.so (three forward ones re-used, fs_ptf_gru_{output,update,inputs}_backward), the 18 matrix
-              products in between (6 recomputed layers, 6 data gradients, 6 weight gradients) are plain fp32 GEMMs.
-    Replaces ~60 eager element-wise torch launches per fold step (13.9 -> see profiles/ ms for the 3-view fold)."""
+
+def _bwd_data(L, st, A, W, N, out, mode=0, mask=None):
+    """out[M,N] (op)= A[M,64] @ W[64,N] on the tensor cores (fs_ptf_gru_bwd_data)."""
+    a = FsGruBwdDataArgs(M=A.shape[0], N=N, mode=mode, lda=A.stride(0), ldc=out.stride(0), ldm=0 if mask is None else mask.stride(0),
+                         A=ptr(A), W=ptr(W), mask=ptr(mask), C=ptr(out))
+    check(L.fs_ptf_gru_bwd_data(C.byref(a), st), "fs_ptf_gru_bwd_data")
+    return out
+
+
+def _bwd_weights(L, st, Y0, Y1, X0, X1, G):
+    """G[128,ldg] = [Y0 | Y1]^T @ [X0 | X1 | 1] over the pairs (fs_ptf_gru_bwd_weights)."""
+    a = FsGruBwdWeightsArgs(M=Y0.shape[0], ldy0=Y0.stride(0), ldy1=0 if Y1 is None else Y1.stride(0), ldx0=X0.stride(0), nx0=X0.shape[1],
+                            ldx1=0 if X1 is None else X1.stride(0), nx1=0 if X1 is None else X1.shape[1], ldg=G.shape[1],
+                            Y0=ptr(Y0), Y1=ptr(Y1), X0=ptr(X0), X1=ptr(X1), G=ptr(G))
+    check(L.fs_ptf_gru_bwd_weights(C.byref(a), st), "fs_ptf_gru_bwd_weights")
+    return G
+
+
+class _GruTrain(torch.autograd.Function):
+    """GRU.forward (networks.py:201-214) of the matched pairs for the TRAINING fold, all of it in libfreesplat_b200.so.
+
+    forward : the fused tensor-core kernel (fs_ptf_gru, 3xTF32), which also leaves the six intermediate activations
+              [Hr | Hz | r_lin | z_lin | Hn | q_lin] (1.5 KB per pair) for the backward.
+    backward: chain rule by hand.  Element-wise work (gathers, positional encodings and their derivatives, gates, scatter of
+              the input gradients incl. atomics for tied pixels) = the glue kernels fs_ptf_gru_{inputs,update} and
+              fs_ptf_gru_{output,update,inputs}_backward; the six data-gradient products = fs_ptf_gru_bwd_data (ReLU masks and
+              the accumulation into dA1 in its epilogue); the six weight gradients and six bias gradients = three
+              fs_ptf_gru_bwd_weights launches (two layers stacked on the 128 MMA rows, a column of ones for the biases).
+              No torch matmul / cuBLAS, no recomputation of the layers.
+    FREESPLAT_B200_PTF_GRU_BWD=cublas selects the earlier recompute + 18 fp32 GEMM path (A/B timing, cross-check in the tests)."""
 
     @staticmethod
     def forward(ctx, feats, dens, wemb, v_feats, v_dens, v_wemb, pair_j, pair_p, M, gru_tc, *params):
         dev = feats.device
         stream = torch.cuda.current_stream(dev).cuda_stream
         state = (feats.contiguous(), None, dens.contiguous(), wemb.contiguous())
+        ctx.tc = GRU_BWD == "tc"
+        acts = torch.empty((6, max(M, 1), 64), dtype=torch.float32, device=dev) if ctx.tc else None
         with torch.cuda.device(dev):
-            out = gru_tc(M, pair_j, pair_p, state, v_feats.contiguous(), v_dens.contiguous(), v_wemb.contiguous(), stream)
+            out = gru_tc(M, pair_j, pair_p, state, v_feats.contiguous(), v_dens.contiguous(), v_wemb.contiguous(), stream, save=acts)
         ctx.M = M
         ctx.sizes = (feats.shape[0], v_feats.shape[0])
+        ctx.acts = acts
         ctx.save_for_backward(state[0], state[2], state[3], v_feats, v_dens, v_wemb, pair_j[:M].clone(), pair_p[:M].clone(), *params)
         return out
 
     @staticmethod
     def backward(ctx, g):
+        if not ctx.tc:
+            return _GruTrain._backward_cublas(ctx, g)
+        L = _lib.lib()
+        feats, dens, wemb, v_feats, v_dens, v_wemb, pj, pp = ctx.saved_tensors[:8]
+        (Wr0, br0, Wr2, br2, Wz0, bz0, Wz2, bz2, Wn0, bn0, Wn2, bn2) = ctx.saved_tensors[8:]
+        M, F = ctx.M, feats.shape[1]
+        N, HW = ctx.sizes
+        dev = feats.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        w = lambda t: t.detach().float().contiguous()
+        Hr, Hz, r_lin, z_lin, Hn, q_lin = ctx.acts.unbind(0)
+        g = g.contiguous()
+        K1, K3 = 2 * F + 48, 2 * F + 24
+        with torch.cuda.device(dev), torch.no_grad():
+            A1, U = e(M, K1), e(M, K3)
+            check(L.fs_ptf_gru_inputs(C.c_int32(M), C.c_int32(F), vp(pj), vp(pp), vp(feats), vp(dens), vp(wemb), vp(v_feats), vp(v_dens),
+                                      vp(v_wemb), vp(A1), st), "fs_ptf_gru_inputs")
+            check(L.fs_ptf_gru_update(C.c_int32(M), C.c_int32(F), vp(A1), vp(r_lin), vp(U), st), "fs_ptf_gru_update")
+            dHn, dHr, dHz = e(M, F), e(M, F), e(M, F)
+            dz_c, dq_c, dA1 = e(M, F), e(M, F), e(M, K1)
+            check(L.fs_ptf_gru_output_backward(C.c_int32(M), C.c_int32(F), vp(A1), vp(z_lin), vp(q_lin), vp(g), vp(dz_c), vp(dq_c),
+                                               vp(dA1), st), "fs_ptf_gru_output_backward")
+            _bwd_data(L, st, dq_c, w(Wn2), F, dHn, mode=1, mask=Hn)
+            dU = _bwd_data(L, st, dHn, w(Wn0), K3, e(M, K3))
+            dr_c = e(M, F)
+            check(L.fs_ptf_gru_update_backward(C.c_int32(M), C.c_int32(F), vp(A1), vp(r_lin), vp(dU), vp(dr_c), vp(dA1), st),
+                  "fs_ptf_gru_update_backward")
+            _bwd_data(L, st, dz_c, w(Wz2), F, dHz, mode=1, mask=Hz)
+            _bwd_data(L, st, dr_c, w(Wr2), F, dHr, mode=1, mask=Hr)
+            _bwd_data(L, st, dHz, w(Wz0), K1, dA1, mode=2)
+            _bwd_data(L, st, dHr, w(Wr0), K1, dA1, mode=2)
+            Gn = _bwd_weights(L, st, dq_c, dHn, Hn, U, e(128, 224))          # [Hn (64) | U (152) | 1]
+            G2 = _bwd_weights(L, st, dr_c, dz_c, Hr, Hz, e(128, 144))        # [Hr (64) | Hz (64) | 1]
+            G0 = _bwd_weights(L, st, dHr, dHz, A1, None, e(128, 192))        # [A1 (176) | 1]
+            gWn2, gbn2, gWn0, gbn0 = Gn[:F, :F], Gn[:F, F + K3], Gn[F:, F:F + K3], Gn[F:, F + K3]
+            gWr2, gbr2, gWz2, gbz2 = G2[:F, :F], G2[:F, 2 * F], G2[F:, F:2 * F], G2[F:, 2 * F]
+            gWr0, gbr0, gWz0, gbz0 = G0[:F, :K1], G0[:F, K1], G0[F:, :K1], G0[F:, K1]
+            d_feats, d_dens, d_wemb = z(N, F), z(N), z(N)
+            dv_feats, dv_dens, dv_wemb = z(HW, F), z(HW), z(HW)
+            check(L.fs_ptf_gru_inputs_backward(C.c_int32(M), C.c_int32(F), vp(pj), vp(pp), vp(dens), vp(wemb), vp(v_dens), vp(v_wemb), vp(dA1),
+                                               vp(d_feats), vp(d_dens), vp(d_wemb), vp(dv_feats), vp(dv_dens), vp(dv_wemb), st),
+                  "fs_ptf_gru_inputs_backward")
+        return (d_feats, d_dens, d_wemb, dv_feats, dv_dens, dv_wemb, None, None, None, None,
+                gWr0, gbr0, gWr2, gbr2, gWz0, gbz0, gWz2, gbz2, gWn0, gbn0, gWn2, gbn2)
+
+    @staticmethod
+    def _backward_cublas(ctx, g):
         L = _lib.lib()
         feats, dens, wemb, v_feats, v_dens, v_wemb, pj, pp = ctx.saved_tensors[:8]
         (Wr0, br0, Wr2, br2, Wz0, bz0, Wz2, bz2, Wn0, bn0, Wn2, bn2) = ctx.saved_tensors[8:]
@@ -447,8 +537,11 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
     if sync_free and (POOL is True or (POOL == "auto" and V >= 6)):
         return _fold_pool(L, gru_tc, feats, coords, dens, wemb, depths, ext16, E_inv, K_px, h, w, F, V, HW, cap, depth_thres, counts,
                           scratch, stream, view_ready, ts, dev)
+    # one unbind per input: the per-view rows are used by several consumers (GRU, merge) -- with feats[i] every use would get its
+    # own SelectBackward, i.e. a zero-filled [V,HW,F] gradient and a full-size add per use (1.7 ms of the 3-view training fold)
+    fv, xv, dv, wv, zv = (t.unbind(0) for t in (feats, coords, dens, wemb, depths))
     if need_grad:
-        state = (feats[0], coords[0], dens[0], wemb[0], ext16[0][None].expand(HW, 16).contiguous(), depths[0])
+        state = (fv[0], xv[0], dv[0], wv[0], ext16[0][None].expand(HW, 16).contiguous(), zv[0])
         nxt = None
     else:
         cur, nxt = _State(cap, F, dev), _State(cap, F, dev)
@@ -482,7 +575,7 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
             if view_ready is not None:
                 ts.wait_event(view_ready[i])
             cin = counts[i - 1, 4:5]                      # N of the current state, on the device
-            view = (feats[i], coords[i], dens[i], wemb[i], depths[i], ext16[i], E_inv[i], K_px[i])
+            view = (fv[i], xv[i], dv[i], wv[i], zv[i], ext16[i], E_inv[i], K_px[i])
             det = tuple(t.detach() for t in state)
             vdet = tuple(t.detach() for t in view)
             out_bufs = None if need_grad else (nxt.feats, nxt.coords, nxt.dens, nxt.wemb, nxt.ext, nxt.depth)
@@ -498,17 +591,17 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
             gru_out = None
             if M > 0 and train_tc:
                 # training: tensor-core forward, hand-derived backward (glue kernels + GEMMs), see _GruTrain
-                gru_out = _gru_train(gru, gru_tc, M, pair_j, pair_p, state, feats[i], dens[i], wemb[i])
+                gru_out = _gru_train(gru, gru_tc, M, pair_j, pair_p, state, fv[i], dv[i], wv[i])
             elif M > 0 and use_tc:
-                gru_out = gru_tc(M, pair_j, pair_p, det, feats[i], dens[i], wemb[i], stream)
+                gru_out = gru_tc(M, pair_j, pair_p, det, fv[i], dv[i], wv[i], stream)
             elif M > 0 and fused_gru:
-                gru_out = _gru_fused(gru, M, F, pair_j, pair_p, det, feats[i], dens[i], wemb[i], stream)
+                gru_out = _gru_fused(gru, M, F, pair_j, pair_p, det, fv[i], dv[i], wv[i], stream)
             elif M > 0:
                 pj, pp = pair_j[:M].long(), pair_p[:M].long()
                 hidden = state[0][pj]                      # global latent   (networks.py:201 `hidden_feat`)
-                inp = feats[i][pp]                         # view-i latent   (`input_feat`)
-                e_in = positional_encoding(torch.stack([state[2][pj], wemb[i][pp]], -1), 6)
-                e_h = positional_encoding(torch.stack([dens[i][pp], state[3][pj]], -1), 6)
+                inp = fv[i][pp]                         # view-i latent   (`input_feat`)
+                e_in = positional_encoding(torch.stack([state[2][pj], wv[i][pp]], -1), 6)
+                e_h = positional_encoding(torch.stack([dv[i][pp], state[3][pj]], -1), 6)
                 gru_out = gru(inp[None, :, None, :], hidden[None, :, None, :], e_in[None, :, None, :],
                               e_h[None, :, None, :])[0, :, 0, :].float().contiguous()
             if timings is not None:
@@ -518,8 +611,8 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
                                   append=append.clone(), zbuf=zbuf.clone(), counts=c))
             if need_grad:
                 meta = (h, w, depth_thres, cin, ext16[i], E_inv[i], K_px[i], scratch, counts[i], c)
-                state = _PtfMerge.apply(state[0][:N], state[1][:N], state[2][:N], state[3][:N], state[4][:N], state[5][:N],
-                                        feats[i], coords[i], dens[i], wemb[i], depths[i], gru_out, meta)
+                state = _PtfMerge.apply(*(t_ if t_.shape[0] == N else t_[:N] for t_ in state),
+                                        fv[i], xv[i], dv[i], wv[i], zv[i], gru_out, meta)
             else:
                 a.gru_out = ptr(gru_out)
                 check(L.fs_ptf_merge(C.byref(a), C.c_void_p(stream)), "fs_ptf_merge")
@@ -530,9 +623,10 @@ def fuse_views(gru, feats, coords, dens, wemb, depths, extrinsics, intrinsics, i
                 timings.append(dict(step=i, N_in=c[0], matched=M, N_out=N_out, match_ms=ev[0].elapsed_time(ev[1]),
                                     gru_ms=ev[1].elapsed_time(ev[2]), merge_ms=ev[2].elapsed_time(ev[3])))
             N = N_out
-    out = (state[0][:N], state[1][:N], state[4][:N].reshape(N, 4, 4), state[5][:N])
+    cut = lambda t_: t_ if t_.shape[0] == N else t_[:N]           # no SliceBackward (zeros + copy) when nothing is cut
+    out = (cut(state[0]), cut(state[1]), cut(state[4]).reshape(N, 4, 4), cut(state[5]))
     if return_debug:
-        return out, debug, (state[2][:N], state[3][:N])
+        return out, debug, (cut(state[2]), cut(state[3]))
     return out
 
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FS_ABI_VERSION 2
+#define FS_ABI_VERSION 3
 #define FS_TILE 16            /* BLOCK_X == BLOCK_Y == 16 (upstream config.h) */
 #define FS_VIEW_FLOATS 48     /* floats per FsView record                     */
 #define FS_REC_FLOATS 12      /* floats per projected-Gaussian record         */
@@ -316,9 +316,39 @@ typedef struct FsPtfGruArgs {
   unsigned char* wscratch;
   float* out;                                                         /* [M,64]        */
   const int32_t* M_dev;           /* optional: the pair count on the DEVICE (fs_ptf_match's counts_out[2]): no host read   */
+  float* save;                    /* optional (training; M must then be exact): six [M,64] matrices [Hr | Hz | r_lin | z_lin | Hn |
+                                     q_lin], the post-ReLU hidden layers and pre-gate outputs fs_ptf_gru_backward consumes        */
 } FsPtfGruArgs;
 int fs_ptf_gru(const FsPtfGruArgs* args, void* stream);
 int64_t fs_ptf_gru_wscratch_bytes(void);
+
+/* The matrix products of the GRU's backward pass (training; the reference: autograd through networks.py:201-214 inside the fold
+ * of encoder_freesplat.py:485-506) on the tensor cores, 3xTF32 like fs_ptf_gru.  Everything element-wise around them is
+ * fs_ptf_gru_{inputs,update,output_backward,update_backward,inputs_backward}.
+ *
+ * fs_ptf_gru_bwd_data:    C[M,N] (op)= A[M,64] . W[64,N]   (W = an nn.Linear weight [out = 64, in = N], row-major, ld = N)
+ *   mode 0: C = P;   mode 1 (N == 64): C = P where mask > 0, else 0 (mask [M,64] = the post-ReLU activation of the layer below);
+ *   mode 2: C += P (16-byte reductions; C must not be written by anything else meanwhile).
+ *   N % 4 == 0, N <= 192; lda, ldc, ldm % 4 == 0 (16-byte aligned rows).                                                 */
+typedef struct FsGruBwdDataArgs {
+  int32_t M, N, mode;
+  int32_t lda, ldc, ldm;
+  const float* A; const float* W; const float* mask;
+  float* C;
+} FsGruBwdDataArgs;
+int fs_ptf_gru_bwd_data(const FsGruBwdDataArgs* args, void* stream);
+/* fs_ptf_gru_bwd_weights: G[128,ldg] = [Y0 | Y1]^T . [X0 | X1 | 1]  summed over the M pairs (G is overwritten).
+ *   Y0, Y1: [M,64] output gradients (Y1 may be NULL: rows 64..127 of G stay zero); X0 [M,nx0], X1 [M,nx1] (may be NULL) the
+ *   layer inputs (nx0 + nx1 <= 224); column nx0 + nx1 of G is the sum of the Y rows (the bias gradients).  ldg % 16 == 0,
+ *   nx0 + nx1 < ldg <= 256.
+ *   Weight gradients of two layers come out of one call as the blocks G[0:64, 0:nx0] and G[64:128, nx0:nx0+nx1] (or both row
+ *   blocks against X0 when the layers share their input).  Summation order over CTAs is not fixed (fp32 atomics).           */
+typedef struct FsGruBwdWeightsArgs {
+  int32_t M, ldy0, ldy1, ldx0, nx0, ldx1, nx1, ldg;
+  const float* Y0; const float* Y1; const float* X0; const float* X1;
+  float* G;
+} FsGruBwdWeightsArgs;
+int fs_ptf_gru_bwd_weights(const FsGruBwdWeightsArgs* args, void* stream);
 
 /* ------------------------------------------------------------ Gaussian head */
 /* GaussianAdapter.forward(fusion=False, coords=...) (gaussian_adapter.py:136-200) as one kernel.               */
@@ -446,7 +476,8 @@ int fs_graph_destroy(void* graph_exec);
 
 int fs_abi_version(void);
 /* sizeof() of the argument structs as compiled (0: FsRasterFwdArgs, 1: FsRasterBwdArgs, 2: FsCostVolumeArgs, 3: FsPtfArgs,
- * 4: FsPtfGruArgs, 5: FsAdapterArgs, 6: FsDepthHeadArgs, 7: FsBackprojectArgs, 8: FsPlyArgs, 9: FsPtfMergeBwdArgs, 10: FsAdapterBwdArgs, 11: FsDepthHeadBwdArgs; -1 otherwise) so that a foreign-language binding can verify its layout.      */
+ * 4: FsPtfGruArgs, 5: FsAdapterArgs, 6: FsDepthHeadArgs, 7: FsBackprojectArgs, 8: FsPlyArgs, 9: FsPtfMergeBwdArgs, 10: FsAdapterBwdArgs, 11: FsDepthHeadBwdArgs,
+ * 12: FsGruBwdDataArgs, 13: FsGruBwdWeightsArgs; -1 otherwise) so that a foreign-language binding can verify its layout.      */
 int fs_struct_size(int32_t which);
 const char* fs_last_error(void);      /* thread-local, valid until the next call  */
 int fs_device_sm_count(void);         /* negative FsStatus on failure             */

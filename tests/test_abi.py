@@ -45,9 +45,11 @@ def test_struct_sizes_match_ctypes(lib):
     from freesplat_b200.cost_volume import FsCostVolumeArgs
     from freesplat_b200.depth_head import FsDepthHeadArgs
     from freesplat_b200.ply_export import FsPlyArgs
-    from freesplat_b200.ptf import FsPtfArgs, FsPtfGruArgs, FsPtfMergeBwdArgs
+    from freesplat_b200.ptf import FsGruBwdDataArgs, FsGruBwdWeightsArgs, FsPtfArgs, FsPtfGruArgs, FsPtfMergeBwdArgs
     for which, st in enumerate([_lib.FsRasterFwdArgs, _lib.FsRasterBwdArgs, FsCostVolumeArgs, FsPtfArgs, FsPtfGruArgs, FsAdapterArgs,
                                FsDepthHeadArgs, FsBackprojectArgs, FsPlyArgs, FsPtfMergeBwdArgs]):
+        assert lib.fs_struct_size(which) == C.sizeof(st), (which, st.__name__, lib.fs_struct_size(which), C.sizeof(st))
+    for which, st in ((12, FsGruBwdDataArgs), (13, FsGruBwdWeightsArgs)):
         assert lib.fs_struct_size(which) == C.sizeof(st), (which, st.__name__, lib.fs_struct_size(which), C.sizeof(st))
     assert lib.fs_struct_size(99) == -1
 

@@ -257,3 +257,87 @@ def test_pool_fold_is_bit_identical_to_compacting_fold(case, monkeypatch):
     assert outs[0][0].shape == outs[1][0].shape and outs[0][0].shape[0] > args[0].shape[1]
     for a_, b_ in zip(outs[0], outs[1]):
         assert np.array_equal(bits(a_), bits(b_))
+
+
+@pytest.mark.parametrize("M", [1, 127, 128, 1000, 33333])
+def test_gru_backward_data_product(M):
+    """fs_ptf_gru_bwd_data (tcgen05, 3xTF32): C (op)= A[M,64] @ W[64,N] against an fp64 product -- the three epilogues (store,
+    ReLU mask, accumulate), the three widths the GRU uses (64, 152 = not a multiple of 16, 176) and strided operands."""
+    import ctypes as C
+    from freesplat_b200 import _lib, ptf
+    L = _lib.lib()
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(M)
+    st = C.c_void_p(torch.cuda.current_stream(torch.device(dev)).cuda_stream)
+    for N, mode in ((64, 1), (152, 0), (176, 2)):
+        wide = torch.randn(M, 3 * 64, generator=g).to(dev)
+        A = wide[:, 64:128]                                      # ld = 192
+        W = torch.randn(64, N, generator=g).to(dev)
+        mask = (torch.randn(M, N, generator=g) * (torch.rand(M, N, generator=g) > 0.4)).to(dev)
+        out = torch.randn(M, N, generator=g).to(dev)
+        want = A.double() @ W.double()
+        if mode == 1:
+            want = want * (mask > 0)
+        if mode == 2:
+            want = want + out.double()
+        with torch.cuda.device(dev):
+            ptf._bwd_data(L, st, A, W, N, out, mode=mode, mask=mask if mode == 1 else None)
+        torch.cuda.synchronize()
+        err = float((out.double() - want).abs().max()) / max(float(want.abs().max()), 1e-30)
+        assert err < 2e-6, (M, N, mode, err)
+
+
+@pytest.mark.parametrize("M", [1, 31, 32, 33, 5000, 77777])
+def test_gru_backward_weight_product(M):
+    """fs_ptf_gru_bwd_weights: G = [Y0 | Y1]^T @ [X0 | X1 | 1] over the pairs against fp64 -- the three shapes of the GRU backward
+    (two layers with separate inputs, two layers sharing one input, Y1 absent), tails that are not a multiple of the 32-pair step."""
+    import ctypes as C
+    from freesplat_b200 import _lib, ptf
+    L = _lib.lib()
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(1000 + M)
+    st = C.c_void_p(torch.cuda.current_stream(torch.device(dev)).cuda_stream)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev)
+    cases = [(r(M, 64), r(M, 64), r(M, 64), r(M, 152), 224), (r(M, 64), r(M, 64), r(M, 176), None, 192),
+             (r(M, 128)[:, 64:], None, r(M, 64), r(M, 64), 144)]
+    for Y0, Y1, X0, X1, ldg in cases:
+        G = torch.full((128, ldg), float("nan"), device=dev)
+        with torch.cuda.device(dev):
+            ptf._bwd_weights(L, st, Y0, Y1, X0, X1, G)
+        torch.cuda.synchronize()
+        Y = torch.cat([Y0, Y1 if Y1 is not None else torch.zeros_like(Y0)], 1).double()
+        X = torch.cat([X0] + ([X1] if X1 is not None else []) + [torch.ones(M, 1, device=dev)], 1).double()
+        want = Y.t() @ X
+        n = X.shape[1]
+        err = float((G[:, :n].double() - want).abs().max()) / max(float(want.abs().max()), 1e-30)
+        assert err < 5e-6, (M, ldg, err)
+        assert float(G[:, n:].abs().max()) == 0.0 if n < ldg else True
+
+
+def test_gru_backward_tensor_core_path_matches_fp32_gemm_path(monkeypatch):
+    """The training fold's gradients with the tensor-core GRU backward (saved activations, fs_ptf_gru_bwd_data / _weights) against the
+    recompute + fp32 cuBLAS path on the same inputs: every input gradient within 2e-4 of its maximum except ReLU-kink flips (a saved
+    3xTF32 pre-activation and an fp32-recomputed one can land on different sides of 0; counted, <= 1e-3)."""
+    from freesplat_b200 import ptf
+    from tests.helpers import grad_report
+    dev = "cuda:0"
+    feats, coords, dens, wemb, depths, ext, K, hw = flat_inputs(synth.ptf_inputs(3, 3, 96, 128))
+    grads = {}
+    for mode in ("tc", "cublas"):
+        monkeypatch.setattr(ptf, "GRU_BWD", mode)
+        t = lambda a, g=True: torch.from_numpy(np.ascontiguousarray(a)).to(dev).requires_grad_(g)
+        tf, tx, td, tw, tz = t(feats), t(coords), t(dens), t(wemb), t(depths)
+        gru = _gru(3, dev)
+        F_, X_, E_, Z_ = ptf.fuse_views(gru, tf, tx, td, tw, tz, t(ext, False), t(K, False), hw)
+        gen = torch.Generator().manual_seed(5)
+        (F_ * torch.randn(F_.shape, generator=gen).to(dev)).sum().backward()
+        grads[mode] = {"feats": tf.grad, "dens": td.grad, "wemb": tw.grad, **{"gru." + n: p.grad for n, p in gru.named_parameters()}}
+    bad = []
+    for name, got in grads["tc"].items():
+        # parameter gradients are sums over all pairs incl. the flipped ones: same additive 5e-3 of max as the reference-golden test
+        is_param = name.startswith("gru.")
+        rep = grad_report(got.cpu().numpy(), grads["cublas"][name].cpu().numpy(), atol_of_max=5e-3 if is_param else 2e-4,
+                          max_outlier_frac=0.0 if is_param else 1e-3, gross=5e-2)
+        if not rep["ok"]:
+            bad.append((name, rep))
+    assert not bad, bad

@@ -292,7 +292,9 @@ int64_t fs_ptf_gru_wscratch_bytes(void) { return (int64_t)ptf_gru_wscratch_bytes
 
 int fs_ptf_gru_bwd_data(const FsGruBwdDataArgs* a, void* stream) {
   FS_REQUIRE(a != nullptr && a->M >= 0 && a->N >= 4 && a->N <= 192 && a->N % 4 == 0, "bad sizes (N % 4 == 0, 4 <= N <= 192)");
-  FS_REQUIRE(a->mode >= 0 && a->mode <= 2, "mode must be 0 (store), 1 (ReLU mask) or 2 (accumulate)");
+  FS_REQUIRE(a->mode >= 0 && a->mode <= 3, "mode must be 0 (store), 1 (ReLU mask), 2 (accumulate) or 3 (update-gate epilogue)");
+  FS_REQUIRE(a->mode != 3 || (a->N == 152 && a->ldc >= 176 && (a->M == 0 || (a->h && a->r_lin && a->dr_lin && a->ldh >= 64 && a->ldh % 4 == 0))),
+             "mode 3 needs N == 152, ldc >= 176, h / r_lin / dr_lin");
   FS_REQUIRE(a->lda >= 64 && a->lda % 4 == 0 && a->ldc >= a->N && a->ldc % 4 == 0, "bad leading dimensions");
   FS_REQUIRE(a->M == 0 || (a->A && a->W && a->C), "NULL buffer");
   FS_REQUIRE(a->mode != 1 || (a->N == 64 && (a->M == 0 || (a->mask && a->ldm >= 64 && a->ldm % 4 == 0))),

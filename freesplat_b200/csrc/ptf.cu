@@ -972,7 +972,8 @@ __global__ void __launch_bounds__(128 * kT) ptf_gru_tc_kernel(int M_host, const 
                                                          const float* __restrict__ wemb, const float* __restrict__ v_feats,
                                                          const float* __restrict__ v_dens, const float* __restrict__ v_wemb,
                                                          const unsigned char* __restrict__ W, const float* __restrict__ biases /*6 x 64*/,
-                                                         float* __restrict__ out, float* __restrict__ save /*6 x [M_host,64] or NULL*/) {
+                                                         float* __restrict__ out, float* __restrict__ save /*6 x [M_host,64] or NULL*/,
+                                                         float* __restrict__ save_a1 /*[M,176] or NULL*/) {
   extern __shared__ __align__(128) unsigned char gru_smem_raw[];
   Smem<kT>& sm = *reinterpret_cast<Smem<kT>*>(gru_smem_raw);
   constexpr int kNT = 128 * kT;
@@ -1087,6 +1088,7 @@ __global__ void __launch_bounds__(128 * kT) ptf_gru_tc_kernel(int M_host, const 
 #pragma unroll
       for (int e = 0; e < 4; e++) v[e] = a1_col(c + e);
       store_a4(sm.A[tile][buf][0], sm.A[tile][buf][1], row, 4 * q, v[0], v[1], v[2], v[3]);
+      if (save_a1 && active) *reinterpret_cast<float4*>(save_a1 + (size_t)m * kK1 + c) = make_float4(v[0], v[1], v[2], v[3]);
     }
     publish();
     if (tid == 0) {
@@ -1302,13 +1304,13 @@ int launch_ptf_gru_tc(const FsPtfGruArgs& a, cudaStream_t s) {
     if ((rc = check_cuda(cudaFuncSetAttribute(gru::ptf_gru_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                          "cudaFuncSetAttribute(ptf_gru_tc_kernel<2>)"))) return rc;
     gru::ptf_gru_tc_kernel<2><<<(a.M + 255) / 256, 256, smem, s>>>(a.M, a.M_dev, a.pair_j, a.pair_p, a.feats, a.dens, a.wemb, a.v_feats, a.v_dens,
-                                                                    a.v_wemb, a.wscratch, a.biases, a.out, a.save);
+                                                                    a.v_wemb, a.wscratch, a.biases, a.out, a.save, a.save_a1);
   } else {
     const size_t smem = sizeof(gru::Smem<1>) + 128;
     if ((rc = check_cuda(cudaFuncSetAttribute(gru::ptf_gru_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                          "cudaFuncSetAttribute(ptf_gru_tc_kernel<1>)"))) return rc;
     gru::ptf_gru_tc_kernel<1><<<(a.M + 127) / 128, 128, smem, s>>>(a.M, a.M_dev, a.pair_j, a.pair_p, a.feats, a.dens, a.wemb, a.v_feats, a.v_dens,
-                                                                    a.v_wemb, a.wscratch, a.biases, a.out, a.save);
+                                                                    a.v_wemb, a.wscratch, a.biases, a.out, a.save, a.save_a1);
   }
   return check_cuda(cudaGetLastError(), "ptf_gru_tc_kernel");
 }

@@ -79,12 +79,13 @@ class FsPtfGruArgs(C.Structure):
                 ("v_feats", C.c_void_p), ("v_dens", C.c_void_p), ("v_wemb", C.c_void_p),
                 ("W_r0", C.c_void_p), ("W_z0", C.c_void_p), ("W_r2", C.c_void_p), ("W_z2", C.c_void_p), ("W_n0", C.c_void_p),
                 ("W_n2", C.c_void_p), ("biases", C.c_void_p), ("wscratch", C.c_void_p), ("out", C.c_void_p), ("M_dev", C.c_void_p),
-                ("save", C.c_void_p)]
+                ("save", C.c_void_p), ("save_a1", C.c_void_p)]
 
 
 class FsGruBwdDataArgs(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("mode", C.c_int32), ("lda", C.c_int32), ("ldc", C.c_int32), ("ldm", C.c_int32),
-                ("A", C.c_void_p), ("W", C.c_void_p), ("mask", C.c_void_p), ("C", C.c_void_p)]
+                ("A", C.c_void_p), ("W", C.c_void_p), ("mask", C.c_void_p), ("C", C.c_void_p),
+                ("h", C.c_void_p), ("r_lin", C.c_void_p), ("dr_lin", C.c_void_p), ("ldh", C.c_int32), ("reserved", C.c_int32)]
 
 
 class FsGruBwdWeightsArgs(C.Structure):
@@ -125,7 +126,7 @@ class _GruTc:
         self.prepared = False
         self.dev = dev
 
-    def __call__(self, M, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream, out=None, M_dev=None, save=None):
+    def __call__(self, M, pair_j, pair_p, state, view_feats, view_dens, view_wemb, stream, out=None, M_dev=None, save=None, save_a1=None):
         L = _lib.lib()
         Ws = self.Ws
         if out is None:
@@ -133,7 +134,7 @@ class _GruTc:
         a = FsPtfGruArgs(M=M, flags=int(self.prepared), pair_j=ptr(pair_j), pair_p=ptr(pair_p), feats=ptr(state[0]), dens=ptr(state[2]),
                          wemb=ptr(state[3]), v_feats=ptr(view_feats), v_dens=ptr(view_dens), v_wemb=ptr(view_wemb),
                          W_r0=ptr(Ws[0]), W_z0=ptr(Ws[1]), W_r2=ptr(Ws[2]), W_z2=ptr(Ws[3]), W_n0=ptr(Ws[4]), W_n2=ptr(Ws[5]),
-                         biases=ptr(self.biases), wscratch=ptr(self.scratch), out=ptr(out), M_dev=ptr(M_dev), save=ptr(save))
+                         biases=ptr(self.biases), wscratch=ptr(self.scratch), out=ptr(out), M_dev=ptr(M_dev), save=ptr(save), save_a1=ptr(save_a1))
         check(L.fs_ptf_gru(C.byref(a), C.c_void_p(stream)), "fs_ptf_gru")
         self.prepared = True
         return out
@@ -167,10 +168,11 @@ def _gru_fused(gru, M, F, pair_j, pair_p, state, view_feats, view_dens, view_wem
 GRU_BWD = os.environ.get("FREESPLAT_B200_PTF_GRU_BWD", "tc")
 
 
-def _bwd_data(L, st, A, W, N, out, mode=0, mask=None):
-    """out[M,N] (op)= A[M,64] @ W[64,N] on the tensor cores (fs_ptf_gru_bwd_data)."""
+def _bwd_data(L, st, A, W, N, out, mode=0, mask=None, h=None, r_lin=None, dr_lin=None):
+    """out[M,N] (op)= A[M,64] @ W[64,N] on the tensor cores (fs_ptf_gru_bwd_data); mode 3: out = dA1, see the header."""
     a = FsGruBwdDataArgs(M=A.shape[0], N=N, mode=mode, lda=A.stride(0), ldc=out.stride(0), ldm=0 if mask is None else mask.stride(0),
-                         A=ptr(A), W=ptr(W), mask=ptr(mask), C=ptr(out))
+                         A=ptr(A), W=ptr(W), mask=ptr(mask), C=ptr(out), h=ptr(h), r_lin=ptr(r_lin), dr_lin=ptr(dr_lin),
+                         ldh=0 if h is None else h.stride(0))
     check(L.fs_ptf_gru_bwd_data(C.byref(a), st), "fs_ptf_gru_bwd_data")
     return out
 
@@ -204,11 +206,13 @@ class _GruTrain(torch.autograd.Function):
         state = (feats.contiguous(), None, dens.contiguous(), wemb.contiguous())
         ctx.tc = GRU_BWD == "tc"
         acts = torch.empty((6, max(M, 1), 64), dtype=torch.float32, device=dev) if ctx.tc else None
+        a1 = torch.empty((max(M, 1), 2 * 64 + 48), dtype=torch.float32, device=dev) if ctx.tc else None
         with torch.cuda.device(dev):
-            out = gru_tc(M, pair_j, pair_p, state, v_feats.contiguous(), v_dens.contiguous(), v_wemb.contiguous(), stream, save=acts)
+            out = gru_tc(M, pair_j, pair_p, state, v_feats.contiguous(), v_dens.contiguous(), v_wemb.contiguous(), stream, save=acts,
+                         save_a1=a1)
         ctx.M = M
         ctx.sizes = (feats.shape[0], v_feats.shape[0])
-        ctx.acts = acts
+        ctx.acts, ctx.a1 = acts, a1
         ctx.save_for_backward(state[0], state[2], state[3], v_feats, v_dens, v_wemb, pair_j[:M].clone(), pair_p[:M].clone(), *params)
         return out
 
@@ -231,19 +235,15 @@ class _GruTrain(torch.autograd.Function):
         g = g.contiguous()
         K1, K3 = 2 * F + 48, 2 * F + 24
         with torch.cuda.device(dev), torch.no_grad():
-            A1, U = e(M, K1), e(M, K3)
-            check(L.fs_ptf_gru_inputs(C.c_int32(M), C.c_int32(F), vp(pj), vp(pp), vp(feats), vp(dens), vp(wemb), vp(v_feats), vp(v_dens),
-                                      vp(v_wemb), vp(A1), st), "fs_ptf_gru_inputs")
+            A1, U = ctx.a1[:M], e(M, K3)
             check(L.fs_ptf_gru_update(C.c_int32(M), C.c_int32(F), vp(A1), vp(r_lin), vp(U), st), "fs_ptf_gru_update")
             dHn, dHr, dHz = e(M, F), e(M, F), e(M, F)
-            dz_c, dq_c, dA1 = e(M, F), e(M, F), e(M, K1)
+            dz_c, dq_c, dr_c, dA1 = e(M, F), e(M, F), e(M, F), e(M, K1)
             check(L.fs_ptf_gru_output_backward(C.c_int32(M), C.c_int32(F), vp(A1), vp(z_lin), vp(q_lin), vp(g), vp(dz_c), vp(dq_c),
                                                vp(dA1), st), "fs_ptf_gru_output_backward")
             _bwd_data(L, st, dq_c, w(Wn2), F, dHn, mode=1, mask=Hn)
-            dU = _bwd_data(L, st, dHn, w(Wn0), K3, e(M, K3))
-            dr_c = e(M, F)
-            check(L.fs_ptf_gru_update_backward(C.c_int32(M), C.c_int32(F), vp(A1), vp(r_lin), vp(dU), vp(dr_c), vp(dA1), st),
-                  "fs_ptf_gru_update_backward")
+            # dU = dHn @ Wn0 never reaches memory: the update-gate chain rule runs in the product's epilogue (mode 3)
+            _bwd_data(L, st, dHn, w(Wn0), K3, dA1, mode=3, h=A1, r_lin=r_lin, dr_lin=dr_c)
             _bwd_data(L, st, dz_c, w(Wz2), F, dHz, mode=1, mask=Hz)
             _bwd_data(L, st, dr_c, w(Wr2), F, dHr, mode=1, mask=Hr)
             _bwd_data(L, st, dHz, w(Wz0), K1, dA1, mode=2)

@@ -317,7 +317,8 @@ typedef struct FsPtfGruArgs {
   float* out;                                                         /* [M,64]        */
   const int32_t* M_dev;           /* optional: the pair count on the DEVICE (fs_ptf_match's counts_out[2]): no host read   */
   float* save;                    /* optional (training; M must then be exact): six [M,64] matrices [Hr | Hz | r_lin | z_lin | Hn |
-                                     q_lin], the post-ReLU hidden layers and pre-gate outputs fs_ptf_gru_backward consumes        */
+                                     q_lin], the post-ReLU hidden layers and pre-gate outputs the backward consumes            */
+  float* save_a1;                 /* optional (training): the first-layer input [M,176] = [h | e_h | x | e_in]                  */
 } FsPtfGruArgs;
 int fs_ptf_gru(const FsPtfGruArgs* args, void* stream);
 int64_t fs_ptf_gru_wscratch_bytes(void);
@@ -328,13 +329,18 @@ int64_t fs_ptf_gru_wscratch_bytes(void);
  *
  * fs_ptf_gru_bwd_data:    C[M,N] (op)= A[M,64] . W[64,N]   (W = an nn.Linear weight [out = 64, in = N], row-major, ld = N)
  *   mode 0: C = P;   mode 1 (N == 64): C = P where mask > 0, else 0 (mask [M,64] = the post-ReLU activation of the layer below);
- *   mode 2: C += P (16-byte reductions; C must not be written by anything else meanwhile).
- *   N % 4 == 0, N <= 192; lda, ldc, ldm % 4 == 0 (16-byte aligned rows).                                                 */
+ *   mode 2: C += P (16-byte reductions; C must not be written by anything else meanwhile);
+ *   mode 3 (N == 152, the product dU = dHn . W_n0): the update-gate chain rule of U = [sigmoid(r_lin) h | x | e_in] in the
+ *           epilogue instead of a stored dU: dr_lin = P[:, :64] h r (1 - r), C[:, :64] += P[:, :64] r, C[:, 64:88] = 0,
+ *           C[:, 88:176] = P[:, 64:152]  (C = dA1 [M,176], h = the first 64 columns of A1, r = sigmoid(r_lin)).
+ *   N % 4 == 0, N <= 192; lda, ldc, ldm, ldh % 4 == 0 (16-byte aligned rows).                                            */
 typedef struct FsGruBwdDataArgs {
   int32_t M, N, mode;
   int32_t lda, ldc, ldm;
   const float* A; const float* W; const float* mask;
   float* C;
+  const float* h; const float* r_lin; float* dr_lin;      /* mode 3 only: A1 (ldh), r_lin [M,64], dr_lin [M,64] */
+  int32_t ldh, reserved;
 } FsGruBwdDataArgs;
 int fs_ptf_gru_bwd_data(const FsGruBwdDataArgs* args, void* stream);
 /* fs_ptf_gru_bwd_weights: G[128,ldg] = [Y0 | Y1]^T . [X0 | X1 | 1]  summed over the M pairs (G is overwritten).

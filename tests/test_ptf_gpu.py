@@ -341,3 +341,27 @@ def test_gru_backward_tensor_core_path_matches_fp32_gemm_path(monkeypatch):
         if not rep["ok"]:
             bad.append((name, rep))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("M", [1, 129, 20000])
+def test_gru_backward_update_gate_epilogue(M):
+    """fs_ptf_gru_bwd_data mode 3: the product dU = dHn @ W_n0 with the chain rule of U = [sigmoid(r_lin) h | x | e_in] in its
+    epilogue (dr_lin, dA1[:, :64] +=, dA1[:, 64:88] = 0, dA1[:, 88:] = dU[:, 64:]) against the same expressions in fp64."""
+    import ctypes as C
+    from freesplat_b200 import _lib, ptf
+    L = _lib.lib()
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(77 + M)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev)
+    st = C.c_void_p(torch.cuda.current_stream(torch.device(dev)).cuda_stream)
+    dHn, Wn0, A1, r_lin, dA1 = r(M, 64), r(64, 152), r(M, 176), r(M, 64), r(M, 176)
+    dr = torch.full((M, 64), float("nan"), device=dev)
+    dU = dHn.double() @ Wn0.double()
+    rr = torch.sigmoid(r_lin.double())
+    want = torch.cat([dA1[:, :64].double() + dU[:, :64] * rr, torch.zeros(M, 24, device=dev, dtype=torch.float64), dU[:, 64:]], 1)
+    want_dr = dU[:, :64] * A1[:, :64].double() * rr * (1 - rr)
+    with torch.cuda.device(dev):
+        ptf._bwd_data(L, st, dHn, Wn0, 152, dA1, mode=3, h=A1, r_lin=r_lin, dr_lin=dr)
+    torch.cuda.synchronize()
+    for got, ref in ((dA1, want), (dr, want_dr)):
+        assert float((got.double() - ref).abs().max()) / float(ref.abs().max()) < 2e-6

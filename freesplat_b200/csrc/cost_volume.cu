@@ -141,6 +141,53 @@ __device__ __forceinline__ void gather_sources_packed(const float4* __restrict__
   }
 }
 
+// Same loop body as gather_sources_packed for the sources [k0, k1), ACCUMULATING into fsum / dsum / the masks (the caller zeroes
+// them): the software-pipelined forward kernel gathers one plane in two instalments, underneath the two MMA round trips of the
+// previous plane.  Sources are still visited in ascending k, so the sums are bit-identical to the one-call version.
+__device__ __forceinline__ void gather_accum_packed(const float4* __restrict__ srcp_b, const float* __restrict__ proj, int k0, int k1, int H,
+                                                    int W, size_t HW, float X0, float X1, float X2, float uvx, float uvy,
+                                                    const float (&cur)[kCvC], unsigned use_mask, float (&fsum)[kCvC], float& dsum,
+                                                    unsigned& geo_mask, unsigned& zero_mask) {
+  for (int k = k0; k < k1; k++) {
+    if (!((use_mask >> k) & 1u)) continue;
+    Taps t;
+    if (!make_taps(proj + 12 * k, X0, X1, X2, H, W, uvx, uvy, t)) continue;
+    geo_mask |= 1u << k;
+    const float4* __restrict__ s = srcp_b + (size_t)k * (kCvC / 4) * HW;
+    float dot = 0.f;
+#pragma unroll
+    for (int g = 0; g < kCvC / 4; g++) {
+      const float4* __restrict__ sg = s + (size_t)g * HW;
+      const float4 a = __ldg(sg + t.o00), b = __ldg(sg + t.o01), c = __ldg(sg + t.o10), d = __ldg(sg + t.o11);
+      const float w0 = fmaf(t.w11, d.x, fmaf(t.w10, c.x, fmaf(t.w01, b.x, t.w00 * a.x)));
+      const float w1 = fmaf(t.w11, d.y, fmaf(t.w10, c.y, fmaf(t.w01, b.y, t.w00 * a.y)));
+      const float w2 = fmaf(t.w11, d.z, fmaf(t.w10, c.z, fmaf(t.w01, b.z, t.w00 * a.z)));
+      const float w3 = fmaf(t.w11, d.w, fmaf(t.w10, c.w, fmaf(t.w01, b.w, t.w00 * a.w)));
+      dot = fmaf(w0, cur[4 * g], dot); dot = fmaf(w1, cur[4 * g + 1], dot);
+      dot = fmaf(w2, cur[4 * g + 2], dot); dot = fmaf(w3, cur[4 * g + 3], dot);
+      fsum[4 * g] += w0; fsum[4 * g + 1] += w1; fsum[4 * g + 2] += w2; fsum[4 * g + 3] += w3;
+    }
+    if (dot == 0.f) zero_mask |= 1u << k;
+    dsum += dot;
+  }
+}
+
+// L1 prefetch (CCTL.PF1) of the two tap rows of every channel group of the sources in [k0, k1) at plane position X: the lanes of a
+// warp cover a contiguous run of texels, so the 32 requests of one instruction fall into ~5 lines.
+__device__ __forceinline__ void prefetch_taps_packed(const float4* __restrict__ srcp_b, const float* __restrict__ proj, int k0, int k1, int H,
+                                                     int W, size_t HW, float X0, float X1, float X2, float uvx, float uvy) {
+  for (int k = k0; k < k1; k++) {
+    Taps t;
+    if (!make_taps(proj + 12 * k, X0, X1, X2, H, W, uvx, uvy, t)) continue;
+    const float4* __restrict__ s = srcp_b + (size_t)k * (kCvC / 4) * HW;
+#pragma unroll
+    for (int g = 0; g < kCvC / 4; g++) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(s + (size_t)g * HW + t.o00));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(s + (size_t)g * HW + t.o11));
+    }
+  }
+}
+
 // CTA -> 32x4 pixel patch (warp = one 32-pixel row segment, the 4 warps = 4 consecutive rows): rows y and y+1 share
 // their bilinear tap rows, which lifts the L1 hit rate of the gather over a 128-pixel run of a single row.
 __device__ __forceinline__ bool patch_pixel(int block, int tid, int H, int W, int& u, int& v) {
@@ -151,7 +198,7 @@ __device__ __forceinline__ bool patch_pixel(int block, int tid, int H, int W, in
 }
 __host__ __device__ inline unsigned patch_blocks(int H, int W) { return (unsigned)(((W + 31) >> 5) * ((H + 3) >> 2)); }
 
-__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
+__device__ __forceinline__ float leaky(float x) { return fmaxf(x, 0.01f * x); }   // == (x > 0 ? x : 0.01 x) for every x, one instruction less
 
 __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_kernel(FsCostVolumeArgs a, int planes_per_block) {
   __shared__ CvSmem sm;
@@ -337,6 +384,13 @@ __device__ __forceinline__ void split_store4(unsigned char* hi, unsigned char* l
   *reinterpret_cast<uint4*>(lo + off) = l;
 }
 
+// MODE 0: gather -> layer 1 -> layer 2 strictly in sequence per plane (round 1).
+// MODE 1: software-pipelined over the planes: the gather of plane d+1 is issued in two instalments (sources [0, K/2) and
+//         [K/2, K)) right behind the tcgen05.commit of layer 1 resp. layer 2 of plane d, so the two MMA -> TMEM -> register round
+//         trips of a CTA are covered by its own loads instead of only by the other CTA of the SM.  Same arithmetic in the same
+//         order: bit-identical output.
+// MODE 2: MODE 1 + L1 prefetch of plane d+2's tap lines.
+template <int MODE>
 __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_tc_kernel(FsCostVolumeArgs a, int planes_per_block) {
   extern __shared__ __align__(128) unsigned char tc_smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(tc_smem_raw);
@@ -347,19 +401,28 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_tc_kernel(FsCostVo
   // ---- one-time setup: weights as tf32 hi/lo B tiles, biases, projections, mbarrier, TMEM ----
   {
     const float* w0 = a.mlp;                                // [32][49]
-    for (int e = tid; e < kCvHid * kK1; e += kCvThreads) {
-      const int n = e / kK1, k = e - n * kK1;
-      const float v = k < kCvIn ? w0[n * kCvIn + k] : 0.f;
-      const uint32_t hi = to_tf32(v), lo = to_tf32(v - __uint_as_float(hi));
+    const float* pb0 = w0 + kCvHid * kCvIn;
+    const float* w1 = pb0 + kCvHid;                         // [32][32]
+    // every load of the thread is issued before the first split / store (one exposed L2 round trip instead of 22)
+    float v0[kCvHid * kK1 / kCvThreads], v1[kCvHid * kCvHid / kCvThreads];
+#pragma unroll
+    for (int q = 0; q < kCvHid * kK1 / kCvThreads; q++) {
+      const int e = tid + q * kCvThreads, n = e / kK1, k = e - n * kK1;
+      v0[q] = k < kCvIn ? __ldg(w0 + n * kCvIn + k) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < kCvHid * kCvHid / kCvThreads; q++) v1[q] = __ldg(w1 + tid + q * kCvThreads);
+#pragma unroll
+    for (int q = 0; q < kCvHid * kK1 / kCvThreads; q++) {
+      const int e = tid + q * kCvThreads, n = e / kK1, k = e - n * kK1;
+      const uint32_t hi = to_tf32(v0[q]), lo = to_tf32(v0[q] - __uint_as_float(hi));
       const uint32_t off = op_off(n, k, kBBytesPerStep);
       *reinterpret_cast<uint32_t*>(sm.B0_hi + off) = hi; *reinterpret_cast<uint32_t*>(sm.B0_lo + off) = lo;
     }
-    const float* pb0 = w0 + kCvHid * kCvIn;
-    const float* w1 = pb0 + kCvHid;                         // [32][32]
-    for (int e = tid; e < kCvHid * kCvHid; e += kCvThreads) {
-      const int n = e / kCvHid, k = e - n * kCvHid;
-      const float v = w1[e];
-      const uint32_t hi = to_tf32(v), lo = to_tf32(v - __uint_as_float(hi));
+#pragma unroll
+    for (int q = 0; q < kCvHid * kCvHid / kCvThreads; q++) {
+      const int e = tid + q * kCvThreads, n = e / kCvHid, k = e - n * kCvHid;
+      const uint32_t hi = to_tf32(v1[q]), lo = to_tf32(v1[q] - __uint_as_float(hi));
       const uint32_t off = op_off(n, k, kBBytesPerStep);
       *reinterpret_cast<uint32_t*>(sm.B1_hi + off) = hi; *reinterpret_cast<uint32_t*>(sm.B1_lo + off) = lo;
     }
@@ -410,6 +473,7 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_tc_kernel(FsCostVo
   const int d0 = blockIdx.y * planes_per_block, d1 = min(a.D, d0 + planes_per_block);
   const uint32_t my_off = (uint32_t)((tid >> 3) * 256 + (tid & 7) * 16);   // row part of op_off
 
+  if constexpr (MODE == 0) {
   for (int d = d0; d < d1; d++) {
     const float zd = __ldg(a.planes + d);
     const float X0 = zd * r0, X1 = zd * r1, X2 = zd * r2;
@@ -484,6 +548,116 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_fwd_tc_kernel(FsCostVo
       if (active) a.out[((size_t)b * a.D + d) * HW + p] = y;
     }
   }
+  } else {
+  // ---------------------------------------------------------------- software-pipelined plane loop
+  float x[kCvC];
+  float dsum = 0.f, rn = 0.f;
+  unsigned geo = 0u, zero = 0u;
+  const int Ka = (K + 1) >> 1;
+  // exact `dot != 0` rule + 1 / n for the plane whose sums are in x / dsum
+  auto finalize = [&](float X0, float X1, float X2) {
+    const unsigned valid = geo & ~zero;
+    if (zero) {
+#pragma unroll
+      for (int c = 0; c < kCvC; c++) x[c] = 0.f;
+      float ds2 = 0.f; unsigned g2 = 0u, z2 = 0u;
+      gather_accum_packed(src_b, sm.proj, 0, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, valid, x, ds2, g2, z2);
+    }
+    rn = 1.0f / ((float)__popc(valid) + 1e-8f);
+  };
+  if (d0 < d1) {                                             // prologue: the first plane, gathered in one go
+    const float zd = __ldg(a.planes + d0);
+    const float X0 = zd * r0, X1 = zd * r1, X2 = zd * r2;
+#pragma unroll
+    for (int c = 0; c < kCvC; c++) x[c] = 0.f;
+    gather_accum_packed(src_b, sm.proj, 0, K, H, W, HW, X0, X1, X2, uvx, uvy, cur, all, x, dsum, geo, zero);
+    finalize(X0, X1, X2);
+  }
+  for (int d = d0; d < d1; d++) {
+    // ---- A operand of layer 1 from the sums of plane d (x is dead afterwards) ----
+#pragma unroll
+    for (int q = 0; q < kCvC / 4; q++) {
+      const uint32_t off = (uint32_t)((q >> 1) * kABytesPerStep + (q & 1) * 128) + my_off;
+      split_store4(sm.A_hi, sm.A_lo, off, x[4 * q] * rn, x[4 * q + 1] * rn, x[4 * q + 2] * rn, x[4 * q + 3] * rn);
+    }
+    split_store4(sm.A_hi, sm.A_lo, (uint32_t)(6 * kABytesPerStep) + my_off, dsum * rn, 0.f, 0.f, 0.f);
+    split_store4(sm.A_hi, sm.A_lo, (uint32_t)(6 * kABytesPerStep + 128) + my_off, 0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int s = 0; s < kSteps1; s++) {
+        const uint64_t dah = make_desc(aA_hi + s * kABytesPerStep), dal = make_desc(aA_lo + s * kABytesPerStep);
+        const uint64_t dbh = make_desc(aB0_hi + s * kBBytesPerStep), dbl = make_desc(aB0_lo + s * kBBytesPerStep);
+        mma_tf32(tmem, dal, dbh, s > 0 ? 1u : 0u);
+        mma_tf32(tmem, dah, dbl, 1u);
+        mma_tf32(tmem, dah, dbh, 1u);
+      }
+      commit(bar);
+    }
+    // ---- first instalment of plane d+1, underneath the layer-1 MMAs ----
+    const bool next = d + 1 < d1;
+    float nX0 = 0.f, nX1 = 0.f, nX2 = 0.f;
+    if (next) {
+      const float zd = __ldg(a.planes + d + 1);
+      nX0 = zd * r0; nX1 = zd * r1; nX2 = zd * r2;
+#pragma unroll
+      for (int c = 0; c < kCvC; c++) x[c] = 0.f;
+      dsum = 0.f; geo = 0u; zero = 0u;
+      gather_accum_packed(src_b, sm.proj, 0, Ka, H, W, HW, nX0, nX1, nX2, uvx, uvy, cur, all, x, dsum, geo, zero);
+    }
+    mbar_wait(bar, phase); phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      float h[kCvHid];
+      tmem_ld32(t_row, h);
+#pragma unroll
+      for (int q = 0; q < kCvHid / 4; q++) {
+        const uint32_t off = (uint32_t)((q >> 1) * kABytesPerStep + (q & 1) * 128) + my_off;
+        split_store4(sm.A_hi, sm.A_lo, off, leaky(h[4 * q] + sm.b0[4 * q]), leaky(h[4 * q + 1] + sm.b0[4 * q + 1]),
+                     leaky(h[4 * q + 2] + sm.b0[4 * q + 2]), leaky(h[4 * q + 3] + sm.b0[4 * q + 3]));
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int s = 0; s < kSteps2; s++) {
+        const uint64_t dah = make_desc(aA_hi + s * kABytesPerStep), dal = make_desc(aA_lo + s * kABytesPerStep);
+        const uint64_t dbh = make_desc(aB1_hi + s * kBBytesPerStep), dbl = make_desc(aB1_lo + s * kBBytesPerStep);
+        mma_tf32(tmem + 32u, dal, dbh, s > 0 ? 1u : 0u);
+        mma_tf32(tmem + 32u, dah, dbl, 1u);
+        mma_tf32(tmem + 32u, dah, dbh, 1u);
+      }
+      commit(bar);
+    }
+    // ---- second instalment of plane d+1, underneath the layer-2 MMAs ----
+    if (next) {
+      gather_accum_packed(src_b, sm.proj, Ka, K, H, W, HW, nX0, nX1, nX2, uvx, uvy, cur, all, x, dsum, geo, zero);
+      finalize(nX0, nX1, nX2);
+      if constexpr (MODE == 2) {
+        if (d + 2 < d1) {
+          const float zd = __ldg(a.planes + d + 2);
+          prefetch_taps_packed(src_b, sm.proj, 0, K, H, W, HW, zd * r0, zd * r1, zd * r2, uvx, uvy);
+        }
+      }
+    }
+    mbar_wait(bar, phase); phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      float h[kCvHid];
+      tmem_ld32(t_row + 32u, h);
+      float y = sm.b2;
+#pragma unroll
+      for (int i = 0; i < kCvHid; i++) y = fmaf(sm.W2[i], leaky(h[i] + sm.b1[i]), y);
+      if (active) a.out[((size_t)b * a.D + d) * HW + p] = y;
+    }
+  }
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u) : "memory");
@@ -509,9 +683,11 @@ int launch_cost_volume_fwd(const FsCostVolumeArgs& a, cudaStream_t s) {
     return check_cuda(cudaGetLastError(), "cost_volume_fwd_kernel");
   }
   const size_t smem = sizeof(tc::Smem) + 128;
-  if (int rc = check_cuda(cudaFuncSetAttribute(tc::cost_volume_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+  // mlp_mode 0 = pipelined (default), 2 = strictly sequential planes (round 1), 3 = pipelined + L1 prefetch
+  auto kern = a.mlp_mode == 2 ? tc::cost_volume_fwd_tc_kernel<0> : (a.mlp_mode == 3 ? tc::cost_volume_fwd_tc_kernel<2> : tc::cost_volume_fwd_tc_kernel<1>);
+  if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                           "cudaFuncSetAttribute(cost_volume_fwd_tc_kernel)")) return rc;
-  tc::cost_volume_fwd_tc_kernel<<<grid, kCvThreads, smem, s>>>(a, ppb);
+  kern<<<grid, kCvThreads, smem, s>>>(a, ppb);
   return check_cuda(cudaGetLastError(), "cost_volume_fwd_tc_kernel");
 }
 
@@ -557,6 +733,16 @@ __global__ void __launch_bounds__(256) cv_unpack_kernel(const float4* __restrict
 // one 16-byte vector reduction (REDG.E.ADD.F32x4): four channels of one tap
 __device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// the same reduction under a predicate instead of a branch (48 per thread and plane in the tensor-core backward)
+__device__ __forceinline__ void red_add_v4_if(bool on, float4* addr, float a, float b, float c, float d) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t"
+      "}\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"((int)on) : "memory");
 }
 
 __device__ __forceinline__ float dleaky(float z) { return z > 0.f ? 1.f : 0.01f; }
@@ -872,16 +1058,29 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(id), "r"(accumulate) : "memory");
 }
-// 3xTF32 product of one k-step: lo*hi + hi*lo + hi*hi
+// Descriptors as (low word, constant high word): the tiles are 1024-byte aligned inside the 227 KB window, so the 14-bit start
+// address field never overflows and the k-step of a tile is a plain add on the low word.  (Building every descriptor from the
+// byte address -- shift, mask, or -- cost ~17 uniform-datapath instructions per MMA: with 96 weight-gradient MMAs per plane the
+// issuing thread arrived ~1.5 us late at the next plane's barrier, ncu r2: 9 % barrier stalls.)
+__device__ __forceinline__ uint32_t dlo_k(uint32_t saddr) { return (saddr >> 4) | ((128u >> 4) << 16); }
+__device__ __forceinline__ uint32_t dlo_mn(uint32_t saddr) { return (saddr >> 4) | ((kGroup >> 4) << 16); }
+constexpr uint32_t kDhiK = (256u >> 4) | (1u << 14);                     // SBO | version 1 (bit 46)
+constexpr uint32_t kDhiMn = (512u >> 4) | (1u << 14) | (1u << 29);       // SBO | version 1 | SWIZZLE_128B_BASE32B (bit 61)
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// 3xTF32 product of one k-step: lo*hi + hi*lo + hi*hi  (b_hi / b_lo: descriptor low words of the k-step)
 __device__ __forceinline__ void mma3_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t id, uint32_t accumulate) {
-  mma_ts(tmem_d, a_lo, desc_k(b_hi), id, accumulate);
-  mma_ts(tmem_d, a_hi, desc_k(b_lo), id, 1u);
-  mma_ts(tmem_d, a_hi, desc_k(b_hi), id, 1u);
+  mma_ts(tmem_d, a_lo, mk_desc(b_hi, kDhiK), id, accumulate);
+  mma_ts(tmem_d, a_hi, mk_desc(b_lo, kDhiK), id, 1u);
+  mma_ts(tmem_d, a_hi, mk_desc(b_hi, kDhiK), id, 1u);
 }
 __device__ __forceinline__ void mma3_mn(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t id, uint32_t accumulate) {
-  mma_ss(tmem_d, desc_mn(a_lo), desc_mn(b_hi), id, accumulate);
-  mma_ss(tmem_d, desc_mn(a_hi), desc_mn(b_lo), id, 1u);
-  mma_ss(tmem_d, desc_mn(a_hi), desc_mn(b_hi), id, 1u);
+  mma_ss(tmem_d, mk_desc(a_lo, kDhiMn), mk_desc(b_hi, kDhiMn), id, accumulate);
+  mma_ss(tmem_d, mk_desc(a_hi, kDhiMn), mk_desc(b_lo, kDhiMn), id, 1u);
+  mma_ss(tmem_d, mk_desc(a_hi, kDhiMn), mk_desc(b_hi, kDhiMn), id, 1u);
 }
 __device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -983,23 +1182,33 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
     const float* w1 = pb0 + kCvHid;                         // [32][32]
     const float* pb1 = w1 + kCvHid * kCvHid;
     const float* w2 = pb1 + kCvHid;
-    for (int e = tid; e < kCvHid * 64; e += kThreads) {     // o = e>>6, i = e&63: columns 0..48 weights, column 49 = b0, rest 0
-      const int o = e >> 6, i = e & 63;
-      const float v = i < kCvIn ? w0[o * kCvIn + i] : (i == kCvIn ? pb0[o] : 0.f);
-      if (i < 56) put_w(sm.W0f_hi, sm.W0f_lo, wk_off(o, i, 32), v);
-      put_w(sm.W0t_hi, sm.W0t_lo, wk_off(i, o, 64), i < kCvIn ? v : 0.f);     // dX needs no bias column
+    // all 12 loads of a thread are issued before the first split / store (the rolled loops waited for one L2 round trip per
+    // iteration: ~10 % of the kernel's stall samples sat in this prologue, ncu r2)
+    float v0[kCvHid * 64 / kThreads], v1[kCvHid * kCvHid / kThreads];
+#pragma unroll
+    for (int q = 0; q < kCvHid * 64 / kThreads; q++) {      // o = e>>6, i = e&63: columns 0..48 weights, column 49 = b0, rest 0
+      const int e = tid + q * kThreads, o = e >> 6, i = e & 63;
+      v0[q] = i < kCvIn ? __ldg(w0 + o * kCvIn + i) : (i == kCvIn ? __ldg(pb0 + o) : 0.f);
     }
-    for (int e = tid; e < kCvHid * kCvHid; e += kThreads) {
-      const int o = e >> 5, i = e & 31;
-      const float v = w1[e];
-      put_w(sm.W1f_hi, sm.W1f_lo, wk_off(o, i, 32), v);
-      put_w(sm.W1t_hi, sm.W1t_lo, wk_off(i, o, 32), v);
+#pragma unroll
+    for (int q = 0; q < kCvHid * kCvHid / kThreads; q++) v1[q] = __ldg(w1 + tid + q * kThreads);
+#pragma unroll
+    for (int q = 0; q < kCvHid * 64 / kThreads; q++) {
+      const int e = tid + q * kThreads, o = e >> 6, i = e & 63;
+      if (i < 56) put_w(sm.W0f_hi, sm.W0f_lo, wk_off(o, i, 32), v0[q]);
+      put_w(sm.W0t_hi, sm.W0t_lo, wk_off(i, o, 64), i < kCvIn ? v0[q] : 0.f);     // dX needs no bias column
+    }
+#pragma unroll
+    for (int q = 0; q < kCvHid * kCvHid / kThreads; q++) {
+      const int e = tid + q * kThreads, o = e >> 5, i = e & 31;
+      put_w(sm.W1f_hi, sm.W1f_lo, wk_off(o, i, 32), v1[q]);
+      put_w(sm.W1t_hi, sm.W1t_lo, wk_off(i, o, 32), v1[q]);
     }
     for (int k = tid; k < kCvHid; k += kThreads) { sm.b1[k] = pb1[k]; sm.W2[k] = w2[k]; }
     for (int k = tid; k < K * 12; k += kThreads) sm.proj[k] = a.proj[(size_t)b * K * 12 + k];
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_chain)) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_dw)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_u32(&sm.bar_dw)) : "memory");   // two issuing threads
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -1017,10 +1226,11 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
     put8(z8, 0u, 0u, false, sm.X_hi, sm.X_lo, r, 56);
   }
   const uint32_t bar_chain = smem_u32(&sm.bar_chain), bar_dw = smem_u32(&sm.bar_dw);
-  const uint32_t aX_hi = smem_u32(sm.X_hi), aX_lo = smem_u32(sm.X_lo), aDZ_hi = smem_u32(sm.dZ_hi), aDZ_lo = smem_u32(sm.dZ_lo);
-  const uint32_t aDZb_hi = smem_u32(sm.dZb_hi), aDZb_lo = smem_u32(sm.dZb_lo);
-  const uint32_t aW0f_hi = smem_u32(sm.W0f_hi), aW0f_lo = smem_u32(sm.W0f_lo), aW1f_hi = smem_u32(sm.W1f_hi), aW1f_lo = smem_u32(sm.W1f_lo);
-  const uint32_t aW1t_hi = smem_u32(sm.W1t_hi), aW1t_lo = smem_u32(sm.W1t_lo), aW0t_hi = smem_u32(sm.W0t_hi), aW0t_lo = smem_u32(sm.W0t_lo);
+  // descriptor low words of the first k-step of every tile (+64 per 1024-byte step, +128 per 2048-byte step)
+  const uint32_t aX_hi = dlo_mn(smem_u32(sm.X_hi)), aX_lo = dlo_mn(smem_u32(sm.X_lo)), aDZ_hi = dlo_mn(smem_u32(sm.dZ_hi)), aDZ_lo = dlo_mn(smem_u32(sm.dZ_lo));
+  const uint32_t aDZb_hi = dlo_mn(smem_u32(sm.dZb_hi)), aDZb_lo = dlo_mn(smem_u32(sm.dZb_lo));
+  const uint32_t aW0f_hi = dlo_k(smem_u32(sm.W0f_hi)), aW0f_lo = dlo_k(smem_u32(sm.W0f_lo)), aW1f_hi = dlo_k(smem_u32(sm.W1f_hi)), aW1f_lo = dlo_k(smem_u32(sm.W1f_lo));
+  const uint32_t aW1t_hi = dlo_k(smem_u32(sm.W1t_hi)), aW1t_lo = dlo_k(smem_u32(sm.W1t_lo)), aW0t_hi = dlo_k(smem_u32(sm.W0t_hi)), aW0t_lo = dlo_k(smem_u32(sm.W0t_lo));
   uint32_t ph_chain = 0, ph_dw = 0;
   constexpr uint32_t kIdK32 = idesc(32, 0, 0), kIdK64 = idesc(64, 0, 0), kIdMN32 = idesc(32, 1, 1);
 
@@ -1091,7 +1301,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < 7; s++)
-        mma3_ts(tmem + kColZ1, tmem + kColXhi + 8u * s, tmem + kColXlo + 8u * s, aW0f_hi + s * 1024, aW0f_lo + s * 1024, kIdK32, s > 0 ? 1u : 0u);
+        mma3_ts(tmem + kColZ1, tmem + kColXhi + 8u * s, tmem + kColXlo + 8u * s, aW0f_hi + s * 64, aW0f_lo + s * 64, kIdK32, s > 0 ? 1u : 0u);
       commit(bar_chain);
     }
     mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u;
@@ -1112,7 +1322,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < 4; s++)
-        mma3_ts(tmem + kColZ2, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW1f_hi + s * 1024, aW1f_lo + s * 1024, kIdK32, s > 0 ? 1u : 0u);
+        mma3_ts(tmem + kColZ2, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW1f_hi + s * 64, aW1f_lo + s * 64, kIdK32, s > 0 ? 1u : 0u);
       commit(bar_chain);
     }
     mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u;
@@ -1139,7 +1349,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < 4; s++)
-        mma3_ts(tmem + kColDA1, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW1t_hi + s * 1024, aW1t_lo + s * 1024, kIdK32, s > 0 ? 1u : 0u);
+        mma3_ts(tmem + kColDA1, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW1t_hi + s * 64, aW1t_lo + s * 64, kIdK32, s > 0 ? 1u : 0u);
       commit(bar_chain);               // (U1 is issued behind the dX product below: the dependent chain never queues behind it)
     }
     mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u;
@@ -1162,16 +1372,21 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < 4; s++)
-        mma3_ts(tmem + kColDX, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW0t_hi + s * 2048, aW0t_lo + s * 2048, kIdK64, s > 0 ? 1u : 0u);
+        mma3_ts(tmem + kColDX, tmem + kColHhi + 8u * s, tmem + kColHlo + 8u * s, aW0t_hi + s * 128, aW0t_lo + s * 128, kIdK64, s > 0 ? 1u : 0u);
       commit(bar_chain);
       // the two weight-gradient products (2 x 48 MMAs) run behind the chain, underneath the scatter of this plane and the gather
-      // of the next one; bar_dw guards the X / A1 / dZ tiles they read (waited in S1 of the next plane)
+      // of the next one; bar_dw (two arrivals) guards the X / A1 / dZ tiles they read (waited in S1 of the next plane).  They are
+      // issued by two threads of different warps (~10 instructions per MMA: one thread issuing all 96 reached the next plane's
+      // barrier ~1.5 us after the other warps).
 #pragma unroll
       for (int s = 0; s < 16; s++)     // k = 8 tile rows per step
-        mma3_mn(tmem + kColU1, aX_hi + s * 1024, aX_lo + s * 1024, aDZ_hi + s * 1024, aDZ_lo + s * 1024, kIdMN32, (first && s == 0) ? 0u : 1u);
+        mma3_mn(tmem + kColU1, aX_hi + s * 64, aX_lo + s * 64, aDZ_hi + s * 64, aDZ_lo + s * 64, kIdMN32, (first && s == 0) ? 0u : 1u);
+      commit(bar_dw);
+    } else if (tid == 128) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < 16; s++)
-        mma3_mn(tmem + kColU0, aX_hi + s * 1024, aX_lo + s * 1024, aDZb_hi + s * 1024, aDZb_lo + s * 1024, kIdMN32, (first && s == 0) ? 0u : 1u);
+        mma3_mn(tmem + kColU0, aX_hi + s * 64, aX_lo + s * 64, aDZb_hi + s * 64, aDZb_lo + s * 64, kIdMN32, (first && s == 0) ? 0u : 1u);
       commit(bar_dw);
     }
     mbar_wait(bar_chain, ph_chain); ph_chain ^= 1u;
@@ -1215,10 +1430,10 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
 #pragma unroll
           for (int e = 0; e < 4; e++) gw[e] = fmaf(dx[4 * q + e], fv, cur[4 * q + e] * gd);
           float4* dg = ds + (size_t)q * HW;
-          if (t.w00 != 0.f) red_add_v4(dg + t.o00, t.w00 * gw[0], t.w00 * gw[1], t.w00 * gw[2], t.w00 * gw[3]);
-          if (t.w01 != 0.f) red_add_v4(dg + t.o01, t.w01 * gw[0], t.w01 * gw[1], t.w01 * gw[2], t.w01 * gw[3]);
-          if (t.w10 != 0.f) red_add_v4(dg + t.o10, t.w10 * gw[0], t.w10 * gw[1], t.w10 * gw[2], t.w10 * gw[3]);
-          if (t.w11 != 0.f) red_add_v4(dg + t.o11, t.w11 * gw[0], t.w11 * gw[1], t.w11 * gw[2], t.w11 * gw[3]);
+          red_add_v4_if(t.w00 != 0.f, dg + t.o00, t.w00 * gw[0], t.w00 * gw[1], t.w00 * gw[2], t.w00 * gw[3]);
+          red_add_v4_if(t.w01 != 0.f, dg + t.o01, t.w01 * gw[0], t.w01 * gw[1], t.w01 * gw[2], t.w01 * gw[3]);
+          red_add_v4_if(t.w10 != 0.f, dg + t.o10, t.w10 * gw[0], t.w10 * gw[1], t.w10 * gw[2], t.w10 * gw[3]);
+          red_add_v4_if(t.w11 != 0.f, dg + t.o11, t.w11 * gw[0], t.w11 * gw[1], t.w11 * gw[2], t.w11 * gw[3]);
         }
       }
     }

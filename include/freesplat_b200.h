@@ -180,8 +180,10 @@ typedef struct FsCostVolumeArgs {
                               (one 16-byte load per tap and 4 channels in the gather)         */
   float* dsrc_packed;      /* backward scratch [B,K,C/4,H*W,4]: dL_dsrc accumulated with 16-byte vector reductions,
                               unpacked to NCHW at the end of the call                           */
-  int32_t mlp_mode;        /* forward: 0 = tcgen05 tensor cores (3xTF32, fp32-accurate), 1 = fp32 CUDA cores
-                              (validation of mode 0)                                         */
+  int32_t mlp_mode;        /* 0 = tcgen05 tensor cores (3xTF32, fp32-accurate; forward software-pipelined over the
+                              planes), 1 = fp32 CUDA cores (validation of mode 0); forward only: 2 = tensor cores with
+                              strictly sequential planes (the round-1 kernel), 3 = mode 0 + L1 prefetch of the next
+                              plane's tap lines (measured slower; kept for the record).  Modes 0/2/3 are bit-identical. */
 } FsCostVolumeArgs;
 
 int fs_cost_volume_forward(const FsCostVolumeArgs* args, void* stream);

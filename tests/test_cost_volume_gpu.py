@@ -98,6 +98,29 @@ def test_backward_vs_reference_golden(path):
         assert _close(got.cpu().numpy(), want) < 2e-4, (name, _close(got.cpu().numpy(), want))
 
 
+@pytest.mark.parametrize("K,D", [(1, 5), (3, 37), (2, 16)])
+def test_pipelined_forward_is_bit_identical_to_sequential(K, D):
+    """mlp_mode 0 (gather of plane d+1 split around the MMA round trips of plane d), 2 (strictly sequential planes) and
+    3 (mode 0 + L1 prefetch) visit the sources in the same order with the same arithmetic: outputs must be equal bit for bit.
+    D = 5 / 37 leave a ragged last plane chunk, K = 1 an empty second instalment, K = 3 an uneven split."""
+    from freesplat_b200 import cost_volume as cvm
+    dev = "cuda:0"
+    V, Hf, Wf = K + 1, 40, 52
+    inp = synth.cost_volume_inputs(11, V, K, 48, Hf, Wf)
+    m = _module(Hf, Wf, D, synth.cost_volume_mlp(11), dev)
+    outs = {}
+    old = cvm.MLP_MODE
+    try:
+        for mode in (0, 2, 3):
+            cvm.MLP_MODE = mode
+            with torch.no_grad():
+                outs[mode] = m(**{k: v.to(dev) for k, v in inp.items()}).cpu()
+    finally:
+        cvm.MLP_MODE = old
+    assert torch.equal(outs[0], outs[2])
+    assert torch.equal(outs[3], outs[2])
+
+
 def test_tensor_core_and_fp32_mlp_agree():
     """mode 0 (tcgen05, 3xTF32 split) vs mode 1 (fp32 CUDA cores) on the same inputs; both vs the oracle."""
     from freesplat_b200 import cost_volume as cvm

@@ -325,6 +325,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
 }
+// One elected lane of a converged warp (elect.sync): inside `if (warp == 0 && elect_one())` ptxas knows that exactly one lane runs,
+// keeps descriptors and addresses in uniform registers and emits 1-2 instructions per tcgen05.mma; under `if (tid == 0)` every MMA
+// was wrapped in an ELECT / R2UR / BRA.U.ANY uniformisation loop plus the descriptor arithmetic: 9-17 instructions per MMA, all on
+// the one warp every other warp of the CTA then waits for at the next barrier (cuobjdump -sass, r2).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(p));
+  return p != 0u;
+}
 __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -998,6 +1007,7 @@ __global__ void __launch_bounds__(kCvThreads) cost_volume_bwd_kernel(FsCostVolum
 namespace tcb {
 
 using tc::commit;
+using tc::elect_one;
 using tc::mbar_wait;
 using tc::smem_u32;
 using tc::to_tf32;
@@ -1297,7 +1307,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       }
     }
     sync_for_mma();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < 7; s++)
@@ -1318,7 +1328,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       }
     }
     sync_for_mma();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < 4; s++)
@@ -1345,7 +1355,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       }
     }
     sync_for_mma();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < 4; s++)
@@ -1368,7 +1378,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       }
     }
     sync_for_mma();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < 4; s++)
@@ -1382,7 +1392,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
       for (int s = 0; s < 16; s++)     // k = 8 tile rows per step
         mma3_mn(tmem + kColU1, aX_hi + s * 64, aX_lo + s * 64, aDZ_hi + s * 64, aDZ_lo + s * 64, kIdMN32, (first && s == 0) ? 0u : 1u);
       commit(bar_dw);
-    } else if (tid == 128) {
+    } else if (warp == 4 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < 16; s++)

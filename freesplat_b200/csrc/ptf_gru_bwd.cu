@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kNT) gru_bwd_data_kernel(int M, int N, const f
     for (int k4 = 0; k4 < kKd / 4; k4++)
       store_a4(a_hi + (k4 >> 2) * bTile(128), a_lo + (k4 >> 2) * bTile(128), tid, (k4 & 3) * 4, av[k4].x, av[k4].y, av[k4].z, av[k4].w);
     publish_operands();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t aH = smem_u32(a_hi), aL = smem_u32(a_lo), bH = smem_u32(b_hi), bL = smem_u32(b_lo);
       const uint32_t id = idesc(Npc);
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kNT) gru_bwd_weights_kernel(int M, const float
     }
     deposit();
     publish_operands();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t aH = smem_u32(a_hi), aL = smem_u32(a_lo), bH = smem_u32(b_hi), bL = smem_u32(b_lo);
       const uint32_t id = idesc(Np);

@@ -28,6 +28,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t d, uint64_t da, uint64_t db, u
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(da),
                "l"(db), "r"(id), "r"(acc) : "memory");
 }
+// One elected lane of a converged warp (elect.sync): inside `if (warp == 0 && elect_one())` ptxas knows that exactly one lane runs,
+// keeps descriptors and addresses in uniform registers and emits 1-2 instructions per tcgen05.mma; under `if (tid == 0)` every MMA
+// was wrapped in an ELECT / R2UR / BRA.U.ANY uniformisation loop plus the descriptor arithmetic: 9-17 instructions per MMA, all on
+// the one warp every other warp of the CTA then waits for at the next barrier (cuobjdump -sass, r2).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(p));
+  return p != 0u;
+}
 __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

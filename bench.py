@@ -442,7 +442,7 @@ def config3_step(dev, gru):
         p_.requires_grad_(False)
     res.update(info)
     res["note"] = ("3 context views (cost volume K=2, D=128), PTF fold, Gaussian head, 4 target views, MSE; every operator of the path "
-                   "forward and backward in libfreesplat_b200.so except the GRU backward (torch autograd through its six nn.Linear); "
+                   "forward and backward in libfreesplat_b200.so (the GRU backward on the tcgen05 data / weight-gradient kernels); "
                    "the fold reads its step counters on the host once per view in training")
     return res
 
@@ -503,6 +503,51 @@ def config5_section(dev, rank, world, steps=3):
             "exchange_bytes_received_per_rank": gather_bytes, "targets_per_rank": len(my_t),
             "note": "exchange overlaps the fold (step i waits for view i only): its exposed time is inside ptf_fold_ms; "
                     "max over ranks, median of %d steps" % steps}
+
+
+def cost_volume_sharded_section(dev, rank, world, steps=3):
+    """SURVEY 8e row 2 at BASELINE config-4/5 size: 10 context views (owned round-robin), ONE all-gather of the stride-4 matching
+    features (3.7 MB per view) and every rank builds the cost volumes (K = 8 nearest sources, D = 128) of ITS reference views
+    (parallel.cost_volume_sharded).  Device-timed, max over ranks; `single_rank_ms` is the same 10 volumes built by one GPU."""
+    import torch
+    import torch.distributed as dist
+    from freesplat_b200 import parallel, synth
+    from freesplat_b200.cost_volume import AVGFeatureVolumeManager
+    V, K, Hf, Wf, D, C = 10, 8, 120, 160, 128, 48
+    inp = synth.cost_volume_inputs(0, V, K, C, Hf, Wf)
+    feats = inp["cur_feats"]                                        # [V,C,Hf,Wf]
+    src_idx = torch.tensor([sorted([j for j in range(V) if j != b], key=lambda j: abs(j - b))[:K] for b in range(V)])
+    ext = synth.camera_path(V, spacing=0.25).to(dev)
+    Kf = synth.intrinsics(V).clone(); Kf[:, 0] *= Wf; Kf[:, 1] *= Hf
+    Kf = Kf.to(dev)
+    m = AVGFeatureVolumeManager(Hf, Wf, num_depth_bins=D, matching_dim_size=C).to(dev)
+    mine = parallel.shard_views(V, rank, world)
+    local = feats[mine].to(dev).contiguous()
+    near, far = inp["min_depth"].to(dev), inp["max_depth"].to(dev)
+    rows = []
+    for it in range(steps + 1):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        dist.barrier()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            ev[0].record()
+            vol, ids = parallel.cost_volume_sharded(m, local, ext, Kf, near, far, src_indices=src_idx)
+            ev[1].record()
+        torch.cuda.synchronize()
+        if it:
+            rows.append(ev[0].elapsed_time(ev[1]))
+    t = torch.tensor([statistics.median(rows)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    single = None
+    if rank == 0:                                                  # the same 10 volumes on one GPU (no exchange)
+        allf = feats.to(dev)
+        with torch.no_grad():
+            single = gpu_ms(lambda: m(cur_feats=allf, src_feats=allf[src_idx.to(dev)], src_extrinsics=inp["src_extrinsics"].to(dev),
+                                      src_poses=inp["src_poses"].to(dev), src_Ks=inp["src_Ks"].to(dev), cur_invK=inp["cur_invK"].to(dev),
+                                      min_depth=near, max_depth=far), n=3, warm=1)
+    return {"workload": f"fvt_10views_K8_D128_{Wf}x{Hf}_context_views_sharded_x{world}", "sharded_ms": float(t[0]),
+            "single_rank_ms": single, "views_per_rank": len(mine), "all_gather_bytes_per_rank": (V - len(mine)) * C * Hf * Wf * 4,
+            "note": "feature all-gather (NCCL) + cost volumes of the rank's own reference views; max over ranks, median of %d" % steps}
 
 
 def run_reference(args):
@@ -684,11 +729,16 @@ def main():
     e2e_all = sorted(float(x) for x in t[2:])
     e2e_ms = e2e_all[1]
     cfg5 = None
+    cvs = None
     if world > 1 and not args.no_ops:
         try:
             cfg5 = config5_section(dev, rank, world)
         except Exception as exc:             # keep the headline line even if the side section fails
             cfg5 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            cvs = cost_volume_sharded_section(dev, rank, world)
+        except Exception as exc:
+            cvs = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank == 0:
         peaks, peak_src = _peaks()
         peak = float(peaks["hbm_gbs"])
@@ -742,7 +792,7 @@ def main():
             except Exception as exc:
                 line["ops"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if cfg5 is not None:
-            line["configs"] = {"config5": cfg5}
+            line["configs"] = {"config5": cfg5, "cost_volume_sharded": cvs}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

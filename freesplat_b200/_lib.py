@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfreesplat_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 vp = C.c_void_p
 
@@ -26,7 +26,7 @@ class FsRasterFwdArgs(C.Structure):
         ("out_color", vp), ("out_depth", vp), ("final_T", vp), ("n_contrib", vp), ("radii", vp),
         ("rec", vp), ("cov3D", vp), ("tiles_touched", vp), ("clamped", vp),
         ("tile_count", vp), ("tile_cursor", vp), ("ranges", vp), ("keybuf", vp),
-        ("point_list", vp), ("status", vp),
+        ("point_list", vp), ("status", vp), ("bins", vp), ("bin_cap", C.c_int32),
     ]
 
 

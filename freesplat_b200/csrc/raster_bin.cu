@@ -34,11 +34,15 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 }
 
 // ---- 3. scatter instances into their tile ranges --------------------------------------------
-__global__ void __launch_bounds__(kThreads) scatter_kernel(FsRasterFwdArgs a, int gx, int gy) {
+// `binned`: the call bins directly in preprocess; this kernel then only runs its body if a bin overflowed (flag word behind the
+// cursors) -- launched with a small grid that strides over the (Gaussian block, view) pairs: the common case exits at once.
+__global__ void __launch_bounds__(kThreads) scatter_kernel(FsRasterFwdArgs a, int gx, int gy, int binned, int nblk_x) {
   if (a.status[2]) return;
-  const int i = blockIdx.x * kThreads + threadIdx.x;
-  const int v = blockIdx.y;
+  if (binned && a.tile_cursor[(size_t)a.V * gx * gy] == 0u) return;
   const int lane = threadIdx.x & 31;
+  for (int blk = blockIdx.x; blk < nblk_x * a.V; blk += gridDim.x) {
+  const int v = blk / nblk_x;
+  const int i = (blk - v * nblk_x) * kThreads + threadIdx.x;
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   unsigned long long key = 0ull;
   if (i < a.P) {
@@ -72,6 +76,7 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(FsRasterFwdArgs a, in
     }
     if (++tx == x1) { tx = x0; ty++; }
   }
+  }
 }
 
 int launch_binning(const FsRasterFwdArgs& a, cudaStream_t s) {
@@ -84,8 +89,11 @@ int launch_binning(const FsRasterFwdArgs& a, cudaStream_t s) {
     if ((rc = check_cuda(cudaGetLastError(), "tile_scan_kernel"))) return rc;
   }
   if (a.P > 0) {
-    dim3 grid((a.P + kThreads - 1) / kThreads, a.V);
-    scatter_kernel<<<grid, kThreads, 0, s>>>(a, gx, gy);
+    const int nblk_x = (a.P + kThreads - 1) / kThreads;
+    const bool binned = use_bins(a);
+    const long long full = (long long)nblk_x * a.V;
+    const unsigned grid = (unsigned)(binned ? (full < 592 ? full : 592) : full);     // fallback path: 4 CTAs per SM, grid-stride
+    scatter_kernel<<<grid, kThreads, 0, s>>>(a, gx, gy, binned ? 1 : 0, nblk_x);
     if ((rc = check_cuda(cudaGetLastError(), "scatter_kernel"))) return rc;
   }
   return FS_OK;

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();                                            // every thread's SH copies have landed
+  const bool binned = use_bins(a);
   for (int v = 0; v < a.V; v++) {
     const size_t vi = (size_t)v * a.P + i;
     const float* __restrict__ view = a.views + (size_t)v * kViewFloats;
@@ -134,12 +135,35 @@ __global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs
       uint32_t* __restrict__ cnt = a.tile_count + (size_t)v * gx * gy;
       const int maxn = __reduce_max_sync(0xffffffffu, my_tiles);
       int tx = rx0, ty = ry0;
-      for (int k = 0; k < maxn; k++) {
-        const bool on = k < my_tiles;
-        const int tile = on ? ty * gx + tx : -1 - (int)(threadIdx.x & 31);
-        const unsigned grp = __match_any_sync(0xffffffffu, tile);
-        if (on && (int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(cnt + tile, (uint32_t)__popc(grp));
-        if (++tx == rx0 + rw) { tx = rx0; ty++; }
+      if (!binned) {
+        for (int k = 0; k < maxn; k++) {
+          const bool on = k < my_tiles;
+          const int tile = on ? ty * gx + tx : -1 - (int)(threadIdx.x & 31);
+          const unsigned grp = __match_any_sync(0xffffffffu, tile);
+          if (on && (int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(cnt + tile, (uint32_t)__popc(grp));
+          if (++tx == rx0 + rw) { tx = rx0; ty++; }
+        }
+      } else {
+        // direct binning: the counting atomic returns the group's first slot in the tile's fixed-capacity bin and every lane of
+        // the group stores its key there (same key as scatter_kernel: depth bits | Gaussian index)
+        const int lane = (int)(threadIdx.x & 31);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(r2.y) << 32) | (unsigned long long)(uint32_t)i;
+        unsigned long long* __restrict__ vb = reinterpret_cast<unsigned long long*>(a.bins) + (size_t)v * gx * gy * (size_t)a.bin_cap;
+        for (int k = 0; k < maxn; k++) {
+          const bool on = k < my_tiles;
+          const int tile = on ? ty * gx + tx : -1 - lane;
+          const unsigned grp = __match_any_sync(0xffffffffu, tile);
+          const int leader = __ffs(grp) - 1;
+          uint32_t base = 0u;
+          if (on && lane == leader) base = atomicAdd(cnt + tile, (uint32_t)__popc(grp));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (on) {
+            const uint32_t slot = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+            if (slot < (uint32_t)a.bin_cap) vb[(size_t)tile * (size_t)a.bin_cap + slot] = key;
+            else a.tile_cursor[(size_t)a.V * gx * gy] = 1u;          // a bin is full: this call falls back to scan + scatter
+          }
+          if (++tx == rx0 + rw) { tx = rx0; ty++; }
+        }
       }
     }
     // records: three 16-byte stores per thread (48-byte stride across the warp; the L2 merges the partial sectors).
@@ -578,7 +602,8 @@ int launch_preprocess(const FsRasterFwdArgs& a, cudaStream_t s) {
   if (fused) {                                       // [counters | cursors | status]: one memset, status[3] = ticket of the fused scan
     if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, (2 * nt + 4) * 4, s), "memset tile counters"))) return rc;
   } else if (a.tile_cursor == a.tile_count + nt) {   // adjacent scratch (the Python wrapper allocates it that way): one memset
-    if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, 2 * nt * 4, s), "memset tile counters"))) return rc;
+    // (+ the bin-overflow flag word behind the cursors when the call bins directly)
+    if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, (2 * nt + (use_bins(a) ? 1 : 0)) * 4, s), "memset tile counters"))) return rc;
   } else {
     if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, nt * 4, s), "memset tile_count"))) return rc;
     if ((rc = check_cuda(cudaMemsetAsync(a.tile_cursor, 0, nt * 4, s), "memset tile_cursor"))) return rc;

@@ -16,6 +16,7 @@
 // exp() is MUFU.EX2 (ex2.approx.ftz) of power*log2(e): |rel err| < 1e-6.
 #include "common.cuh"
 #include "raster_sort.cuh"
+#include "raster_scan.cuh"
 
 namespace fs {
 
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) render_fwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, unsigned long long* keybuf, uint32_t* point_list,
     const float4* __restrict__ rec, const float* __restrict__ views, const uint32_t* __restrict__ status, int P, int H, int W,
     int gx, int ntiles, float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ final_T,
-    uint32_t* __restrict__ n_contrib) {
+    uint32_t* __restrict__ n_contrib, const unsigned long long* __restrict__ bins, int bin_cap, const uint32_t* __restrict__ bin_flag) {
   if (status[2]) return;
   extern __shared__ unsigned long long skeys[];
   RenderSmem& sm = *reinterpret_cast<RenderSmem*>(skeys);
@@ -85,8 +86,10 @@ __global__ void __launch_bounds__(kThreads) render_fwd_kernel(
     const int n = (int)(range.y - range.x);
     if (n > 0) {
       unsigned long long* g = keybuf + range.x;
+      // direct binning: the unsorted keys sit in the tile's bin (unless a bin overflowed and the call fell back to the scatter pass)
+      const unsigned long long* src = (bins != nullptr && *bin_flag == 0u) ? bins + (size_t)t_flat * (size_t)bin_cap : g;
       if (n <= kSortSmemKeys) {
-        for (int k = tid; k < n; k += kThreads) skeys[k] = g[k];
+        for (int k = tid; k < n; k += kThreads) skeys[k] = src[k];
         if (n <= 32) bitonic_sort_fixed<5>(skeys, n, tid);
         else if (n <= 64) bitonic_sort_fixed<6>(skeys, n, tid);
         else if (n <= 128) bitonic_sort_fixed<7>(skeys, n, tid);
@@ -536,10 +539,12 @@ int launch_render_fwd(const FsRasterFwdArgs& a, cudaStream_t s) {
         a.H, a.W, gx, gx * gy, a.out_color, a.out_depth, a.final_T, a.n_contrib);
     return check_cuda(cudaGetLastError(), "render_fwd2_kernel");
   }
+  const bool binned = use_bins(a);
   render_fwd_kernel<<<gx * gy * a.V, kThreads, kSortSmemKeys * 8, s>>>(
       reinterpret_cast<const uint2*>(a.ranges), a.tile_count /* holds the tile order after binning */,
       reinterpret_cast<unsigned long long*>(a.keybuf), a.point_list, reinterpret_cast<const float4*>(a.rec), a.views, a.status, a.P,
-      a.H, a.W, gx, gx * gy, a.out_color, a.out_depth, a.final_T, a.n_contrib);
+      a.H, a.W, gx, gx * gy, a.out_color, a.out_depth, a.final_T, a.n_contrib,
+      binned ? reinterpret_cast<const unsigned long long*>(a.bins) : nullptr, a.bin_cap, a.tile_cursor + (size_t)a.V * gx * gy);
   return check_cuda(cudaGetLastError(), "render_fwd_kernel");
 }
 

@@ -104,4 +104,11 @@ __host__ inline bool scan_fused_into_preprocess(const FsRasterFwdArgs& a) {
   return a.P > 0 && a.status == a.tile_cursor + nt && a.tile_cursor == a.tile_count + nt;
 }
 
+// Direct binning (FsRasterFwdArgs::bins): decided from the arguments alone, so that the three stage launches of one call agree.
+__host__ __device__ inline bool use_bins(const FsRasterFwdArgs& a) {
+  const size_t nt = (size_t)a.V * tiles_x(a.W) * tiles_y(a.H);
+  return a.bins != nullptr && a.bin_cap > 0 && a.bin_cap <= kSortSmemKeys && a.P > 0 && !(a.stages & FS_STAGE_RENDER_PACKED) &&
+         a.tile_cursor == a.tile_count + nt && a.status != a.tile_cursor + nt;
+}
+
 }  // namespace fs

@@ -30,6 +30,9 @@ RENDER_PACKED = os.environ.get("FREESPLAT_B200_RENDER_PACKED", "0") == "1"
 # (preprocess 47 -> 61 us against 9 us saved in the binning stage: a 256-thread CTA scans 3600 counters in ~14 us at the tail of
 # the kernel, the 1024-thread launch in ~6 us + launch latency that the CUDA graph already hides) -> off by default
 FUSED_SCAN = os.environ.get("FREESPLAT_B200_FUSED_SCAN", "0") == "1"
+# direct binning (FsRasterFwdArgs.bins): keys per tile bin; 0 = off (preprocess counts, a separate scatter pass appends the keys).
+# A tile with more instances than this makes the call fall back to the scatter pass on the device: results are identical.
+BIN_CAP = int(os.environ.get("FREESPLAT_B200_BIN_CAP", "2048"))
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -148,7 +151,7 @@ class RasterState:
     """Tensors a forward call leaves behind (saved for backward; the parity comparables)."""
     __slots__ = ("P", "V", "H", "W", "M", "sh_degree", "scale_modifier", "views", "rec", "cov3D", "radii",
                  "clamped", "tiles_touched", "ranges", "point_list", "keybuf", "final_T", "n_contrib", "status",
-                 "capacity", "color", "depth", "sh_layout", "cov_stride", "tile_buf")
+                 "capacity", "color", "depth", "sh_layout", "cov_stride", "tile_buf", "bins", "bin_cap")
 
     def num_rendered(self) -> int:
         s = self.status.cpu()
@@ -194,6 +197,10 @@ def _alloc_state(dev, P, V, H, W, M, sh_degree, scale_modifier, capacity, sh_lay
     st.point_list = e(max(capacity, 1), dtype=torch.int32)
     # FREESPLAT_B200_FUSED_SCAN=0: a separate status buffer -> the stand-alone one-block scan kernel runs (A/B measurements)
     st.status = st.tile_buf[2 * nt:] if FUSED_SCAN else e(4, dtype=torch.int32)
+    # tile bins of the direct-binning path (16 KB per tile at 2048 keys; only the occupied head of a bin is ever touched);
+    # tile_buf[2 nt] is the bin-overflow flag, zeroed with the counters
+    st.bin_cap = BIN_CAP if (0 < BIN_CAP <= 4096 and not FUSED_SCAN and not RENDER_PACKED and nt * BIN_CAP * 8 <= (1 << 30)) else 0
+    st.bins = e(nt * st.bin_cap, dtype=torch.int64) if st.bin_cap else None
     return st
 
 
@@ -209,7 +216,8 @@ def _fwd_args(st: RasterState, means3D, opacities, views, shs, colors_precomp, s
         out_color=ptr(st.color), out_depth=ptr(st.depth), final_T=ptr(st.final_T), n_contrib=ptr(st.n_contrib),
         radii=ptr(st.radii), rec=ptr(st.rec), cov3D=ptr(st.cov3D), tiles_touched=ptr(st.tiles_touched),
         clamped=ptr(st.clamped), tile_count=ptr(tile_count), tile_cursor=ptr(tile_cursor),
-        ranges=ptr(st.ranges), keybuf=ptr(st.keybuf), point_list=ptr(st.point_list), status=ptr(st.status))
+        ranges=ptr(st.ranges), keybuf=ptr(st.keybuf), point_list=ptr(st.point_list), status=ptr(st.status),
+        bins=ptr(st.bins), bin_cap=st.bin_cap)
 
 
 # scratch of inference calls (no autograd graph keeps it alive), reused by the next call with the same shape on the same

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FS_ABI_VERSION 3
+#define FS_ABI_VERSION 4
 #define FS_TILE 16            /* BLOCK_X == BLOCK_Y == 16 (upstream config.h) */
 #define FS_VIEW_FLOATS 48     /* floats per FsView record                     */
 #define FS_REC_FLOATS 12      /* floats per projected-Gaussian record         */
@@ -107,6 +107,15 @@ typedef struct FsRasterFwdArgs {
   uint32_t* status;      /* [4] {R_lo, R_hi, overflow(R>capacity), reserved}.  If tile_count, tile_cursor and status are
                             ONE buffer [counters | cursors | status] the tile scan runs inside the preprocess kernel
                             (its last CTA; status[3] is the ticket): one launch fewer per step                         */
+  uint64_t* bins;        /* optional [V*tiles*bin_cap] scratch (NULL = off): DIRECT BINNING.  preprocess appends every instance key
+                            to the fixed-capacity bin of its tile while it counts (the counting atomic returns the slot), the render
+                            kernel sorts its tile straight out of the bin: the scatter pass (a second walk over all Gaussians with an
+                            atomic round trip per tile) does not run.  If any tile holds more than bin_cap instances, a flag word
+                            (tile_cursor[V*tiles], zeroed with the counters) is raised and the call falls back, on the device and
+                            inside the same launch sequence, to scan + scatter: results are identical either way.  Requires
+                            tile_cursor == tile_count + V*tiles with one spare word behind it, a separate `status`, and
+                            bin_cap <= 4096.                                                                              */
+  int32_t bin_cap;       /* keys per tile bin                                                                             */
 } FsRasterFwdArgs;
 
 #define FS_STAGE_PREPROCESS 1  /* per-Gaussian projection + tile counting            */

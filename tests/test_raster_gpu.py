@@ -70,6 +70,29 @@ def test_packed_two_pixel_render_kernel_is_bit_identical(monkeypatch):
         assert torch.equal(a.point_list[:R], b.point_list[:R]) and torch.equal(a.keybuf[:R], b.keybuf[:R])
 
 
+def test_direct_binning_matches_scatter_path_and_falls_back(monkeypatch):
+    """FsRasterFwdArgs.bins (preprocess appends the instance keys to per-tile bins, no scatter pass) against the counted +
+    scattered path (BIN_CAP = 0): same ranges, sorted keys, lists and images bit for bit.  BIN_CAP = 64 is smaller than the
+    heaviest tile of every scene: the device-side fallback (flag word -> scan + scatter inside the same launch sequence) must
+    give the same result again; the crowded scene also has a tile above the 4096-key shared-memory sort."""
+    from freesplat_b200 import rasterizer
+    for sc in (synth.pixel_aligned_scene(seed=1, h=120, w=160, n_context=2, n_target=3, keep=None),
+               synth.random_scene(seed=4, h=64, w=64, P=30000, sigma_px=(0.5, 2.0)), synth.random_scene(seed=3, h=100, w=77, P=3000)):
+        out = []
+        for cap in (0, 2048, 64):
+            monkeypatch.setattr(rasterizer, "BIN_CAP", cap)
+            st, _ = rc.run_cuda(sc, bg=(0.1, 0.2, 0.3))
+            assert (st.bins is not None) == (cap > 0)
+            R = st.num_rendered()
+            heaviest = int((st.ranges[:, 1] - st.ranges[:, 0]).max())
+            out.append((R, heaviest, st.ranges.clone(), st.point_list[:R].clone(), st.keybuf[:R].clone(), st.color.clone(), st.depth.clone(),
+                        st.final_T.clone(), st.n_contrib.clone()))
+        assert out[0][0] == out[1][0] == out[2][0] > 0 and out[0][1] > 64
+        for other in out[1:]:
+            for a, b in zip(out[0][2:], other[2:]):
+                assert torch.equal(a, b)
+
+
 def test_scan_fused_into_preprocess_is_bit_identical(monkeypatch):
     """[counters | cursors | status] in one buffer -> the tile scan runs in the last preprocess CTA (ticket in status[3]);
     a separate status buffer -> the stand-alone scan kernel.  Same ranges, lists and images; 18 views x 300 tiles covers the

@@ -28,9 +28,13 @@ namespace fs {
 // The scan itself lives in raster_scan.cuh (tile_scan_block<NT>): it is run by the LAST CTA of preprocess_kernel to finish
 // its tile counting (raster_pre.cu: one launch and ~9 us less per step), and by this stand-alone kernel when a call has no
 // Gaussians or runs the binning stage on its own.
+// `bin_flag` (direct binning only): the bin-overflow word of this call; copied to status[3] so that the host, whenever it looks at
+// the status word anyway, learns that this shape keeps falling back and stops asking for bins.
 __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ count, uint32_t* __restrict__ ranges,
-                                                         uint32_t* __restrict__ status, int n, long long capacity) {
+                                                         uint32_t* __restrict__ status, int n, long long capacity,
+                                                         const uint32_t* __restrict__ bin_flag) {
   tile_scan_block<1024>(count, ranges, status, n, capacity);
+  if (threadIdx.x == 0 && bin_flag != nullptr) status[3] = *bin_flag;      // (thread 0 wrote status[0..3] inside the scan)
 }
 
 // ---- 3. scatter instances into their tile ranges --------------------------------------------
@@ -85,7 +89,8 @@ int launch_binning(const FsRasterFwdArgs& a, cudaStream_t s) {
   int rc;
   // the scan normally ran inside preprocess (last CTA); stand-alone only if that stage was not part of this call sequence
   if (!scan_fused_into_preprocess(a)) {
-    tile_scan_kernel<<<1, 1024, 0, s>>>(a.tile_count, a.ranges, a.status, nt, (long long)a.capacity);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(a.tile_count, a.ranges, a.status, nt, (long long)a.capacity,
+                                        use_bins(a) ? a.tile_cursor + nt : nullptr);
     if ((rc = check_cuda(cudaGetLastError(), "tile_scan_kernel"))) return rc;
   }
   if (a.P > 0) {

@@ -32,7 +32,7 @@ RENDER_PACKED = os.environ.get("FREESPLAT_B200_RENDER_PACKED", "0") == "1"
 FUSED_SCAN = os.environ.get("FREESPLAT_B200_FUSED_SCAN", "0") == "1"
 # direct binning (FsRasterFwdArgs.bins): keys per tile bin; 0 = off (preprocess counts, a separate scatter pass appends the keys).
 # A tile with more instances than this makes the call fall back to the scatter pass on the device: results are identical.
-BIN_CAP = int(os.environ.get("FREESPLAT_B200_BIN_CAP", "2048"))
+BIN_CAP = int(os.environ.get("FREESPLAT_B200_BIN_CAP", "4096"))
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -75,6 +75,9 @@ def pack_views(viewmatrix, projmatrix, campos, bg, tanfovx, tanfovy, scene_scale
 # overflow).  A hint that shrank to "what the last scene needed" would make a deferred-check step of a denser scene overflow
 # with nobody looking (every kernel early-returns on the overflow flag, the outputs stay uninitialised).
 _capacity_hint: dict = {}
+# shapes whose tiles overflowed their bins (status[3] of an earlier call): no bins for them any more -- the device-side fallback
+# keeps every call correct, this only stops paying for bins that are not used
+_bins_off: set = set()
 # default overflow check of the public calls: "deferred" = no host sync (the status word is copied to pinned memory behind
 # the kernels and inspected by the NEXT call, which raises and grows the workspace), "sync" = read it before returning.
 DEFAULT_CHECK = os.environ.get("FREESPLAT_B200_CHECK", "deferred")
@@ -95,6 +98,7 @@ def _grow_hint(key, R: int) -> int:
 
 def reset_capacity_hints() -> None:
     _capacity_hint.clear()
+    _bins_off.clear()
 
 
 class _Pending:
@@ -135,6 +139,8 @@ def poll_deferred(block: bool = False) -> None:
             keep.append(p)
             continue
         R = (int(p.host[0]) & 0xFFFFFFFF) | ((int(p.host[1]) & 0xFFFFFFFF) << 32)
+        if int(p.host[3]):
+            _note_bin_fallback(p.key)
         if int(p.host[2]):
             _grow_hint(p.key, R)
             bad = (R, p.capacity)
@@ -145,6 +151,12 @@ def poll_deferred(block: bool = False) -> None:
             f"an earlier rasterizer call (check_overflow='deferred') needed {bad[0]} tile instances but its workspace held "
             f"{bad[1]}: its outputs were invalid.  The workspace has been grown; re-run that step "
             "(or use check_overflow='sync' / FREESPLAT_B200_CHECK=sync).")
+
+
+def _note_bin_fallback(key) -> None:
+    _bins_off.add(key)
+    for ck in [c for c in _scratch_cache if c[0] == key]:
+        del _scratch_cache[ck]
 
 
 class RasterState:
@@ -172,7 +184,7 @@ def _f32c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
 
 
 def _alloc_state(dev, P, V, H, W, M, sh_degree, scale_modifier, capacity, sh_layout, cov_stride, debug_buffers=False,
-                 outputs=True) -> RasterState:
+                 outputs=True, bins_ok=True) -> RasterState:
     """Every buffer one forward call writes (outputs, saved-for-backward state, binning scratch)."""
     gx, gy = (W + 15) // 16, (H + 15) // 16
     nt = V * gx * gy
@@ -199,7 +211,7 @@ def _alloc_state(dev, P, V, H, W, M, sh_degree, scale_modifier, capacity, sh_lay
     st.status = st.tile_buf[2 * nt:] if FUSED_SCAN else e(4, dtype=torch.int32)
     # tile bins of the direct-binning path (16 KB per tile at 2048 keys; only the occupied head of a bin is ever touched);
     # tile_buf[2 nt] is the bin-overflow flag, zeroed with the counters
-    st.bin_cap = BIN_CAP if (0 < BIN_CAP <= 4096 and not FUSED_SCAN and not RENDER_PACKED and nt * BIN_CAP * 8 <= (1 << 30)) else 0
+    st.bin_cap = BIN_CAP if (bins_ok and 0 < BIN_CAP <= 4096 and not FUSED_SCAN and not RENDER_PACKED and nt * BIN_CAP * 8 <= (1 << 30)) else 0
     st.bins = e(nt * st.bin_cap, dtype=torch.int64) if st.bin_cap else None
     return st
 
@@ -265,13 +277,14 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
                     if len(_scratch_cache) >= 8:
                         _scratch_cache.clear()
                     st = _scratch_cache[ck] = _alloc_state(dev, P, V, H, W, M, sh_degree, scale_modifier, capacity, sh_layout,
-                                                           cov_stride, outputs=False)
+                                                           cov_stride, outputs=False, bins_ok=key not in _bins_off)
                 st.sh_degree, st.scale_modifier, st.sh_layout, st.cov_stride = sh_degree, scale_modifier, sh_layout, cov_stride
                 st.color = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev)
                 st.depth = torch.empty((V, H, W), dtype=torch.float32, device=dev)
                 st.radii = torch.empty((V, P), dtype=torch.int32, device=dev)
             else:
-                st = _alloc_state(dev, P, V, H, W, M, sh_degree, scale_modifier, capacity, sh_layout, cov_stride, debug_buffers)
+                st = _alloc_state(dev, P, V, H, W, M, sh_degree, scale_modifier, capacity, sh_layout, cov_stride, debug_buffers,
+                                  bins_ok=key not in _bins_off)
             st.views = views
             a = _fwd_args(st, means3D, opacities, views, shs, colors_precomp, scales, rotations, cov3D_precomp, prefiltered)
             if stage_events is None:
@@ -293,6 +306,8 @@ def raster_forward_raw(means3D, opacities, views, H, W, *, shs=None, colors_prec
                 return st
             s = st.status.cpu()
             R = (int(s[0]) & 0xFFFFFFFF) | ((int(s[1]) & 0xFFFFFFFF) << 32)
+            if int(s[3]) and st.bin_cap:
+                _note_bin_fallback(key)
             if not int(s[2]):
                 return st
             if R > 0xFFFFFFFF:
@@ -359,7 +374,8 @@ class RasterPlan:
         P, V, sh_degree, scale_modifier, sh_layout, cov_stride = self.meta
         self.destroy()
         with torch.cuda.device(self.dev):
-            self.st = _alloc_state(self.dev, P, V, self.H, self.W, self.M, sh_degree, scale_modifier, capacity, sh_layout, cov_stride)
+            self.st = _alloc_state(self.dev, P, V, self.H, self.W, self.M, sh_degree, scale_modifier, capacity, sh_layout, cov_stride,
+                                   bins_ok=self.key not in _bins_off)
             self.st.views = self.views
             m, o, shs, cp, sc, ro, cov = self.inputs
             self.args = _fwd_args(self.st, m, o.reshape(-1), self.views, shs, cp, sc, ro, cov)
@@ -406,6 +422,8 @@ class RasterPlan:
     def check(self):
         """(R, overflowed) of the last run: ONE host read (waits for the stream)."""
         s = self.st.status.cpu()
+        if int(s[3]) and self.st.bin_cap:
+            _note_bin_fallback(self.key)          # the next (re)build of a plan for this shape runs without bins
         return (int(s[0]) & 0xFFFFFFFF) | ((int(s[1]) & 0xFFFFFFFF) << 32), bool(int(s[2]))
 
     def grow(self, R: int):

@@ -104,7 +104,7 @@ typedef struct FsRasterFwdArgs {
   uint64_t* keybuf;      /* [capacity]  (depth_bits<<32 | gaussian) per instance,
                             sorted ascending inside each tile range on return    */
   uint32_t* point_list;  /* [capacity]  Gaussian index per sorted instance       */
-  uint32_t* status;      /* [4] {R_lo, R_hi, overflow(R>capacity), reserved}.  If tile_count, tile_cursor and status are
+  uint32_t* status;      /* [4] {R_lo, R_hi, overflow(R>capacity), bin fallback taken (direct binning; else 0)}.  If tile_count, tile_cursor and status are
                             ONE buffer [counters | cursors | status] the tile scan runs inside the preprocess kernel
                             (its last CTA; status[3] is the ticket): one launch fewer per step                         */
   uint64_t* bins;        /* optional [V*tiles*bin_cap] scratch (NULL = off): DIRECT BINNING.  preprocess appends every instance key

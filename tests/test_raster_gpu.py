@@ -81,13 +81,20 @@ def test_direct_binning_matches_scatter_path_and_falls_back(monkeypatch):
         out = []
         for cap in (0, 2048, 64):
             monkeypatch.setattr(rasterizer, "BIN_CAP", cap)
+            rasterizer.reset_capacity_hints()                  # (forgets that this shape fell back before)
             st, _ = rc.run_cuda(sc, bg=(0.1, 0.2, 0.3))
             assert (st.bins is not None) == (cap > 0)
+            heavy = int((st.ranges[:, 1] - st.ranges[:, 0]).max())
+            assert int(st.status.cpu()[3]) == int(0 < cap < heavy)   # status[3]: the call took the device-side fallback
             R = st.num_rendered()
             heaviest = int((st.ranges[:, 1] - st.ranges[:, 0]).max())
             out.append((R, heaviest, st.ranges.clone(), st.point_list[:R].clone(), st.keybuf[:R].clone(), st.color.clone(), st.depth.clone(),
                         st.final_T.clone(), st.n_contrib.clone()))
         assert out[0][0] == out[1][0] == out[2][0] > 0 and out[0][1] > 64
+        # the host noticed the fallback (sync check): the next state of this shape is built without bins
+        st2, _ = rc.run_cuda(sc, bg=(0.1, 0.2, 0.3))
+        assert st2.bins is None and torch.equal(st2.color, out[0][5])
+        rasterizer.reset_capacity_hints()
         for other in out[1:]:
             for a, b in zip(out[0][2:], other[2:]):
                 assert torch.equal(a, b)

@@ -18,7 +18,8 @@ Works with the NCCL backend on GPUs and with gloo on the CPU (tests/test_paralle
 """
 from __future__ import annotations
 
-from typing import List, Sequence
+import os
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -145,8 +146,10 @@ class ViewExchange:
     (encoder_freesplat.py:443-519), so `ptf.fuse_views(..., view_ready=ready_events)` folds view v while views v+1.. are
     still in flight over NVLink: the exchange costs its first two views, not all ten."""
 
-    def __init__(self, num_views: int, HW: int, F: int, device, group=None, rounds: bool = True):
+    def __init__(self, num_views: int, HW: int, F: int, device, group=None, rounds: Optional[bool] = None):
         self.V, self.HW, self.F, self.dev, self.group = num_views, HW, F, device, group
+        if rounds is None:
+            rounds = os.environ.get("FREESPLAT_B200_EXCHANGE_ROUNDS", "0") == "1"
         self.rounds = rounds      # False: one broadcast per view (measured at 4 / 8 ranks: 7.85 / 8.33 ms for config 5)
         self.block = torch.empty((num_views, HW * (F + 6)), dtype=torch.float32, device=device)
         self.ready_events = [torch.cuda.Event() for _ in range(num_views)]

@@ -149,20 +149,36 @@ __global__ void __launch_bounds__(kThreads, 4) preprocess_kernel(FsRasterFwdArgs
         const int lane = (int)(threadIdx.x & 31);
         const unsigned long long key = ((unsigned long long)__float_as_uint(r2.y) << 32) | (unsigned long long)(uint32_t)i;
         unsigned long long* __restrict__ vb = reinterpret_cast<unsigned long long*>(a.bins) + (size_t)v * gx * gy * (size_t)a.bin_cap;
-        for (int k = 0; k < maxn; k++) {
-          const bool on = k < my_tiles;
-          const int tile = on ? ty * gx + tx : -1 - lane;
-          const unsigned grp = __match_any_sync(0xffffffffu, tile);
-          const int leader = __ffs(grp) - 1;
-          uint32_t base = 0u;
-          if (on && lane == leader) base = atomicAdd(cnt + tile, (uint32_t)__popc(grp));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          if (on) {
-            const uint32_t slot = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-            if (slot < (uint32_t)a.bin_cap) vb[(size_t)tile * (size_t)a.bin_cap + slot] = key;
-            else a.tile_cursor[(size_t)a.V * gx * gy] = 1u;          // a bin is full: this call falls back to scan + scatter
+        // up to four tiles per pass: their slot atomics are in flight together and are consumed afterwards (one L2 round trip per
+        // pass instead of one per tile); passes beyond the warp's maximum are skipped by warp-uniform branches
+        const unsigned lt_mask = (1u << lane) - 1u;
+        const uint32_t cap = (uint32_t)a.bin_cap;
+        for (int k0 = 0; k0 < maxn; k0 += 4) {
+          unsigned grp[4];
+          uint32_t base[4];
+          int tl[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            grp[u] = 0u; base[u] = 0u; tl[u] = -1;
+            if (k0 + u < maxn) {                                     // warp-uniform
+              const bool on = k0 + u < my_tiles;
+              tl[u] = on ? ty * gx + tx : -1 - lane;
+              grp[u] = __match_any_sync(0xffffffffu, tl[u]);
+              if (on && lane == __ffs(grp[u]) - 1) base[u] = atomicAdd(cnt + tl[u], (uint32_t)__popc(grp[u]));
+              if (++tx == rx0 + rw) { tx = rx0; ty++; }
+            }
           }
-          if (++tx == rx0 + rw) { tx = rx0; ty++; }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (k0 + u < maxn) {                                     // warp-uniform
+              const uint32_t b = __shfl_sync(0xffffffffu, base[u], __ffs(grp[u]) - 1);
+              if (tl[u] >= 0) {
+                const uint32_t slot = b + (uint32_t)__popc(grp[u] & lt_mask);
+                if (slot < cap) vb[(size_t)tl[u] * (size_t)cap + slot] = key;
+                else a.tile_cursor[(size_t)a.V * gx * gy] = 1u;      // a bin is full: this call falls back to scan + scatter
+              }
+            }
+          }
         }
       }
     }

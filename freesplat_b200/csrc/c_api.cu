@@ -77,6 +77,7 @@ int fs_raster_forward(const FsRasterFwdArgs* a, void* stream) {
              "NULL buffer");
   FS_REQUIRE(a->P == 0 || (a->means3D && a->opacities), "NULL input");
   FS_REQUIRE(a->capacity == 0 || (a->keybuf && a->point_list), "NULL key buffers");
+  FS_REQUIRE(a->bins == nullptr || (a->bin_cap >= 1 && a->bin_cap <= 4096), "bin_cap must be 1..4096 when bins is given");
   FS_REQUIRE((long long)tiles_x(a->W) * tiles_y(a->H) * a->V < (1ll << 31), "too many tiles");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int rc;

@@ -770,7 +770,7 @@ def main():
                     "protocol": "median of 3 timings of K steps", "ms_per_step_all": [x / args.steps for x in e2e_all],
                     "h2d_gbs_per_rank": h2d_rank / (e2e_ms / args.steps * 1e-3) / 1e9,
                     "d2h_gbs_per_rank": d2h / (e2e_ms / args.steps * 1e-3) / 1e9, "numa": numa},
-            "gpu_launches": launches * args.steps,      # camera records, preprocess, tile scan, scatter, sort+render (graph nodes)
+            "gpu_launches": launches * args.steps,      # camera records, preprocess, tile scan (+ fallback scatter), sort+render (graph nodes)
             "stage_ms": {"preprocess": sum(pre_ms) / len(pre_ms), "binning": sum(bin_ms) / len(bin_ms), "render": rd},
             "roofline": {"kernel": "render_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

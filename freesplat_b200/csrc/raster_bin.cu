@@ -28,25 +28,16 @@ namespace fs {
 // The scan itself lives in raster_scan.cuh (tile_scan_block<NT>): it is run by the LAST CTA of preprocess_kernel to finish
 // its tile counting (raster_pre.cu: one launch and ~9 us less per step), and by this stand-alone kernel when a call has no
 // Gaussians or runs the binning stage on its own.
-// `bin_flag` (direct binning only): the bin-overflow word of this call; copied to status[3] so that the host, whenever it looks at
-// the status word anyway, learns that this shape keeps falling back and stops asking for bins.
 __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ count, uint32_t* __restrict__ ranges,
-                                                         uint32_t* __restrict__ status, int n, long long capacity,
-                                                         const uint32_t* __restrict__ bin_flag) {
+                                                         uint32_t* __restrict__ status, int n, long long capacity) {
   tile_scan_block<1024>(count, ranges, status, n, capacity);
-  if (threadIdx.x == 0 && bin_flag != nullptr) status[3] = *bin_flag;      // (thread 0 wrote status[0..3] inside the scan)
 }
 
 // ---- 3. scatter instances into their tile ranges --------------------------------------------
-// `binned`: the call bins directly in preprocess; this kernel then only runs its body if a bin overflowed (flag word behind the
-// cursors) -- launched with a small grid that strides over the (Gaussian block, view) pairs: the common case exits at once.
-__global__ void __launch_bounds__(kThreads) scatter_kernel(FsRasterFwdArgs a, int gx, int gy, int binned, int nblk_x) {
-  if (a.status[2]) return;
-  if (binned && a.tile_cursor[(size_t)a.V * gx * gy] == 0u) return;
-  const int lane = threadIdx.x & 31;
-  for (int blk = blockIdx.x; blk < nblk_x * a.V; blk += gridDim.x) {
-  const int v = blk / nblk_x;
-  const int i = (blk - v * nblk_x) * kThreads + threadIdx.x;
+// One 256-thread group `t256` handles Gaussians [256 * bx, +256) of view v.
+__device__ __forceinline__ void scatter_group(const FsRasterFwdArgs& a, int gx, int gy, int v, int bx, int t256) {
+  const int lane = t256 & 31;
+  const int i = bx * kThreads + t256;
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   unsigned long long key = 0ull;
   if (i < a.P) {
@@ -75,11 +66,53 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(FsRasterFwdArgs a, in
     if (on && lane == leader) base = atomicAdd(a.tile_cursor + tbase + tile, (uint32_t)__popc(grp));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (on) {
-      const uint32_t start = __ldg(a.ranges + 2 * (tbase + tile));
+      const uint32_t start = __ldcg(a.ranges + 2 * (tbase + tile));
       a.keybuf[start + base + (uint32_t)__popc(grp & ((1u << lane) - 1u))] = key;
     }
     if (++tx == x1) { tx = x0; ty++; }
   }
+}
+
+__global__ void __launch_bounds__(kThreads) scatter_kernel(FsRasterFwdArgs a, int gx, int gy) {
+  if (a.status[2]) return;
+  scatter_group(a, gx, gy, blockIdx.y, blockIdx.x, threadIdx.x);
+}
+
+// Direct binning: ONE launch for the tile scan and the (rare) fallback scatter.  CTA 0 scans; the other CTAs leave at once unless a
+// bin overflowed (flag word behind the cursors), in which case they wait for the scan (ready word next to the flag: the grid is at
+// most one CTA per SM, so CTA 0 is resident and the wait cannot deadlock) and rebuild the compact key ranges, grid-striding over the
+// (view, 256-Gaussian group) pairs.  status[3] reports the fallback to the host.
+__global__ void __launch_bounds__(1024) scan_scatter_kernel(FsRasterFwdArgs a, int gx, int gy, int nblk_x) {
+  const int nt = a.V * gx * gy;
+  uint32_t* flag = a.tile_cursor + nt;                     // [0] a bin overflowed   [1] the scan has finished
+  __shared__ uint32_t s_over;
+  if (blockIdx.x == 0) {
+    tile_scan_block<1024>(a.tile_count, a.ranges, a.status, nt, a.capacity);
+    __syncthreads();                                       // every range / status store of the CTA is issued
+    if (threadIdx.x == 0) {
+      s_over = __ldcg(flag);
+      a.status[3] = s_over;
+      __threadfence();
+      atomicExch(flag + 1, 1u);
+    }
+    __syncthreads();
+    if (s_over == 0u) return;
+  } else {
+    if (threadIdx.x == 0) {
+      s_over = __ldcg(flag);
+      if (s_over) {
+        while (atomicAdd(flag + 1, 0u) == 0u) {}
+        __threadfence();
+      }
+    }
+    __syncthreads();
+    if (s_over == 0u) return;
+  }
+  if (__ldcg(a.status + 2)) return;                        // R exceeds the workspace: the call reports overflow
+  const int groups = nblk_x * a.V;
+  for (int gidx = (int)blockIdx.x * 4 + (int)(threadIdx.x >> 8); gidx < groups; gidx += (int)gridDim.x * 4) {
+    const int v = gidx / nblk_x;
+    scatter_group(a, gx, gy, v, gidx - v * nblk_x, (int)(threadIdx.x & 255));
   }
 }
 
@@ -87,18 +120,22 @@ int launch_binning(const FsRasterFwdArgs& a, cudaStream_t s) {
   const int gx = tiles_x(a.W), gy = tiles_y(a.H);
   const int nt = a.V * gx * gy;
   int rc;
+  if (use_bins(a)) {                                       // (implies a separate status buffer: no fused scan)
+    const int nblk_x = (a.P + kThreads - 1) / kThreads;
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    scan_scatter_kernel<<<sms > 0 ? sms : 1, 1024, 0, s>>>(a, gx, gy, nblk_x);
+    return check_cuda(cudaGetLastError(), "scan_scatter_kernel");
+  }
   // the scan normally ran inside preprocess (last CTA); stand-alone only if that stage was not part of this call sequence
   if (!scan_fused_into_preprocess(a)) {
-    tile_scan_kernel<<<1, 1024, 0, s>>>(a.tile_count, a.ranges, a.status, nt, (long long)a.capacity,
-                                        use_bins(a) ? a.tile_cursor + nt : nullptr);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(a.tile_count, a.ranges, a.status, nt, (long long)a.capacity);
     if ((rc = check_cuda(cudaGetLastError(), "tile_scan_kernel"))) return rc;
   }
   if (a.P > 0) {
-    const int nblk_x = (a.P + kThreads - 1) / kThreads;
-    const bool binned = use_bins(a);
-    const long long full = (long long)nblk_x * a.V;
-    const unsigned grid = (unsigned)(binned ? (full < 592 ? full : 592) : full);     // fallback path: 4 CTAs per SM, grid-stride
-    scatter_kernel<<<grid, kThreads, 0, s>>>(a, gx, gy, binned ? 1 : 0, nblk_x);
+    dim3 grid((a.P + kThreads - 1) / kThreads, a.V);
+    scatter_kernel<<<grid, kThreads, 0, s>>>(a, gx, gy);
     if ((rc = check_cuda(cudaGetLastError(), "scatter_kernel"))) return rc;
   }
   return FS_OK;

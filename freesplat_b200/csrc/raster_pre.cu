@@ -618,8 +618,8 @@ int launch_preprocess(const FsRasterFwdArgs& a, cudaStream_t s) {
   if (fused) {                                       // [counters | cursors | status]: one memset, status[3] = ticket of the fused scan
     if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, (2 * nt + 4) * 4, s), "memset tile counters"))) return rc;
   } else if (a.tile_cursor == a.tile_count + nt) {   // adjacent scratch (the Python wrapper allocates it that way): one memset
-    // (+ the bin-overflow flag word behind the cursors when the call bins directly)
-    if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, (2 * nt + (use_bins(a) ? 1 : 0)) * 4, s), "memset tile counters"))) return rc;
+    // (+ the bin-overflow flag and the scan-ready word behind the cursors when the call bins directly)
+    if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, (2 * nt + (use_bins(a) ? 2 : 0)) * 4, s), "memset tile counters"))) return rc;
   } else {
     if ((rc = check_cuda(cudaMemsetAsync(a.tile_count, 0, nt * 4, s), "memset tile_count"))) return rc;
     if ((rc = check_cuda(cudaMemsetAsync(a.tile_cursor, 0, nt * 4, s), "memset tile_cursor"))) return rc;

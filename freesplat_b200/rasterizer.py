@@ -416,8 +416,9 @@ class RasterPlan:
         return self
 
     def launches_per_run(self) -> int:
-        # preprocess, tile scan (its own launch unless FUSED_SCAN), scatter, sort + render (+ camera records)
-        return (3 if FUSED_SCAN else 4) + int(self.cameras is not None)
+        # preprocess, tile scan (its own launch unless FUSED_SCAN), scatter, sort + render (+ camera records); with direct binning
+        # the scan and the fallback scatter are one launch
+        return (3 if (FUSED_SCAN or self.st.bin_cap) else 4) + int(self.cameras is not None)
 
     def check(self):
         """(R, overflowed) of the last run: ONE host read (waits for the stream)."""

@@ -1414,9 +1414,10 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
 #pragma unroll
       for (int e = 0; e < 8; e++) { dx[e] = __uint_as_float(q0[e]); dx[8 + e] = __uint_as_float(q1[e]); dx[16 + e] = __uint_as_float(q2[e]); }
     }
-    if (active && g != 0.f) {
-      const float dxdot = __uint_as_float(dd);
-      const float gd = dxdot * rn;
+    const bool row_on = active && g != 0.f;
+    const float dxdot = __uint_as_float(dd);
+    const float gd = dxdot * rn;
+    if (row_on) {
       // d dot_k / d cur[c] = w_k[c] and gd is the same for every source: gd * sum_k w_k[c] = dxdot * (x[c] * rn)
       if (valid == geo) {
 #pragma unroll
@@ -1427,24 +1428,47 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_bwd_tc_kernel(FsCostV
 #pragma unroll
         for (int c = 0; c < kHalfC; c++) dcur[c] = fmaf(gd, wsum[c], dcur[c]);
       }
-      // back through the masked means: d(warped_k)[c] = [valid_k] dx[c] / n + [geo_k] cur[c] dxdot / n
-      for (int k = 0; k < K; k++) {
-        if (!((geo >> k) & 1u)) continue;
-        Taps t;
-        make_taps(sm.proj + 12 * k, X0, X1, X2, H, W, uvx, uvy, t);
-        const float fv = ((valid >> k) & 1u) ? rn : 0.f;
-        float4* __restrict__ ds = dsrc_b + ((size_t)k * (kCvC / 4) + g0) * HW;
+    }
+    // back through the masked means: d(warped_k)[c] = [valid_k] dx[c] / n + [geo_k] cur[c] dxdot / n, scattered with 16-byte vector
+    // reductions.  The lanes of a warp are 32 neighbouring pixels of one row: where the sampling step is one texel, lane L's RIGHT
+    // taps are lane L+1's LEFT taps.  Those pairs are merged in registers (shuffle + add) and leave as ONE reduction: the scatter
+    // was 25 % of this kernel's stall samples with 11 GB of reduction traffic into L2 per backward (ncu r2), this halves it.
+    // Every lane runs the loop (the shuffles are warp-wide); lanes without a contribution carry zero weights and offset -1.
+    for (int k = 0; k < K; k++) {
+      const bool on_k = row_on && ((geo >> k) & 1u);
+      if (!__any_sync(0xffffffffu, on_k)) continue;                        // warp-uniform
+      Taps t;
+      if (!(on_k && make_taps(sm.proj + 12 * k, X0, X1, X2, H, W, uvx, uvy, t))) {
+        t.o00 = t.o01 = t.o10 = t.o11 = -1;
+        t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
+      }
+      const int nb00 = __shfl_down_sync(0xffffffffu, t.o00, 1), nb10 = __shfl_down_sync(0xffffffffu, t.o10, 1);
+      const bool send_top = lane < 31 && t.w01 != 0.f && nb00 == t.o01;    // my right taps go to lane + 1 ...
+      const bool send_bot = lane < 31 && t.w11 != 0.f && nb10 == t.o11;
+      const bool recv_top = __shfl_up_sync(0xffffffffu, (int)send_top, 1) != 0 && lane > 0;   // ... and lane - 1's come to me
+      const bool recv_bot = __shfl_up_sync(0xffffffffu, (int)send_bot, 1) != 0 && lane > 0;
+      const float fv = (on_k && ((valid >> k) & 1u)) ? rn : 0.f;
+      const float gk = on_k ? gd : 0.f;
+      float4* __restrict__ ds = dsrc_b + ((size_t)k * (kCvC / 4) + g0) * HW;
 #pragma unroll
-        for (int q = 0; q < kHalfC / 4; q++) {
-          float gw[4];
+      for (int q = 0; q < kHalfC / 4; q++) {
+        float c00[4], c01[4], c10[4], c11[4];
 #pragma unroll
-          for (int e = 0; e < 4; e++) gw[e] = fmaf(dx[4 * q + e], fv, cur[4 * q + e] * gd);
-          float4* dg = ds + (size_t)q * HW;
-          red_add_v4_if(t.w00 != 0.f, dg + t.o00, t.w00 * gw[0], t.w00 * gw[1], t.w00 * gw[2], t.w00 * gw[3]);
-          red_add_v4_if(t.w01 != 0.f, dg + t.o01, t.w01 * gw[0], t.w01 * gw[1], t.w01 * gw[2], t.w01 * gw[3]);
-          red_add_v4_if(t.w10 != 0.f, dg + t.o10, t.w10 * gw[0], t.w10 * gw[1], t.w10 * gw[2], t.w10 * gw[3]);
-          red_add_v4_if(t.w11 != 0.f, dg + t.o11, t.w11 * gw[0], t.w11 * gw[1], t.w11 * gw[2], t.w11 * gw[3]);
+        for (int e = 0; e < 4; e++) {
+          const float gw = fmaf(dx[4 * q + e], fv, cur[4 * q + e] * gk);
+          c00[e] = t.w00 * gw; c01[e] = t.w01 * gw; c10[e] = t.w10 * gw; c11[e] = t.w11 * gw;
         }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float rt = __shfl_up_sync(0xffffffffu, c01[e], 1), rb = __shfl_up_sync(0xffffffffu, c11[e], 1);
+          if (recv_top) c00[e] += rt;
+          if (recv_bot) c10[e] += rb;
+        }
+        float4* dg = ds + (size_t)q * HW;
+        red_add_v4_if(t.w00 != 0.f || recv_top, dg + t.o00, c00[0], c00[1], c00[2], c00[3]);
+        red_add_v4_if(t.w01 != 0.f && !send_top, dg + t.o01, c01[0], c01[1], c01[2], c01[3]);
+        red_add_v4_if(t.w10 != 0.f || recv_bot, dg + t.o10, c10[0], c10[1], c10[2], c10[3]);
+        red_add_v4_if(t.w11 != 0.f && !send_bot, dg + t.o11, c11[0], c11[1], c11[2], c11[3]);
       }
     }
   }
